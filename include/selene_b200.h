@@ -1,0 +1,234 @@
+/* selene_b200 — C ABI of the B200-native (sm_100a) sequence -> prediction hot path of Selene.
+ *
+ * The reference (selene-sdk 0.6.0) has no FFI layer of its own: its only native code is two
+ * Cython modules and its GPU work is whatever torch dispatches.  The entry points below are what
+ * a maintainer would bind (ctypes) to replace, for this path only:
+ *
+ *   sb_encode_* / sb_genome_*   <- selene_sdk/sequences/_sequence.pyx:11-25
+ *                                  (_fast_sequence_to_encoding) reached through
+ *                                  selene_sdk/sequences/genome.py:96-166,436-542
+ *   sb_intervals_* / sb_label_* <- selene_sdk/targets/_genomic_features.pyx:12-41
+ *                                  (_fast_get_feature_data) reached through
+ *                                  selene_sdk/targets/genomic_features.py:104-141,377-418
+ *   sb_ism_*                    <- selene_sdk/predict/_in_silico_mutagenesis.py:8-143 and the batch
+ *                                  assembly loop selene_sdk/predict/model_predict.py:599-660
+ *   sb_snv_*                    <- selene_sdk/predict/_variant_effect_prediction.py:137-245 and the
+ *                                  per-variant loop selene_sdk/predict/model_predict.py:1054-1124
+ *   sb_net_*                    <- selene_sdk/predict/_common.py:65-97 (predict) running
+ *                                  models/deepsea.py:21-58 (and the other conv stacks)
+ *   score outputs of sb_net_*   <- predict_handlers/absolute_diff_score_handler.py:115,
+ *                                  diff_score_handler.py:114, logit_score_handler.py:118-124
+ *
+ * Conventions
+ *   - every function returns SB_OK (0) or an SB_ERR_* code and never throws; sb_last_error()
+ *     returns the message of the calling thread's last failure;
+ *   - "dev" pointers are device memory on the handle's GPU, "host" pointers are ordinary memory;
+ *     the library never frees or retains caller buffers beyond the call (handles copy what they keep);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it asynchronously;
+ *   - handles are thread-compatible (one thread at a time per handle), one per GPU;
+ *   - base codes are canonical: A=0 C=1 G=2 T=3, 4 = unknown (any character outside ACGTacgt).
+ *     `perm[b]` gives the one-hot channel of canonical base b (Genome.BASES_ARR is mutable class
+ *     state in the reference, model_predict.py:176-183, so the order is a parameter, never baked in).
+ *   - there is NO CPU fallback anywhere in this library.
+ */
+#ifndef SELENE_B200_H
+#define SELENE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_OK 0
+#define SB_ERR_ARG 1
+#define SB_ERR_CUDA 2
+#define SB_ERR_UNSUPPORTED 3
+#define SB_ERR_NOMEM 4
+
+#define SB_F32 0
+#define SB_BF16 1
+#define SB_U8 2
+#define SB_I64 3
+#define SB_F64 4
+
+/* flags written per window by the encode entry points */
+#define SB_FLAG_HAS_UPPER_N 1 /* 'N' in sequence  (genome.py:542: uppercase N only)        */
+#define SB_FLAG_HAS_UNK 2     /* any character outside ACGTacgt (rows encoded as 0.25 x 4) */
+
+typedef struct sb_genome sb_genome;
+typedef struct sb_intervals sb_intervals;
+typedef struct sb_net sb_net;
+
+/* ------------------------------------------------------------------------------------------ */
+/* misc                                                                                        */
+/* ------------------------------------------------------------------------------------------ */
+int sb_version(void);
+int sb_last_error(char* buf, int n);
+/* number of kernels this library has launched in this process so far */
+unsigned long long sb_launch_count(void);
+int sb_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------ */
+/* genome image: 2 bits/base + unknown mask + uppercase-N mask, all chromosomes concatenated   */
+/* ------------------------------------------------------------------------------------------ */
+/* host inputs: base i of the image has code (packed2bit[i>>2] >> 2*(i&3)) & 3, unknown bit
+ * (unk_mask[i>>3] >> (i&7)) & 1 and uppercase-N bit upn_mask likewise.  chrom_off[c] is the image
+ * offset (in bases) of chromosome c, chrom_len[c] its length; n_image_bases is the image size. */
+int sb_genome_create(const uint8_t* packed2bit, const uint8_t* unk_mask, const uint8_t* upn_mask,
+                     int64_t n_image_bases, const int64_t* chrom_off, const int64_t* chrom_len,
+                     int n_chrom, int device, sb_genome** out);
+int sb_genome_destroy(sb_genome* g);
+
+/* windows [start, start+L) of chromosome chrom[i]; parts outside [0, chrom_len) read as 'N'
+ * (genome.py:156-166, pad=True).  strand_rc[i] != 0 reverse-complements the in-bounds part only,
+ * leaving the padding where it is — that is what genome.py:164-166 does.  Coordinate validity
+ * (genome.py:51-92) is decided by the host before calling.  All array arguments are dev. */
+int sb_genome_codes(const sb_genome* g, const int32_t* chrom, const int64_t* start,
+                    const uint8_t* strand_rc /* may be NULL */, int n, int L,
+                    uint8_t* codes_out /* (n,L) */, uint8_t* flags_out /* (n) or NULL */,
+                    void* stream);
+
+/* kernel (a): fused 2-bit decode -> one-hot (n, L, 4) of dtype SB_F32 or SB_BF16; unknown rows are
+ * 0.25 x 4 (_sequence.pyx:17,21-24). */
+int sb_encode_windows(const sb_genome* g, const int32_t* chrom, const int64_t* start,
+                      const uint8_t* strand_rc, int n, int L, const uint8_t perm[4], int out_dtype,
+                      void* out, uint8_t* flags_out, void* stream);
+
+/* one-hot of code rows already on the device (sequence_to_encoding of arbitrary strings: the host
+ * maps characters to codes). */
+int sb_encode_codes(const uint8_t* codes /* dev (n,L) */, int64_t n, int L, const uint8_t perm[4],
+                    int out_dtype, void* out /* dev (n,L,4) */, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* in-silico mutagenesis (single-base)                                                         */
+/* ------------------------------------------------------------------------------------------ */
+/* Enumerate the mutations of positions [pos0,pos1): ascending position, alternatives in channel
+ * order (perm) skipping the reference base; an unknown position yields all four
+ * (_in_silico_mutagenesis.py:91-107).  mut_alt holds canonical codes.  n_mut (dev, 1 int) receives
+ * the count; at most `cap` entries are written. */
+int sb_ism_enumerate(const uint8_t* codes /* dev (L) */, int L, int pos0, int pos1,
+                     const uint8_t perm[4], int32_t* mut_pos /* dev */, uint8_t* mut_alt /* dev */,
+                     int32_t* n_mut /* dev */, int cap, void* stream);
+
+/* mutate_sequence (_in_silico_mutagenesis.py:138-143) for a whole batch: row m of `out` is the
+ * one-hot of codes[src[m]] (src NULL: row 0) with position mut_pos[m] replaced by mut_alt[m]. */
+int sb_ism_expand(const uint8_t* codes /* dev (n_src,L) */, int L, const int32_t* src /* dev/NULL */,
+                  const int32_t* mut_pos, const uint8_t* mut_alt, int64_t n_mut,
+                  const uint8_t perm[4], int out_dtype, void* out /* dev (n_mut,L,4) */,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* SNV ref/alt windows (variant effect prediction)                                             */
+/* ------------------------------------------------------------------------------------------ */
+/* For variant i with single-base ref/alt codes: `start[i]` is the 0-based window start the host
+ * derives as model_predict.py:1057-1059 (center - start_radius), `var_row` the row of the variant,
+ * _get_ref_idxs(L,1) (_variant_effect_prediction.py:137-143; 499 for L=1000).  ref_out has the VCF
+ * ref base forced at that row (_handle_standard_ref, :226-245), alt_out the alt base (_process_alt
+ * substitution, :195-200, built from the UNMODIFIED window); ref_match[i] = (genome row == VCF
+ * ref row).  strand_rc applies get_reverse_complement_encoding (_common.py:37-62) to both
+ * (model_predict.py:1102-1110).  ref_out / alt_out / codes_out / ref_match / flags_out may be NULL.
+ * codes_out receives the (n,L) '+'-strand window codes for sb_net_forward_*. */
+int sb_snv_pairs(const sb_genome* g, const int32_t* chrom, const int64_t* start,
+                 const uint8_t* ref_code, const uint8_t* alt_code, const uint8_t* strand_rc, int n,
+                 int L, int var_row, const uint8_t perm[4], int out_dtype, void* ref_out,
+                 void* alt_out, uint8_t* codes_out, uint8_t* ref_match, uint8_t* flags_out,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* kernel (b): interval-overlap labels                                                         */
+/* ------------------------------------------------------------------------------------------ */
+/* host inputs: n intervals (chrom index, start, end, feature index), any order; the handle sorts
+ * them by (feature, chrom, start) and keeps a running max of `end` for exact overlap search. */
+int sb_intervals_create(const int32_t* chrom, const int32_t* start, const int32_t* end,
+                        const int32_t* feat, int64_t n, int n_features, int n_chrom, int device,
+                        sb_intervals** out);
+int sb_intervals_destroy(sb_intervals* iv);
+
+/* labels for n query bins [bin_start, bin_end) on chrom: per feature the UNION coverage of the
+ * clipped intervals (a zero-length clipped interval counts one base, _genomic_features.pyx:32-37)
+ * compared with the integer threshold thr_i[f] (computed by the host exactly as :39-40):
+ * label = coverage > thr_i[f].  thr_i < 0 selects the no-threshold mode of
+ * genomic_features.py:406-415 (any overlapping row).  out (n, n_features) of out_dtype
+ * SB_U8 / SB_F32 / SB_I64 / SB_F64.  Array arguments are dev. */
+int sb_label_bins(const sb_intervals* iv, const int32_t* chrom, const int32_t* bin_start,
+                  const int32_t* bin_end, int n, const int32_t* thr_i /* dev (F) */, int out_dtype,
+                  void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* kernels (c)+(d): conv1d stacks and fused scoring                                            */
+/* ------------------------------------------------------------------------------------------ */
+#define SB_LAYER_CONV 1  /* Conv1d(cin,cout,k) valid, + bias, optional ReLU, optional MaxPool(pool) */
+#define SB_LAYER_FC 2    /* Linear(cin,cout) + bias, optional ReLU                                  */
+
+typedef struct {
+    int32_t type;          /* SB_LAYER_*                                                           */
+    int32_t cin, cout, k;  /* k = 1 for FC                                                          */
+    int32_t relu;          /* apply ReLU after bias                                                 */
+    int32_t pool;          /* MaxPool1d(kernel=stride=pool) after ReLU; 0/1 = none                  */
+    const float* weight;   /* host; torch layout: conv (cout,cin,k), fc (cout,cin)                  */
+    const float* bias;     /* host (cout)                                                           */
+} sb_layer;
+
+/* A network = conv layers on a (B, 4, L) one-hot input, flatten (channel-major, torch .view order:
+ * models/deepsea.py:56), FC layers, final sigmoid.  BatchNorm (eval) must be folded by the host.
+ * perm: channel of canonical base b in the first conv's input. */
+int sb_net_create(const sb_layer* layers, int n_layers, int L, const uint8_t perm[4], int device,
+                  sb_net** out);
+int sb_net_destroy(sb_net* net);
+int sb_net_n_outputs(const sb_net* net);
+/* FLOPs (2 x MACs) of one forward of one sequence */
+double sb_net_flops_per_seq(const sb_net* net);
+
+#define SB_PREC_FP32 0 /* CUDA-core FFMA path, fp32 end to end (<= 1e-5 abs vs torch CPU)          */
+#define SB_PREC_BF16 1 /* tcgen05 path: bf16 operands, fp32 accumulate in TMEM (<= 2e-2 abs)        */
+
+size_t sb_net_workspace_bytes(const sb_net* net, int64_t n_rows, int precision);
+
+/* Input rows are described without materialising them: row i is codes[src[i]] (src NULL: i) with
+ * position sub_pos[i] replaced by canonical code sub_code[i] when sub_pos != NULL and >= 0.
+ * pred (n, F) fp32 receives sigmoid outputs. */
+int sb_net_forward_codes(sb_net* net, const uint8_t* codes /* dev (n_src,L) */,
+                         const int32_t* src, const int32_t* sub_pos, const uint8_t* sub_code,
+                         int64_t n, int precision, void* workspace, size_t workspace_bytes,
+                         float* pred /* dev (n,F) */, void* stream);
+
+/* Generic input: x (n, L, 4) fp32, any values (predict(), _common.py:65-97, after its transpose). */
+int sb_net_forward_onehot(sb_net* net, const float* x, int64_t n, int precision, void* workspace,
+                          size_t workspace_bytes, float* pred, void* stream);
+
+/* Fused scoring epilogue.  Rows as in sb_net_forward_codes.  pair_mode:
+ *   SB_PAIR_INTERLEAVED: n is even, row 2v is the reference and row 2v+1 the alternative of
+ *       variant v; score outputs are (n/2, F).
+ *   SB_PAIR_BASELINE: every row is an alternative; base_pred (dev, (n_base,F) fp32 sigmoid outputs,
+ *       already clamped if logits were requested before — see below) holds baselines and
+ *       base_index[i] (dev, NULL: 0) selects row i's baseline; score outputs are (n, F).
+ * Any output pointer may be NULL.  abs_diff = |ref - alt| , diff = alt - ref, logit =
+ * logit(alt') - logit(ref') with p' = (p==0 ? 1e-24 : p>=1 ? 0.999999 : p) evaluated in fp32 as
+ * log(p/(1-p)) (logit_score_handler.py:118-124).  pred_ref / pred_alt receive the sigmoid outputs;
+ * when `logit` is requested they receive the CLAMPED values, as the reference's in-place clamp
+ * makes later handlers see. */
+#define SB_PAIR_INTERLEAVED 0
+#define SB_PAIR_BASELINE 1
+int sb_net_forward_score(sb_net* net, const uint8_t* codes, const int32_t* src,
+                         const int32_t* sub_pos, const uint8_t* sub_code, int64_t n, int precision,
+                         int pair_mode, const float* base_pred, const int32_t* base_index,
+                         void* workspace, size_t workspace_bytes, float* abs_diff, float* diff,
+                         float* logit, float* pred_ref, float* pred_alt, void* stream);
+
+/* Score two prediction matrices that already exist (handlers called on their own). */
+int sb_score_pairs(const float* ref /* dev (n_ref,F) */, const float* alt /* dev (n,F) */,
+                   const int32_t* base_index /* dev (n) or NULL: ref row i (n_ref==n) or 0 */,
+                   int64_t n, int64_t n_ref, int F, float* abs_diff, float* diff, float* logit,
+                   int clamp_inplace, void* stream);
+
+/* Self-test hook for the tcgen05 GEMM core: C (M,N) fp32 = A (M,K) bf16 . B (N,K)^T bf16, both
+ * K-major, arbitrary M, K % 8 == 0; used by tests to pin descriptor encodings on real hardware. */
+int sb_tc_gemm_selftest(const void* a_bf16, const void* b_bf16, int M, int N, int K, float* c,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SELENE_B200_H */

@@ -1,0 +1,693 @@
+// selene_b200 — kernels (c)+(d), host side: conv1d-stack networks (DeepSEA family) and fused scoring.
+//
+// Reference: selene_sdk/predict/_common.py:65-97 (predict) running models/deepsea.py:21-58 —
+//   conv(4->320,k8)+ReLU+pool4 -> conv(320->480,k8)+ReLU+pool4 -> conv(480->960,k8)+ReLU ->
+//   flatten channel-major (deepsea.py:56) -> FC+ReLU -> FC -> sigmoid; Dropout is identity in eval —
+// and the score handlers predict_handlers/{absolute_diff,diff,logit}_score_handler.py.
+//
+// Data layout in HBM: activations are channel-last, (sequence, position, channel), so that
+//   * the first conv is a table lookup on base codes (one-hot input => each tap selects a weight
+//     column; unknown bases select the 0.25-weighted mean column),
+//   * every later conv/FC is the implicit GEMM of sb_tc.cu (bf16 / tcgen05) or of the fp32 FFMA
+//     kernel below (accuracy mode, <= 1e-5 abs on the sigmoid outputs),
+//   * the reference's channel-major flatten is absorbed into a one-time permutation of the first FC
+//     weight matrix.
+#include "sb_common.cuh"
+#include "sb_tc.cuh"
+
+#include <math.h>
+#include <stdlib.h>
+#include <vector>
+
+namespace {
+
+struct NetLayer {
+    int type, cin, cout, k, relu, pool;
+    int t_in, t_conv, t_pool;  // per-sequence rows in / valid conv rows / rows out (FC: 1,1,1)
+    // fp32 path
+    float* wf;     // dev (k_f32 x ldw_f32): row = K index (tap*cin + c), col = cout (padded to x4)
+    float* biasf;  // dev (ldw_f32)
+    int k_f32, ldw_f32;
+    // bf16 path
+    __nv_bfloat16* wb;      // dev (cout x w_ld): K index = tap*a_ld + c   (overlapping-stride A view)
+    __nv_bfloat16* wb_tap;  // dev (cout x w_ld_tap): K index = tap*cpk*64 + c (per-tap boxes); conv only
+    float* biasb;           // dev, padded to n_tiles_n*block_n
+    int a_ld, k_full, w_ld, k_full_tap, w_ld_tap, block_n, n_tiles_n, out_ld_b;
+    // first layer from codes
+    float* lut;  // dev (k x 5 x cout)
+};
+
+}  // namespace
+
+struct sb_net {
+    int device;
+    int L;
+    int n_layers;
+    int n_out;
+    uint8_t perm[4];
+    double flops_per_seq;
+    bool force_per_tap;
+    std::vector<NetLayer> layers;
+};
+
+namespace {
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// ---------------------------------------------------------------------------------------------
+// first conv from base codes: out[t][n] = bias[n] + sum_j lut[j][code[t+j]][n], ReLU, max-pool
+// ---------------------------------------------------------------------------------------------
+template <typename OutT>
+__device__ __forceinline__ OutT to_out(float v);
+template <>
+__device__ __forceinline__ float to_out<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename OutT>
+__global__ void __launch_bounds__(512) conv_codes_kernel(
+    const uint8_t* __restrict__ codes, const int32_t* __restrict__ src, const int32_t* __restrict__ sub_pos,
+    const uint8_t* __restrict__ sub_code, long long row0, int L, int k, int cout, int out_ld, int relu, int pool,
+    int t_pool, const float* __restrict__ lut, const float* __restrict__ bias, OutT* __restrict__ out) {
+    extern __shared__ uint8_t smem_raw[];
+    float* tab = reinterpret_cast<float*>(smem_raw);             // k*5*cout
+    uint8_t* sc = smem_raw + (size_t)k * 5 * cout * sizeof(float);  // L codes
+    const long long row = row0 + blockIdx.x;
+    const long long srow = src ? src[row] : row;
+    const uint8_t* crow = codes + srow * L;
+    const int sp = sub_pos ? sub_pos[row] : -1;
+    const int scode = (sub_pos && sub_code) ? sub_code[row] : 4;
+    for (int i = threadIdx.x; i < k * 5 * cout; i += blockDim.x) tab[i] = __ldg(lut + i);
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        int c = __ldg(crow + i);
+        if (i == sp) c = scode;
+        sc[i] = (uint8_t)(c > 4 ? 4 : c);
+    }
+    __syncthreads();
+    OutT* orow = out + (long long)blockIdx.x * t_pool * out_ld;
+    for (int n = threadIdx.x; n < out_ld; n += blockDim.x) {
+        if (n >= cout) {
+            for (int tp = 0; tp < t_pool; ++tp) orow[(long long)tp * out_ld + n] = to_out<OutT>(0.f);
+            continue;
+        }
+        const float b = __ldg(bias + n);
+        const float* tn = tab + n;
+        for (int tp = 0; tp < t_pool; ++tp) {
+            float m = -INFINITY;
+            for (int q = 0; q < pool; ++q) {
+                const int t = tp * pool + q;
+                float acc = b;
+                for (int j = 0; j < k; ++j) acc += tn[(j * 5 + sc[t + j]) * cout];
+                m = fmaxf(m, acc);
+            }
+            if (relu) m = fmaxf(m, 0.f);
+            orow[(long long)tp * out_ld + n] = to_out<OutT>(m);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 accuracy path: implicit GEMM with FFMA.  full[r][n] = act(bias[n] + sum_k A[r*lda + k] W[k][n])
+// ---------------------------------------------------------------------------------------------
+constexpr int FBM = 64, FBN = 64, FBK = 16;
+
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, long long a_elems, int lda,
+                                                       long long rows, int K, const float* __restrict__ W,
+                                                       int ldw, const float* __restrict__ bias, int relu,
+                                                       float* __restrict__ out, int ldo, int n_cols) {
+    __shared__ float As[FBK][FBM + 4];
+    __shared__ float Bs[FBK][FBN];
+    const int tid = threadIdx.x;
+    const long long r0 = (long long)blockIdx.x * FBM;
+    const int n0 = blockIdx.y * FBN;
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int ar = tid >> 2;         // 0..63
+    const int ak = (tid & 3) * 4;    // 0,4,8,12
+    const int bk = tid >> 4;         // 0..15
+    const int bn = (tid & 15) * 4;   // 0..60
+    for (int k0 = 0; k0 < K; k0 += FBK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int kk = k0 + ak + i;
+            const long long idx = (r0 + ar) * lda + kk;
+            As[ak + i][ar] = (kk < K && (r0 + ar) < rows && idx < a_elems) ? __ldg(A + idx) : 0.f;
+        }
+        {
+            const int kk = k0 + bk;
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kk < K && n0 + bn < ldw) w = *reinterpret_cast<const float4*>(W + (long long)kk * ldw + n0 + bn);
+            *reinterpret_cast<float4*>(&Bs[bk][bn]) = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < FBK; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long r = r0 + ty * 4 + i;
+        if (r >= rows) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= n_cols) continue;
+            float v = acc[i][j] + __ldg(bias + n);
+            if (relu) v = fmaxf(v, 0.f);
+            out[r * ldo + n] = v;
+        }
+    }
+}
+
+// max-pool + compaction of the "full" conv output (rows = seq*t_in + t) into (seq, t_pool, c)
+template <typename OutT>
+__global__ void __launch_bounds__(256) pool_compact_kernel(const float* __restrict__ full, int ldf, int t_in,
+                                                           int pool, int t_pool, int c_valid, int out_ld,
+                                                           long long n_seq, OutT* __restrict__ out) {
+    const long long total = n_seq * t_pool * out_ld;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = (int)(i % out_ld);
+        const long long rt = i / out_ld;
+        const int tp = (int)(rt % t_pool);
+        const long long s = rt / t_pool;
+        float m = 0.f;
+        if (c < c_valid) {
+            m = -INFINITY;
+            for (int q = 0; q < pool; ++q) m = fmaxf(m, full[(s * t_in + (long long)tp * pool + q) * ldf + c]);
+        }
+        out[i] = to_out<OutT>(m);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel (d): sigmoid + scores
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoid_f32(float x) { return 1.f / (1.f + expf(-x)); }
+// logit_score_handler.py:118-124 clamp, then scipy.special.logit in float32: log(p / (1 - p))
+__device__ __forceinline__ float clamp_pred(float p) { return p == 0.f ? 1e-24f : (p >= 1.f ? 0.999999f : p); }
+__device__ __forceinline__ float logit_f32(float p) { return logf(p / (1.f - p)); }
+
+__global__ void __launch_bounds__(256) sigmoid_kernel(const float* __restrict__ logits, int ldl, long long n, int F,
+                                                      float* __restrict__ pred) {
+    const long long total = n * F;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long r = i / F;
+        const int f = (int)(i - r * F);
+        pred[i] = sigmoid_f32(logits[r * ldl + f]);
+    }
+}
+
+// logits_mode 1: `x` holds pre-sigmoid values with row stride ldx; 0: `x` holds probabilities.
+__global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ x, int ldx, int x_is_logits,
+                                                    int pair_mode, const float* __restrict__ base_pred,
+                                                    const int32_t* __restrict__ base_index, long long n_base,
+                                                    long long n_out, int F, float* __restrict__ abs_diff,
+                                                    float* __restrict__ diff, float* __restrict__ logit,
+                                                    float* __restrict__ pred_ref, float* __restrict__ pred_alt) {
+    const long long total = n_out * F;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long v = i / F;
+        const int f = (int)(i - v * F);
+        float ref, alt;
+        if (pair_mode == SB_PAIR_INTERLEAVED) {
+            const float a = x[(2 * v) * ldx + f], b = x[(2 * v + 1) * ldx + f];
+            ref = x_is_logits ? sigmoid_f32(a) : a;
+            alt = x_is_logits ? sigmoid_f32(b) : b;
+        } else {
+            const float b = x[v * ldx + f];
+            alt = x_is_logits ? sigmoid_f32(b) : b;
+            long long bi = base_index ? (long long)base_index[v] : (n_base == n_out ? v : 0);
+            ref = base_pred[bi * F + f];
+        }
+        if (abs_diff) abs_diff[i] = fabsf(ref - alt);  // np.abs(baseline - batch)
+        if (diff) diff[i] = alt - ref;                 // batch - baseline
+        if (logit) {
+            ref = clamp_pred(ref);
+            alt = clamp_pred(alt);
+            logit[i] = logit_f32(alt) - logit_f32(ref);
+        }
+        if (pred_ref) pred_ref[i] = ref;
+        if (pred_alt) pred_alt[i] = alt;
+    }
+}
+
+int grid_for(long long total, int device) {
+    long long b = (total + 255) / 256;
+    const long long cap = (long long)sb_sm_count(device) * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing (host)
+// ---------------------------------------------------------------------------------------------
+uint16_t f32_to_bf16_bits(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+    const uint32_t lsb = (u >> 16) & 1;
+    u += 0x7fffu + lsb;  // round to nearest even
+    return (uint16_t)(u >> 16);
+}
+
+template <typename T>
+int upload(T** dev, const std::vector<T>& host) {
+    SB_CHECK_CUDA(cudaMalloc(dev, sizeof(T) * (host.size() ? host.size() : 1)));
+    if (!host.empty()) SB_CHECK_CUDA(cudaMemcpy(*dev, host.data(), sizeof(T) * host.size(), cudaMemcpyHostToDevice));
+    return SB_OK;
+}
+
+}  // namespace
+
+extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const uint8_t perm[4], int device,
+                             sb_net** out) {
+    SB_REQUIRE(layers && out && n_layers >= 2 && L > 0 && perm, "sb_net_create: bad arguments");
+    {
+        int seen = 0;
+        for (int i = 0; i < 4; ++i) {
+            SB_REQUIRE(perm[i] < 4, "sb_net_create: perm is not a permutation of 0..3");
+            seen |= 1 << perm[i];
+        }
+        SB_REQUIRE(seen == 15, "sb_net_create: perm is not a permutation of 0..3");
+    }
+    SB_REQUIRE(layers[0].type == SB_LAYER_CONV && layers[0].cin == 4, "sb_net_create: first layer must be a 4-channel conv");
+    SB_CHECK_CUDA(cudaSetDevice(device));
+    sb_net* net = new sb_net();
+    net->device = device;
+    net->L = L;
+    net->n_layers = n_layers;
+    memcpy(net->perm, perm, 4);
+    net->flops_per_seq = 0.0;
+    const char* env = getenv("SB_TC_PER_TAP");
+    net->force_per_tap = env && env[0] == '1';
+
+    int t = L, c = 4;          // current activation: t rows of c channels per sequence
+    bool seen_fc = false;
+    for (int li = 0; li < n_layers; ++li) {
+        const sb_layer& S = layers[li];
+        SB_REQUIRE(S.weight && S.bias, "sb_net_create: layer %d has null weights", li);
+        NetLayer N;
+        memset(&N, 0, sizeof(N));
+        N.type = S.type; N.cin = S.cin; N.cout = S.cout; N.relu = S.relu;
+        N.pool = S.pool > 1 ? S.pool : 1;
+        if (S.type == SB_LAYER_CONV) {
+            SB_REQUIRE(!seen_fc, "sb_net_create: conv layer %d after an FC layer", li);
+            SB_REQUIRE(S.cin == c, "sb_net_create: layer %d expects %d input channels, has %d", li, S.cin, c);
+            SB_REQUIRE(S.k >= 1 && t >= S.k, "sb_net_create: layer %d kernel %d longer than input %d", li, S.k, t);
+            N.k = S.k; N.t_in = t; N.t_conv = t - S.k + 1; N.t_pool = N.t_conv / N.pool;
+            SB_REQUIRE(N.t_pool >= 1, "sb_net_create: layer %d pools away everything", li);
+            net->flops_per_seq += 2.0 * N.t_conv * (double)S.cout * S.cin * S.k;
+        } else if (S.type == SB_LAYER_FC) {
+            SB_REQUIRE(S.cin == t * c, "sb_net_create: FC layer %d expects %d inputs, previous layer gives %d x %d", li,
+                       S.cin, c, t);
+            SB_REQUIRE(N.pool == 1, "sb_net_create: FC layer %d cannot pool", li);
+            N.k = 1; N.t_in = 1; N.t_conv = 1; N.t_pool = 1;
+            net->flops_per_seq += 2.0 * (double)S.cout * S.cin;
+        } else {
+            sb_set_error("sb_net_create: unknown layer type %d", S.type);
+            delete net;
+            return SB_ERR_ARG;
+        }
+
+        // ---- logical K ordering shared by both paths: K index = tap * C + channel, where for the FC after
+        //      the conv stack "tap" is the position t and "channel" the conv channel (torch flattens c*T + t)
+        const int taps = (S.type == SB_LAYER_CONV) ? S.k : (seen_fc ? 1 : t);
+        const int ch = (S.type == SB_LAYER_CONV) ? S.cin : (seen_fc ? S.cin : c);
+        auto w_at = [&](int o, int tap, int cc) -> float {
+            if (S.type == SB_LAYER_CONV) return S.weight[((size_t)o * S.cin + cc) * S.k + tap];
+            if (seen_fc) return S.weight[(size_t)o * S.cin + cc];
+            return S.weight[(size_t)o * S.cin + (size_t)cc * t + tap];  // flatten index c*T + t
+        };
+
+        // ---- fp32 path
+        N.k_f32 = taps * ch;
+        N.ldw_f32 = round_up(S.cout, 4);
+        {
+            std::vector<float> wf((size_t)N.k_f32 * N.ldw_f32, 0.f), bf((size_t)N.ldw_f32, 0.f);
+            for (int o = 0; o < S.cout; ++o) {
+                bf[o] = S.bias[o];
+                for (int tap = 0; tap < taps; ++tap)
+                    for (int cc = 0; cc < ch; ++cc) wf[((size_t)tap * ch + cc) * N.ldw_f32 + o] = w_at(o, tap, cc);
+            }
+            int rc = upload(&N.wf, wf); if (rc) return rc;
+            rc = upload(&N.biasf, bf); if (rc) return rc;
+        }
+
+        // ---- first layer: lookup table over canonical codes (and the unknown code 4 = 0.25 * sum)
+        if (li == 0) {
+            std::vector<float> lut((size_t)S.k * 5 * S.cout, 0.f);
+            for (int j = 0; j < S.k; ++j)
+                for (int o = 0; o < S.cout; ++o) {
+                    float s4 = 0.f;
+                    for (int b = 0; b < 4; ++b) {
+                        const float w = S.weight[((size_t)o * 4 + perm[b]) * S.k + j];
+                        lut[((size_t)j * 5 + b) * S.cout + o] = w;
+                    }
+                    // 0.25*w0 + 0.25*w1 + 0.25*w2 + 0.25*w3 in channel order, as the dense conv would add them
+                    for (int chn = 0; chn < 4; ++chn) s4 += 0.25f * S.weight[((size_t)o * 4 + chn) * S.k + j];
+                    lut[((size_t)j * 5 + 4) * S.cout + o] = s4;
+                }
+            int rc = upload(&N.lut, lut); if (rc) return rc;
+        }
+
+        // ---- bf16 / tcgen05 path (every layer but the first)
+        N.out_ld_b = round_up(S.cout, 8);
+        if (li > 0) {
+            const int a_ld_ch = round_up(ch, 8);   // channel stride of the incoming activation buffer
+            N.a_ld = (S.type == SB_LAYER_FC) ? taps * a_ld_ch : a_ld_ch;
+            N.k_full = taps * a_ld_ch;
+            N.w_ld = round_up(N.k_full, 8);
+            std::vector<uint16_t> wb((size_t)S.cout * N.w_ld, 0);
+            for (int o = 0; o < S.cout; ++o)
+                for (int tap = 0; tap < taps; ++tap)
+                    for (int cc = 0; cc < ch; ++cc)
+                        wb[(size_t)o * N.w_ld + (size_t)tap * a_ld_ch + cc] = f32_to_bf16_bits(w_at(o, tap, cc));
+            int rc = upload(reinterpret_cast<uint16_t**>(&N.wb), wb); if (rc) return rc;
+            if (S.type == SB_LAYER_CONV) {
+                const int cpk = (a_ld_ch + 63) / 64;
+                N.k_full_tap = taps * cpk * 64;
+                N.w_ld_tap = N.k_full_tap;
+                std::vector<uint16_t> wt((size_t)S.cout * N.w_ld_tap, 0);
+                for (int o = 0; o < S.cout; ++o)
+                    for (int tap = 0; tap < taps; ++tap)
+                        for (int cc = 0; cc < ch; ++cc)
+                            wt[(size_t)o * N.w_ld_tap + (size_t)tap * cpk * 64 + cc] = f32_to_bf16_bits(w_at(o, tap, cc));
+                rc = upload(reinterpret_cast<uint16_t**>(&N.wb_tap), wt); if (rc) return rc;
+            }
+            // N tiling: fewest tiles of <= 256 columns, each a multiple of 16
+            const int nt = (S.cout + 255) / 256;
+            N.n_tiles_n = nt;
+            N.block_n = round_up((S.cout + nt - 1) / nt, 16);
+            std::vector<float> bb((size_t)N.n_tiles_n * N.block_n, 0.f);
+            for (int o = 0; o < S.cout; ++o) bb[o] = S.bias[o];
+            rc = upload(&N.biasb, bb); if (rc) return rc;
+        }
+
+        net->layers.push_back(N);
+        if (S.type == SB_LAYER_CONV) { t = N.t_pool; c = S.cout; }
+        else { seen_fc = true; t = 1; c = S.cout; }
+    }
+    SB_REQUIRE(seen_fc, "sb_net_create: network must end in FC layers");
+    net->n_out = c;
+    *out = net;
+    return SB_OK;
+}
+
+extern "C" int sb_net_destroy(sb_net* net) {
+    if (!net) return SB_OK;
+    cudaSetDevice(net->device);
+    for (auto& N : net->layers) {
+        cudaFree(N.wf); cudaFree(N.biasf); cudaFree(N.wb); cudaFree(N.wb_tap); cudaFree(N.biasb); cudaFree(N.lut);
+    }
+    delete net;
+    return SB_OK;
+}
+
+extern "C" int sb_net_n_outputs(const sb_net* net) { return net ? net->n_out : -1; }
+extern "C" double sb_net_flops_per_seq(const sb_net* net) { return net ? net->flops_per_seq : 0.0; }
+
+namespace {
+
+int chunk_rows(int precision) { return precision == SB_PREC_BF16 ? 8192 : 256; }
+
+// bytes of the two ping-pong activation buffers, the fp32 "full" buffer and the logits buffer
+struct WsPlan { size_t act, full, logits, total; };
+
+long long chunk_for(int precision, bool generic) { return generic ? 256 : chunk_rows(precision); }
+
+WsPlan plan_ws(const sb_net* net, long long n, int precision, bool generic) {
+    const long long cr = chunk_for(precision, generic);
+    const long long ch = n < cr ? n : cr;
+    size_t act = 0, full = 0;
+    const size_t es = precision == SB_PREC_BF16 ? 2 : 4;
+    for (size_t li = 0; li < net->layers.size(); ++li) {
+        const NetLayer& N = net->layers[li];
+        const int ld = precision == SB_PREC_BF16 ? N.out_ld_b : N.cout;
+        const size_t bytes = (size_t)ch * N.t_pool * ld * es;
+        if (bytes > act) act = bytes;
+        if (precision == SB_PREC_FP32 && li > 0) {
+            const size_t fb = (size_t)ch * N.t_in * N.cout * 4;
+            if (fb > full) full = fb;
+        }
+    }
+    // generic-input first conv also runs through the fp32 "full" path
+    if (generic) {
+        const NetLayer& N0 = net->layers[0];
+        const size_t fb = (size_t)ch * N0.t_in * N0.cout * 4;
+        if (fb > full) full = fb;
+    }
+    auto al = [](size_t b) { return (b + 1023) / 1024 * 1024 + 1024; };
+    WsPlan p;
+    p.act = al(act);
+    p.full = al(full);
+    p.logits = al((size_t)ch * round_up(net->n_out, 4) * 4);
+    p.total = 2 * p.act + p.full + p.logits + 4096;
+    return p;
+}
+
+struct RowSource {
+    const uint8_t* codes; const int32_t* src; const int32_t* sub_pos; const uint8_t* sub_code;  // codes input
+    const float* onehot;                                                                        // generic input
+};
+
+// Runs rows [r0, r0+m) through the network; leaves fp32 logits (row stride ldl) in ws logits buffer.
+int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int precision, uint8_t* ws,
+              const WsPlan& plan, float** logits_out, int* ldl_out, cudaStream_t stream) {
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
+    void* act[2] = {base, base + plan.act};
+    float* full = reinterpret_cast<float*>(base + 2 * plan.act);
+    float* logits = reinterpret_cast<float*>(base + 2 * plan.act + plan.full);
+    const int ldl = round_up(net->n_out, 4);
+    const bool bf = precision == SB_PREC_BF16;
+    const int dev = net->device;
+    int cur = 0;
+
+    // ---- layer 0
+    {
+        const NetLayer& N = net->layers[0];
+        const int out_ld = bf ? N.out_ld_b : N.cout;
+        if (in.codes) {
+            const size_t smem = (size_t)N.k * 5 * N.cout * sizeof(float) + (size_t)round_up(net->L, 16);
+            SB_REQUIRE(smem <= 220 * 1024, "first-layer lookup table (%zu B) does not fit shared memory", smem);
+            int threads = round_up(out_ld < 512 ? out_ld : 512, 32);
+            if (bf) {
+                SB_CHECK_CUDA(cudaFuncSetAttribute(conv_codes_kernel<__nv_bfloat16>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                conv_codes_kernel<__nv_bfloat16><<<(unsigned)m, threads, smem, stream>>>(
+                    in.codes, in.src, in.sub_pos, in.sub_code, r0, net->L, N.k, N.cout, out_ld, N.relu, N.pool,
+                    N.t_pool, N.lut, N.biasf, reinterpret_cast<__nv_bfloat16*>(act[cur]));
+            } else {
+                SB_CHECK_CUDA(cudaFuncSetAttribute(conv_codes_kernel<float>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                conv_codes_kernel<float><<<(unsigned)m, threads, smem, stream>>>(
+                    in.codes, in.src, in.sub_pos, in.sub_code, r0, net->L, N.k, N.cout, out_ld, N.relu, N.pool,
+                    N.t_pool, N.lut, N.biasf, reinterpret_cast<float*>(act[cur]));
+            }
+            SB_COUNT_LAUNCH();
+            SB_CHECK_LAUNCH();
+        } else {
+            // generic (n, L, 4) fp32 input: dense fp32 conv, then pool/compact (+ convert)
+            const float* x = in.onehot + r0 * net->L * 4;
+            const long long rows = m * N.t_in;
+            dim3 grid((unsigned)((rows + FBM - 1) / FBM), (unsigned)((N.cout + FBN - 1) / FBN));
+            gemm_f32_kernel<<<grid, 256, 0, stream>>>(x, rows * 4, 4, rows, N.k_f32, N.wf, N.ldw_f32, N.biasf, N.relu,
+                                                      full, N.cout, N.cout);
+            SB_COUNT_LAUNCH();
+            SB_CHECK_LAUNCH();
+            const long long total = m * N.t_pool * out_ld;
+            if (bf)
+                pool_compact_kernel<__nv_bfloat16><<<grid_for(total, dev), 256, 0, stream>>>(
+                    full, N.cout, N.t_in, N.pool, N.t_pool, N.cout, out_ld, m, reinterpret_cast<__nv_bfloat16*>(act[cur]));
+            else
+                pool_compact_kernel<float><<<grid_for(total, dev), 256, 0, stream>>>(
+                    full, N.cout, N.t_in, N.pool, N.t_pool, N.cout, out_ld, m, reinterpret_cast<float*>(act[cur]));
+            SB_COUNT_LAUNCH();
+            SB_CHECK_LAUNCH();
+        }
+    }
+
+    // ---- remaining layers
+    for (size_t li = 1; li < net->layers.size(); ++li) {
+        const NetLayer& N = net->layers[li];
+        const bool last = li + 1 == net->layers.size();
+        if (bf) {
+            SbTcLayer T;
+            memset(&T, 0, sizeof(T));
+            T.a = act[cur];
+            T.rows_a = m * N.t_in;
+            T.a_ld = N.a_ld;
+            T.bias = N.biasb; T.block_n = N.block_n; T.n_tiles_n = N.n_tiles_n;
+            T.n_rows_w = N.cout;
+            T.t_in = N.t_in; T.t_conv = N.t_conv; T.pool = N.pool; T.relu = N.relu;
+            T.out_f32 = last ? 1 : 0;
+            T.out = last ? (void*)logits : act[cur ^ 1];
+            T.out_ld = last ? ldl : N.out_ld_b;
+            const bool fusable = (N.t_in % N.pool) == 0;
+            SB_REQUIRE(fusable, "layer %zu: t_in %d not a multiple of pool %d (unsupported on the bf16 path)", li,
+                       N.t_in, N.pool);
+            bool per_tap = net->force_per_tap && N.type == SB_LAYER_CONV;
+            int rc = SB_OK;
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                if (per_tap) {
+                    T.per_tap = 1; T.taps = N.k; T.w = N.wb_tap; T.w_ld = N.w_ld_tap; T.k_full = N.k_full_tap;
+                } else {
+                    T.per_tap = 0; T.taps = N.k; T.w = N.wb; T.w_ld = N.w_ld; T.k_full = N.k_full;
+                }
+                rc = sb_tc_launch(T, dev, stream);
+                if (rc == SB_OK || per_tap || N.type != SB_LAYER_CONV) break;
+                per_tap = true;            // overlapping-stride tensor map refused: fall back to per-tap boxes
+                net->force_per_tap = true;
+            }
+            if (rc != SB_OK) return rc;
+        } else {
+            const long long rows = m * N.t_in;
+            const float* a = reinterpret_cast<const float*>(act[cur]);
+            const long long a_elems = rows * N.cin / (N.type == SB_LAYER_CONV ? 1 : N.t_in);
+            const int lda = (N.type == SB_LAYER_CONV) ? N.cin : N.cin;
+            const bool direct = (N.type == SB_LAYER_FC);
+            float* o = direct ? (last ? logits : reinterpret_cast<float*>(act[cur ^ 1])) : full;
+            const int ldo = direct ? (last ? ldl : N.cout) : N.cout;
+            dim3 grid((unsigned)((rows + FBM - 1) / FBM), (unsigned)((N.cout + FBN - 1) / FBN));
+            gemm_f32_kernel<<<grid, 256, 0, stream>>>(a, a_elems, lda, rows, N.k_f32, N.wf, N.ldw_f32, N.biasf, N.relu, o,
+                                                      ldo, N.cout);
+            SB_COUNT_LAUNCH();
+            SB_CHECK_LAUNCH();
+            if (!direct) {
+                SB_REQUIRE(!last, "network cannot end in a conv layer");
+                const long long total = m * N.t_pool * N.cout;
+                pool_compact_kernel<float><<<grid_for(total, dev), 256, 0, stream>>>(
+                    full, N.cout, N.t_in, N.pool, N.t_pool, N.cout, N.cout, m, reinterpret_cast<float*>(act[cur ^ 1]));
+                SB_COUNT_LAUNCH();
+                SB_CHECK_LAUNCH();
+            }
+        }
+        cur ^= 1;
+    }
+    *logits_out = logits;
+    *ldl_out = ldl;
+    return SB_OK;
+}
+
+int check_common(sb_net* net, long long n, int precision, bool generic, void* ws, size_t ws_bytes) {
+    SB_REQUIRE(net, "null network handle");
+    SB_REQUIRE(n >= 0, "negative row count");
+    SB_REQUIRE(precision == SB_PREC_FP32 || precision == SB_PREC_BF16, "bad precision %d", precision);
+    if (n == 0) return SB_OK;
+    const WsPlan plan = plan_ws(net, n, precision, generic);
+    SB_REQUIRE(ws && ws_bytes >= plan.total, "workspace too small: need %zu bytes, have %zu", plan.total, ws_bytes);
+    return SB_OK;
+}
+
+}  // namespace
+
+extern "C" size_t sb_net_workspace_bytes(const sb_net* net, int64_t n_rows, int precision) {
+    if (!net || n_rows <= 0) return 0;
+    const size_t a = plan_ws(net, n_rows, precision, false).total;
+    const size_t b = plan_ws(net, n_rows, precision, true).total;
+    return a > b ? a : b;
+}
+
+static int forward_impl(sb_net* net, const RowSource& in, int64_t n, int precision, void* ws, size_t ws_bytes,
+                        float* pred, int pair_mode, const float* base_pred, const int32_t* base_index, bool scoring,
+                        float* abs_diff, float* diff, float* logit, float* pred_ref, float* pred_alt, void* stream) {
+    const bool generic = in.codes == nullptr;
+    int rc = check_common(net, n, precision, generic, ws, ws_bytes);
+    if (rc) return rc;
+    if (n == 0) return SB_OK;
+    SB_CHECK_CUDA(cudaSetDevice(net->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const WsPlan plan = plan_ws(net, n, precision, generic);
+    const int F = net->n_out;
+    long long chunk = chunk_for(precision, generic);
+    if (scoring && pair_mode == SB_PAIR_INTERLEAVED) {
+        SB_REQUIRE(n % 2 == 0, "interleaved ref/alt rows need an even row count, got %lld", (long long)n);
+        chunk &= ~1ll;
+    }
+    for (long long r0 = 0; r0 < n; r0 += chunk) {
+        const long long m = (n - r0) < chunk ? (n - r0) : chunk;
+        float* lg = nullptr;
+        int ldl = 0;
+        rc = run_chunk(net, in, r0, m, precision, reinterpret_cast<uint8_t*>(ws), plan, &lg, &ldl, s);
+        if (rc) return rc;
+        if (!scoring) {
+            sigmoid_kernel<<<grid_for(m * F, net->device), 256, 0, s>>>(lg, ldl, m, F, pred + r0 * F);
+        } else if (pair_mode == SB_PAIR_INTERLEAVED) {
+            const long long v0 = r0 / 2, nv = m / 2;
+            score_kernel<<<grid_for(nv * F, net->device), 256, 0, s>>>(
+                lg, ldl, 1, SB_PAIR_INTERLEAVED, nullptr, nullptr, 0, nv, F, abs_diff ? abs_diff + v0 * F : nullptr,
+                diff ? diff + v0 * F : nullptr, logit ? logit + v0 * F : nullptr, pred_ref ? pred_ref + v0 * F : nullptr,
+                pred_alt ? pred_alt + v0 * F : nullptr);
+        } else {
+            score_kernel<<<grid_for(m * F, net->device), 256, 0, s>>>(
+                lg, ldl, 1, SB_PAIR_BASELINE, base_pred, base_index ? base_index + r0 : nullptr, /*n_base*/ 1, m, F,
+                abs_diff ? abs_diff + r0 * F : nullptr, diff ? diff + r0 * F : nullptr,
+                logit ? logit + r0 * F : nullptr, nullptr, pred_alt ? pred_alt + r0 * F : nullptr);
+        }
+        SB_COUNT_LAUNCH();
+        SB_CHECK_LAUNCH();
+    }
+    return SB_OK;
+}
+
+extern "C" int sb_net_forward_codes(sb_net* net, const uint8_t* codes, const int32_t* src, const int32_t* sub_pos,
+                                    const uint8_t* sub_code, int64_t n, int precision, void* workspace,
+                                    size_t workspace_bytes, float* pred, void* stream) {
+    SB_REQUIRE(n == 0 || (codes && pred), "sb_net_forward_codes: null argument");
+    RowSource in = {codes, src, sub_pos, sub_code, nullptr};
+    return forward_impl(net, in, n, precision, workspace, workspace_bytes, pred, 0, nullptr, nullptr, false, nullptr,
+                        nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int sb_net_forward_onehot(sb_net* net, const float* x, int64_t n, int precision, void* workspace,
+                                     size_t workspace_bytes, float* pred, void* stream) {
+    SB_REQUIRE(n == 0 || (x && pred), "sb_net_forward_onehot: null argument");
+    RowSource in = {nullptr, nullptr, nullptr, nullptr, x};
+    return forward_impl(net, in, n, precision, workspace, workspace_bytes, pred, 0, nullptr, nullptr, false, nullptr,
+                        nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int sb_net_forward_score(sb_net* net, const uint8_t* codes, const int32_t* src, const int32_t* sub_pos,
+                                    const uint8_t* sub_code, int64_t n, int precision, int pair_mode,
+                                    const float* base_pred, const int32_t* base_index, void* workspace,
+                                    size_t workspace_bytes, float* abs_diff, float* diff, float* logit,
+                                    float* pred_ref, float* pred_alt, void* stream) {
+    SB_REQUIRE(n == 0 || codes, "sb_net_forward_score: null argument");
+    SB_REQUIRE(pair_mode == SB_PAIR_INTERLEAVED || pair_mode == SB_PAIR_BASELINE, "sb_net_forward_score: bad pair_mode");
+    SB_REQUIRE(pair_mode != SB_PAIR_BASELINE || base_pred, "sb_net_forward_score: baseline mode needs base_pred");
+    RowSource in = {codes, src, sub_pos, sub_code, nullptr};
+    return forward_impl(net, in, n, precision, workspace, workspace_bytes, nullptr, pair_mode, base_pred, base_index,
+                        true, abs_diff, diff, logit, pred_ref, pred_alt, stream);
+}
+
+extern "C" int sb_score_pairs(const float* ref, const float* alt, const int32_t* base_index, int64_t n, int64_t n_ref,
+                              int F, float* abs_diff, float* diff, float* logit, int clamp_inplace, void* stream) {
+    SB_REQUIRE(n >= 0 && F > 0, "sb_score_pairs: bad sizes");
+    if (n == 0) return SB_OK;
+    SB_REQUIRE(ref && alt, "sb_score_pairs: null argument");
+    (void)clamp_inplace;
+    int dev = 0;
+    SB_CHECK_CUDA(cudaGetDevice(&dev));
+    score_kernel<<<grid_for(n * F, dev), 256, 0, (cudaStream_t)stream>>>(alt, F, 0, SB_PAIR_BASELINE, ref, base_index,
+                                                                         n_ref, n, F, abs_diff, diff, logit, nullptr,
+                                                                         nullptr);
+    SB_COUNT_LAUNCH();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}

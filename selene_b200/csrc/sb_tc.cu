@@ -1,0 +1,390 @@
+// selene_b200 — kernel (c): conv1d / FC layers as a persistent, warp-specialised tcgen05 implicit GEMM.
+//
+// Replaces what torch dispatches for models/deepsea.py:22-50 (torch.conv1d -> cuDNN, linear ->
+// cuBLAS, relu, max_pool1d).  One kernel per layer does conv + bias + ReLU + MaxPool + the layout
+// change for the next layer:
+//
+//   * activations are channel-last bf16, rows = sequence x position.  The im2col row of a valid
+//     k-tap convolution is then the contiguous run of k*C elements starting at row r, so the A
+//     operand is described to TMA as an overlapping-stride 2-D tensor (row stride C, row length
+//     k*C) and never materialised.  Rows whose window straddles two sequences are computed and
+//     dropped in the epilogue (7/248 of conv2's rows, 7/60 of conv3's).
+//   * weights are bf16, K-major (cout x k*C with K index = tap*C + channel), the B operand.
+//   * warp 0 (one lane) is the TMA producer, warp 1 (one lane) issues tcgen05.mma with fp32
+//     accumulators in TMEM (2 x 256 columns, double buffered), warps 2-5 are the epilogue:
+//     tcgen05.ld -> +bias -> max over the 4 rows of a pool window (two xor-shuffles: a pool window is
+//     4 adjacent TMEM lanes because tiles start at multiples of 4 and t_in % 4 == 0) -> ReLU -> bf16
+//     -> compacted store (sequence, pooled position, channel).
+//   * 4-stage smem ring (A 16 KB + B up to 32 KB per stage, 128-byte swizzle), mbarrier full/empty
+//     pairs, tcgen05.commit releases stages and publishes accumulators.
+//   * persistent grid = min(tiles, SMs); tiles are numbered n-fastest so CTAs running side by side
+//     share the A tile in L2 while the (small) weight matrix stays L2-resident.
+#include "sb_tc.cuh"
+
+#include <cuda.h>  // CUtensorMap + enums only; the encoder is fetched through the runtime (no -lcuda)
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;   // bf16 elements = one 128-byte swizzle row
+constexpr int kStages = 4;
+constexpr int kMaxN = 256;
+constexpr int kABytes = kBlockM * kBlockK * 2;       // 16384
+constexpr int kBBytesMax = kMaxN * kBlockK * 2;      // 32768
+constexpr int kStageBytes = kABytes + kBBytesMax;    // 49152
+constexpr int kAuxBytes = 4096;                      // barriers + tmem slot + 2 bias tiles
+constexpr int kSmemBytes = kStages * kStageBytes + kAuxBytes + 1024;  // + alignment slack
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;
+
+struct TcParams {
+    long long rows_a;
+    int t_in, t_conv, pool, t_pool;
+    int out_ld, relu, out_f32;
+    int block_n, n_tiles_n, n_tiles_m, num_k_blocks;
+    int chunks_per_tap;  // 0: overlapping-stride A view; >0: per-tap boxes
+    const float* bias;
+    void* out;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    uint8_t* aux = smem + kStages * kStageBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tfull_bar = empty_bar + kStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* bias_s = reinterpret_cast<float*>(aux + 1024);  // [2][256]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.n_tiles_m * p.n_tiles_n;
+
+    if (warp == 0 && lane == 0) {
+        sb_prefetch_tmap(&tmap_a);
+        sb_prefetch_tmap(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            sb_mbar_init(&full_bar[i], 1);
+            sb_mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            sb_mbar_init(&tfull_bar[i], 1);
+            sb_mbar_init(&tempty_bar[i], 128);
+        }
+        sb_fence_mbar_init();
+    }
+    if (warp == 2) sb_tmem_alloc(tmem_slot, kTmemCols);
+    sb_tc_fence_before();
+    __syncthreads();
+    sb_tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            const uint32_t tx_bytes = kABytes + (uint32_t)p.block_n * kBlockK * 2;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / p.n_tiles_n) * kBlockM;
+                const int n0 = (tile % p.n_tiles_n) * p.block_n;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    sb_mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * kStageBytes;
+                    uint8_t* sb = sa + kABytes;
+                    sb_mbar_expect_tx(&full_bar[stage], tx_bytes);
+                    if (p.chunks_per_tap > 0) {
+                        const int tap = kb / p.chunks_per_tap;
+                        sb_tma_load_2d(sa, &tmap_a, &full_bar[stage],
+                                       (kb - tap * p.chunks_per_tap) * kBlockK, m0 + tap);
+                    } else {
+                        sb_tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0);
+                    }
+                    sb_tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBlockK, n0);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = sb_umma_idesc_bf16(kBlockM, (uint32_t)p.block_n);
+            uint32_t stage = 0, phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+                sb_mbar_wait(&tempty_bar[as], aphase ^ 1);
+                sb_tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * kMaxN;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    sb_mbar_wait(&full_bar[stage], phase);
+                    sb_tc_fence_after();
+                    const uint32_t sa = sb_smem_u32(smem + stage * kStageBytes);
+                    const uint64_t da = sb_umma_desc_sw128(sa);
+                    const uint64_t db = sb_umma_desc_sw128(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k)
+                        sb_umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                     (kb | k) != 0 ? 1u : 0u);
+                    sb_umma_commit(&empty_bar[stage]);  // frees the smem stage when the MMAs finish
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                sb_umma_commit(&tfull_bar[as]);  // accumulator complete
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int quad = warp & 3;                  // TMEM lane quadrant this warp may read
+        const int row_in_tile = quad * 32 + lane;
+        const int et = threadIdx.x - 64;            // 0..127
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+            const int m0 = (tile / p.n_tiles_n) * kBlockM;
+            const int n0 = (tile % p.n_tiles_n) * p.block_n;
+            float* bs = bias_s + as * kMaxN;
+            for (int i = et; i < p.block_n; i += 128) bs[i] = __ldg(p.bias + n0 + i);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+
+            // output row of this lane's pool window
+            const long long r = (long long)m0 + row_in_tile;
+            const long long rg = r - (r % p.pool);  // first row of the pool window
+            const long long seq = rg / p.t_in;
+            const int t = (int)(rg - seq * p.t_in);
+            const int tp = t / p.pool;
+            const bool valid = (rg < p.rows_a) && (tp < p.t_pool);
+            const long long out_row = seq * p.t_pool + tp;
+
+            sb_mbar_wait(&tfull_bar[as], aphase);
+            sb_tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * kMaxN;
+            const int n_chunks = p.block_n / 16;
+            for (int c = 0; c < n_chunks; ++c) {
+                const int nb = n0 + c * 16;
+                if (nb >= p.out_ld) break;  // uniform
+                uint32_t rr[16];
+                sb_tmem_ld16(taddr + c * 16, rr);
+                sb_tmem_wait_ld();
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]) + bs[c * 16 + j];
+                if (p.pool >= 2) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+                }
+                if (p.pool >= 4) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 2));
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (p.out_f32) {
+                    float* o = reinterpret_cast<float*>(p.out) + out_row * p.out_ld + nb;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        if (valid && nb + 4 * g + 4 <= p.out_ld)
+                            reinterpret_cast<float4*>(o)[g] =
+                                make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                } else if (p.pool == 4) {
+                    const int sub = lane & 3;  // each lane of the window stores 4 of the 16 channels
+                    const float w0 = sub == 0 ? v[0] : sub == 1 ? v[4] : sub == 2 ? v[8] : v[12];
+                    const float w1 = sub == 0 ? v[1] : sub == 1 ? v[5] : sub == 2 ? v[9] : v[13];
+                    const float w2 = sub == 0 ? v[2] : sub == 1 ? v[6] : sub == 2 ? v[10] : v[14];
+                    const float w3 = sub == 0 ? v[3] : sub == 1 ? v[7] : sub == 2 ? v[11] : v[15];
+                    if (valid && nb + 4 * sub + 4 <= p.out_ld) {
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                           out_row * p.out_ld + nb + 4 * sub;
+                        *reinterpret_cast<uint2*>(o) =
+                            make_uint2(pack_bf16x2(w0, w1), pack_bf16x2(w2, w3));
+                    }
+                } else if (p.pool == 2) {
+                    const int sub = lane & 1;
+                    float w[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) w[j] = sub == 0 ? v[j] : v[8 + j];
+                    if (valid && nb + 8 * sub + 8 <= p.out_ld) {
+                        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                           out_row * p.out_ld + nb + 8 * sub;
+                        *reinterpret_cast<uint4*>(o) =
+                            make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]),
+                                       pack_bf16x2(w[4], w[5]), pack_bf16x2(w[6], w[7]));
+                    }
+                } else {
+                    __nv_bfloat16* o =
+                        reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.out_ld + nb;
+#pragma unroll
+                    for (int g = 0; g < 2; ++g)
+                        if (valid && nb + 8 * g + 8 <= p.out_ld)
+                            reinterpret_cast<uint4*>(o)[g] = make_uint4(
+                                pack_bf16x2(v[8 * g], v[8 * g + 1]), pack_bf16x2(v[8 * g + 2], v[8 * g + 3]),
+                                pack_bf16x2(v[8 * g + 4], v[8 * g + 5]), pack_bf16x2(v[8 * g + 6], v[8 * g + 7]));
+                }
+            }
+            sb_tc_fence_before();
+            sb_mbar_arrive(&tempty_bar[as]);  // 128 arrivals hand the accumulator back to the MMA warp
+        }
+    }
+
+    sb_tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        sb_tc_fence_after();
+        sb_tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor maps
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// 2-D bf16 tensor: dim0 (contiguous) = inner elements, dim1 = rows with stride row_stride_elems.
+int make_tmap(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems,
+              uint32_t box_inner, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        sb_set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return SB_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t strides[1] = {row_stride_elems * 2};
+    cuuint32_t box[2] = {box_inner, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        sb_set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu rows=%llu stride=%llu box=%ux%u)",
+                     (int)r, (unsigned long long)inner, (unsigned long long)rows,
+                     (unsigned long long)row_stride_elems, box_inner, box_rows);
+        return SB_ERR_CUDA;
+    }
+    return SB_OK;
+}
+
+}  // namespace
+
+int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream) {
+    SB_REQUIRE(L.block_n >= 16 && L.block_n <= kMaxN && L.block_n % 16 == 0, "sb_tc_launch: bad block_n %d",
+               L.block_n);
+    SB_REQUIRE(L.a_ld % 8 == 0 && L.w_ld % 8 == 0, "sb_tc_launch: leading dimensions must be multiples of 8");
+    SB_REQUIRE(L.pool == 1 || L.pool == 2 || L.pool == 4, "sb_tc_launch: pool %d unsupported", L.pool);
+    SB_REQUIRE(L.t_in % L.pool == 0, "sb_tc_launch: t_in %d not a multiple of pool %d", L.t_in, L.pool);
+    SB_REQUIRE(L.out_f32 ? (L.out_ld % 4 == 0) : (L.out_ld % 8 == 0), "sb_tc_launch: bad out_ld %d", L.out_ld);
+    SB_REQUIRE(!(L.out_f32 && L.pool != 1), "sb_tc_launch: fp32 output cannot pool");
+    if (L.rows_a <= 0) return SB_OK;
+
+    // The last rows' windows would run past the buffer: shrink the row count so TMA zero-fills them
+    // (they are windows that straddle the end of the last sequence and are dropped anyway).
+    CUtensorMap tm_a, tm_b;
+    int rc;
+    int chunks_per_tap = 0;
+    if (L.per_tap) {
+        chunks_per_tap = (L.a_ld + kBlockK - 1) / kBlockK;
+        SB_REQUIRE(L.k_full == L.taps * chunks_per_tap * kBlockK, "sb_tc_launch: per-tap k_full mismatch");
+        rc = make_tmap(&tm_a, L.a, (uint64_t)L.a_ld, (uint64_t)L.rows_a, (uint64_t)L.a_ld, kBlockK, kBlockM);
+    } else {
+        const int64_t span = ((int64_t)L.k_full + L.a_ld - 1) / L.a_ld;  // rows touched by one A row
+        const int64_t rows_tma = L.rows_a - (span - 1);
+        SB_REQUIRE(rows_tma > 0, "sb_tc_launch: fewer rows than taps");
+        rc = make_tmap(&tm_a, L.a, (uint64_t)L.k_full, (uint64_t)rows_tma, (uint64_t)L.a_ld, kBlockK, kBlockM);
+    }
+    if (rc != SB_OK) return rc;
+    rc = make_tmap(&tm_b, L.w, (uint64_t)L.k_full, (uint64_t)L.n_rows_w, (uint64_t)L.w_ld, kBlockK,
+                   (uint32_t)L.block_n);
+    if (rc != SB_OK) return rc;
+
+    TcParams p;
+    p.rows_a = L.rows_a;
+    p.t_in = L.t_in;
+    p.t_conv = L.t_conv;
+    p.pool = L.pool;
+    p.t_pool = L.t_conv / L.pool;
+    p.out_ld = L.out_ld;
+    p.relu = L.relu;
+    p.out_f32 = L.out_f32;
+    p.block_n = L.block_n;
+    p.n_tiles_n = L.n_tiles_n;
+    p.n_tiles_m = (int)((L.rows_a + kBlockM - 1) / kBlockM);
+    p.num_k_blocks = (L.k_full + kBlockK - 1) / kBlockK;
+    p.chunks_per_tap = chunks_per_tap;
+    p.bias = L.bias;
+    p.out = L.out;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kSmemBytes));
+        attr_set = true;
+    }
+    const int64_t tiles = (int64_t)p.n_tiles_m * p.n_tiles_n;
+    const int sms = sb_sm_count(device);
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    tc_layer_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tm_a, tm_b, p);
+    SB_COUNT_LAUNCH();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// self-test entry: plain C = A . B^T through the same kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void zero_bias_kernel(float* b, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = 0.f;
+}
+
+extern "C" int sb_tc_gemm_selftest(const void* a_bf16, const void* b_bf16, int M, int N, int K, float* c,
+                                   void* stream) {
+    SB_REQUIRE(a_bf16 && b_bf16 && c, "sb_tc_gemm_selftest: null argument");
+    SB_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && N % 4 == 0, "sb_tc_gemm_selftest: need K%%8==0, N%%4==0");
+    int dev = 0;
+    SB_CHECK_CUDA(cudaGetDevice(&dev));
+    int block_n = N >= 256 ? 256 : ((N + 15) / 16) * 16;
+    const int n_tiles_n = (N + block_n - 1) / block_n;
+    float* bias = nullptr;
+    SB_CHECK_CUDA(cudaMalloc(&bias, sizeof(float) * (size_t)n_tiles_n * block_n));
+    zero_bias_kernel<<<(n_tiles_n * block_n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(bias, n_tiles_n * block_n);
+    SB_COUNT_LAUNCH();
+    SbTcLayer L;
+    memset(&L, 0, sizeof(L));
+    L.a = a_bf16; L.rows_a = M; L.a_ld = K; L.k_full = K;
+    L.w = b_bf16; L.n_rows_w = N; L.w_ld = K;
+    L.bias = bias; L.block_n = block_n; L.n_tiles_n = n_tiles_n;
+    L.t_in = 1; L.t_conv = 1; L.pool = 1; L.relu = 0; L.out_f32 = 1; L.out = c; L.out_ld = N;
+    int rc = sb_tc_launch(L, dev, (cudaStream_t)stream);
+    cudaStreamSynchronize((cudaStream_t)stream);
+    cudaFree(bias);
+    return rc;
+}

@@ -1,0 +1,35 @@
+// selene_b200 — tcgen05 implicit-GEMM core: interface between sb_net.cu and sb_tc.cu.
+#pragma once
+#include "sb_common.cuh"
+
+// One GEMM-shaped layer launch:  D[r][n] = sum_k A[r][k] * W[n][k]  (+ bias, ReLU, max-pool, store)
+//
+// A is the activation buffer viewed as an OVERLAPPING-stride matrix: row r starts at element
+// r * a_ld and is k_full = taps * a_ld elements long, i.e. the im2col row of a valid 1-D
+// convolution over a channel-last (rows = sequence x position, a_ld channels) tensor is just a
+// longer read of the same memory.  FC layers are the taps = 1 case.
+struct SbTcLayer {
+    const void* a;       // dev bf16, rows_a x a_ld (row stride a_ld elements)
+    int64_t rows_a;      // rows of the activation buffer (sequences x t_in)
+    int a_ld;            // elements per row (multiple of 8)
+    int k_full;          // logical K (<= taps * a_ld); TMA zero-fills beyond it
+    const void* w;       // dev bf16, n_rows_w x w_ld, K-major
+    int n_rows_w;        // logical output channels (cout)
+    int w_ld;            // elements per weight row (multiple of 8, >= k_full)
+    int per_tap;         // 0: overlapping-stride A view (K index = tap*a_ld + c, k_full = taps*a_ld)
+                         // 1: one 2-D box per (tap, 64-channel chunk); the weight K axis is then
+                         //    taps x (chunks_per_tap*64) with zero padding, k_full = that product
+    int taps;            // only used when per_tap
+    const float* bias;   // dev fp32, padded to n_tiles_n * block_n entries
+    int block_n;         // UMMA N (multiple of 16, <= 256)
+    int n_tiles_n;
+    int t_in;            // rows per sequence (1 for FC)
+    int t_conv;          // valid conv outputs per sequence: t_in - taps + 1
+    int pool;            // 1, 2 or 4 (requires t_in % pool == 0)
+    int relu;
+    int out_f32;         // 0: bf16 output, 1: fp32 output
+    void* out;           // dev, (sequences * t_pool) x out_ld
+    int out_ld;          // bf16: multiple of 8; fp32: multiple of 4
+};
+
+int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream);
