@@ -1,0 +1,366 @@
+"""GPU parity tests: every kernel is called through the C ABI (via the ctypes host classes) and
+compared with the CPU oracle on identical seeded inputs.  Integer / one-hot / label outputs must be
+bit-exact; fp32 predictions <= 1e-5 abs; bf16 predictions <= 2e-2 abs on sigmoid outputs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from oracle import selene_oracle as O  # noqa: E402
+import sb_helpers as H  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    return torch
+
+
+@pytest.fixture(scope="module")
+def genome_pair(tmp_path_factory):
+    from selene_b200.sequences import Genome
+    g = H.synth_genome()
+    path = str(tmp_path_factory.mktemp("g") / "synth.fa")
+    H.write_fasta(g, path)
+    Genome.update_bases_order(['A', 'C', 'G', 'T'])
+    return g, Genome(path)
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 GEMM core
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(128, 240, 64), (128, 16, 128), (256, 256, 256), (300, 480, 2560),
+                                   (1000, 920, 928), (77, 100, 72), (4096, 960, 3840)])
+def test_tc_gemm_selftest(torch, M, N, K):
+    from selene_b200 import _lib
+    lib = _lib.load()
+    gen = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = (torch.randn((M, K), device="cuda", generator=gen) * 0.5).to(torch.bfloat16)
+    b = (torch.randn((N, K), device="cuda", generator=gen) * 0.5).to(torch.bfloat16)
+    c = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32)
+    _lib.check(lib.sb_tc_gemm_selftest(_lib.ptr(a), _lib.ptr(b), M, N, K, _lib.ptr(c), _lib.stream_ptr()),
+               "sb_tc_gemm_selftest")
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().t()
+    err = (c - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), "max abs err %g" % err
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel (a): encode / codes / flags
+# ------------------------------------------------------------------------------------------------
+def test_encode_small_fasta_goldens(torch, tmp_path):
+    """Known answers of the reference's test_genome.py:40-60 (incl. lowercase and unknowns)."""
+    from selene_b200.sequences import Genome
+    Genome.update_bases_order(['A', 'C', 'G', 'T'])
+    got = Genome.sequence_to_encoding("ATACTTGA")
+    exp = np.array([[1, 0, 0, 0], [0, 0, 0, 1], [1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 0, 1],
+                    [0, 0, 1, 0], [1, 0, 0, 0]], dtype=np.float32)
+    assert got.dtype == np.float32 and np.array_equal(got, exp)
+    got = Genome.sequence_to_encoding("AnnUAtCa")
+    exp = O.sequence_to_encoding("AnnUAtCa")
+    assert np.array_equal(got, exp) and np.array_equal(got[1], np.full(4, 0.25, np.float32))
+    assert Genome.sequence_to_encoding("").shape == (0, 4)
+    assert Genome.encoding_to_sequence(exp) == "ANNNATCA"
+
+
+@pytest.mark.parametrize("L", [1, 7, 200, 1000])
+def test_encode_windows_vs_oracle(torch, genome_pair, L):
+    g, G = genome_pair
+    rng = np.random.default_rng(L)
+    chroms, starts, strands = [], [], []
+    names = list(g.keys())
+    for _ in range(64):
+        c = names[rng.integers(0, len(names))]
+        # include windows hanging over both ends (pad=True semantics)
+        s = int(rng.integers(-L, len(g[c])))
+        chroms.append(c)
+        starts.append(s)
+        strands.append("+-"[rng.integers(0, 2)])
+    enc, flags = G.encode_windows(chroms, starts, L, strands=strands)
+    enc_b, _ = G.encode_windows(chroms, starts, L, strands=strands, dtype="bfloat16")
+    codes, flags2 = G.window_codes(chroms, starts, L, strands=strands)
+    enc, flags, enc_b = enc.cpu().numpy(), flags.cpu().numpy(), enc_b.float().cpu().numpy()
+    codes = codes.cpu().numpy()
+    assert np.array_equal(flags, flags2.cpu().numpy())
+    for i in range(64):
+        seq = O.get_sequence_from_coords(g, chroms[i], starts[i], starts[i] + L, strands[i], pad=True)
+        if seq == "":      # start >= len etc.; the host rejects these before the kernel
+            continue
+        exp = O.sequence_to_encoding(seq)
+        assert np.array_equal(enc[i], exp), (chroms[i], starts[i], strands[i])
+        assert np.array_equal(enc_b[i], exp)
+        assert bool(flags[i] & 1) == ("N" in seq)
+        exp_codes = np.array([{"A": 0, "C": 1, "G": 2, "T": 3}.get(ch.upper(), 4) for ch in seq], np.uint8)
+        assert np.array_equal(codes[i], exp_codes)
+
+
+def test_genome_reference_api(torch, genome_pair):
+    g, G = genome_pair
+    assert G.get_chrs() == sorted(g.keys())
+    assert dict(G.get_chr_lens()) == {k: len(v) for k, v in g.items()}
+    c = "chr2"
+    n = len(g[c])
+    for (s, e, strand, pad) in [(0, 50, "+", False), (100, 1100, "-", False), (-5, 20, "+", True),
+                                (n - 10, n + 7, "-", True), (-5, 20, "+", False), (n, n + 5, "+", True),
+                                (30, 30, "+", False), (10, 40, ".", False)]:
+        exp_s = O.get_sequence_from_coords(g, c, s, e, strand, pad)
+        assert G.get_sequence_from_coords(c, s, e, strand, pad) == exp_s
+        exp, exp_unk = O.get_encoding_from_coords_check_unk(g, c, s, e, strand, pad)
+        got, unk = G.get_encoding_from_coords_check_unk(c, s, e, strand, pad)
+        assert got.shape == exp.shape and np.array_equal(got, exp) and unk == exp_unk
+    assert G.get_encoding_from_coords("chrZ", 0, 10).shape == (0, 4)
+    with pytest.raises(ValueError):
+        G.get_encoding_from_coords(c, 0, 10, strand="x")
+    assert G.coords_in_bounds(c, 0, n) and not G.coords_in_bounds(c, 0, n + 1)
+
+
+def test_bases_order_is_a_parameter(torch, genome_pair):
+    g, G = genome_pair
+    from selene_b200.sequences import Genome
+    try:
+        Genome.update_bases_order(['A', 'G', 'C', 'T'])
+        got = G.get_encoding_from_coords("chr1", 60, 260)
+        exp = O.sequence_to_encoding(g["chr1"][60:260], ['A', 'G', 'C', 'T'])
+        assert np.array_equal(got, exp)
+    finally:
+        Genome.update_bases_order(['A', 'C', 'G', 'T'])
+
+
+# ------------------------------------------------------------------------------------------------
+# ISM enumeration + expansion
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seq,rng_", [("ATCCG", None), ("ATCCG", (1, 3)), ("ANNTC", None), (None, None)])
+def test_ism_enumerate_and_expand(torch, seq, rng_):
+    from selene_b200.predict._in_silico_mutagenesis import ism_mutations_device, expand_mutants_device
+    from selene_b200.sequences import Genome
+    if seq is None:
+        r = np.random.default_rng(0)
+        seq = "".join(np.array(list("ACGTN"))[r.choice(5, 1000, p=[.24, .24, .24, .24, .04])].tolist())
+    s0, e0 = rng_ if rng_ else (0, len(seq))
+    exp = O.in_silico_mutagenesis_sequences(seq, 1, start_position=s0, end_position=e0)
+    pos, alt, codes = ism_mutations_device(seq, s0, e0)
+    got = [[(int(p), "ACGT"[int(a)])] for p, a in zip(pos.cpu().numpy(), alt.cpu().numpy())]
+    assert got == exp
+    enc = O.sequence_to_encoding(seq)
+    out = expand_mutants_device(codes, pos, alt).cpu().numpy()
+    assert out.shape == (len(exp), len(seq), 4)
+    for m in range(0, len(exp), max(1, len(exp) // 97)):
+        assert np.array_equal(out[m], O.mutate_sequence(enc, exp[m]))
+
+
+def test_ism_golden_ATCCG(torch):
+    """selene_sdk/predict/tests/test_model_predict.py:12-31."""
+    from selene_b200.predict._in_silico_mutagenesis import in_silico_mutagenesis_sequences
+    observed = in_silico_mutagenesis_sequences("ATCCG")
+    expected = [[(0, 'C')], [(0, 'G')], [(0, 'T')], [(1, 'A')], [(1, 'C')], [(1, 'G')], [(2, 'A')], [(2, 'G')],
+                [(2, 'T')], [(3, 'A')], [(3, 'G')], [(3, 'T')], [(4, 'A')], [(4, 'C')], [(4, 'T')]]
+    assert observed == expected
+
+
+# ------------------------------------------------------------------------------------------------
+# SNV ref/alt pairs
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("L", [1000, 201])
+def test_snv_pairs_vs_oracle(torch, genome_pair, L):
+    g, G = genome_pair
+    rng = np.random.default_rng(2024 + L)
+    names = list(g.keys())
+    sr, er = O.radii(L)
+    var_row = O.get_ref_idxs(L, 1)[0]
+    variants = []
+    for i in range(96):
+        c = names[rng.integers(0, len(names))]
+        pos = int(rng.integers(1, len(g[c]) + 1))        # 1-based; windows may hang over the ends
+        true_ref = g[c][pos - 1]
+        ref = true_ref.upper() if rng.random() > 0.15 else "ACGT"[rng.integers(0, 4)]
+        if ref not in "ACGT":
+            ref = "N" if rng.random() < 0.5 else "A"
+        alt = "ACGTN"[rng.integers(0, 5)]
+        variants.append((c, pos, ref, alt, "+-"[rng.integers(0, 2)]))
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+    res = G.snv_pairs([v[0] for v in variants], [v[1] - sr for v in variants],
+                      [code.get(v[2], 4) for v in variants], [code.get(v[3], 4) for v in variants], L, var_row,
+                      strands=[v[4] for v in variants], want_codes=True)
+    ref_o, alt_o = res["ref"].cpu().numpy(), res["alt"].cpu().numpy()
+    match, flags = res["ref_match"].cpu().numpy(), res["flags"].cpu().numpy()
+    for i, (c, pos, ref, alt, strand) in enumerate(variants):
+        start, end = pos - sr, pos + er
+        # the reference queries without pad (model_predict.py:1061-1064); out-of-bounds variants are
+        # filtered by read_vcf_file, so only in-bounds windows are comparable
+        if start < 0 or end > len(g[c]):
+            continue
+        r, a, m, u = O.snv_ref_alt_encodings(g, c, pos, ref, alt, strand, L)
+        assert np.array_equal(ref_o[i], r), variants[i]
+        assert np.array_equal(alt_o[i], a), variants[i]
+        assert bool(match[i]) == m and bool(flags[i] & 1) == u
+
+
+# ------------------------------------------------------------------------------------------------
+# kernel (b): labels
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("thr", [0.5, 0.29, 1.0, {"default": 0.4, "f3": 0.01}, None])
+def test_labels_vs_oracle(torch, tmp_path, thr):
+    from selene_b200.targets import GenomicFeatures
+    g = H.synth_genome(length=30000)
+    rows = H.synth_intervals(g)
+    path = str(tmp_path / "feat.bed.gz")
+    H.write_bed(rows, path)
+    feats = ["f%d" % i for i in range(12)]
+    GF = GenomicFeatures(path, feats, feature_thresholds=thr)
+    by = H.rows_by_chrom(rows)
+    fid = {f: i for i, f in enumerate(feats)}
+    rng = np.random.default_rng(5)
+    names = list(g.keys())
+    qc, qs, qe = [], [], []
+    for _ in range(300):
+        c = names[rng.integers(0, len(names))]
+        s = int(rng.integers(0, len(g[c]) - 200))
+        qc.append(c); qs.append(s); qe.append(s + 200)
+    got = GF.label_bins(qc, qs, qe, out_dtype="int64").cpu().numpy()
+    for i in range(300):
+        r = O.query_rows(by, qc[i], qs[i], qe[i])
+        if thr is None:
+            exp = O.feature_data_no_threshold(12, fid, r)
+        else:
+            exp = O.fast_get_feature_data(qs[i], qe[i], GF._feature_thresholds_vec, fid, r)
+        assert np.array_equal(got[i], exp), (qc[i], qs[i])
+    one = GF.get_feature_data(qc[0], qs[0], qe[0])
+    assert one.dtype == (np.float64 if thr is None else np.int64) and np.array_equal(one, got[0])
+    z = GF.get_feature_data("chrNope", 0, 200)
+    assert z.dtype == np.float64 and not z.any()
+
+
+def test_labels_reference_goldens(torch, tmp_path):
+    """Rows and expected vectors of selene_sdk/targets/tests/test_genomic_features.py:24-42,151-187."""
+    from selene_b200.targets import GenomicFeatures
+    feats = ["CTCF", "eGFP-FOS", "GABP", "Pbx3", "Pol2", "TBP"]
+    rows = [("1", 0, 5, "Pol2"), ("1", 7, 8, "CTCF"), ("1", 14, 18, "TBP"), ("1", 150, 152, "GABP"),
+            ("1", 5, 1000, "CTCF"), ("1", 152, 200, "Pbx3"), ("1", 195, 400, "eGFP-FOS")]
+    # plus the fixture rows of the reference test module
+    rows2 = [("1", 0, 5, "CTCF"), ("1", 4, 8, "eGFP-FOS"), ("1", 0, 10, "GABP"), ("1", 5, 10, "Pbx3"),
+             ("1", 5, 6, "Pol2"), ("1", 7, 15, "TBP")]
+    for rr, queries in ((rows, [(0, 200), (150, 350)]), (rows2, [(0, 5), (5, 10), (0, 10), (2, 8)])):
+        path = str(tmp_path / ("g%d.bed" % len(rr)))
+        H.write_bed(sorted(rr, key=lambda r: r[1]), path)
+        for thr in (0.5, 0.1, 1.0):
+            GF = GenomicFeatures(path, feats, feature_thresholds=thr)
+            by = H.rows_by_chrom(rr)
+            fid = {f: i for i, f in enumerate(feats)}
+            for s, e in queries:
+                exp = O.fast_get_feature_data(s, e, GF._feature_thresholds_vec, fid, O.query_rows(by, "1", s, e))
+                assert np.array_equal(GF.get_feature_data("1", s, e), exp)
+
+
+# ------------------------------------------------------------------------------------------------
+# kernels (c)+(d): DeepSEA forward + scores
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def deepsea(torch):
+    from selene_b200.nets import B200Net
+    layers = O.deepsea_layers(1000, 919, seed=0)
+    return layers, B200Net(layers, 1000)
+
+
+def _rand_codes(n, L, seed, p_unk=0.01):
+    r = np.random.default_rng(seed)
+    return r.choice(5, (n, L), p=[(1 - p_unk) / 4] * 4 + [p_unk]).astype(np.uint8)
+
+
+def _onehot(codes):
+    out = np.zeros(codes.shape + (4,), np.float32)
+    for b in range(4):
+        out[codes == b, b] = 1
+    out[codes == 4] = 0.25
+    return out
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+def test_deepsea_forward_vs_oracle(torch, deepsea, precision, tol):
+    layers, net = deepsea
+    codes = _rand_codes(6, 1000, 11)
+    exp = O.stack_forward(_onehot(codes), layers)
+    got = net.forward_codes(torch.from_numpy(codes).cuda(), precision=precision).cpu().numpy()
+    assert got.shape == (6, 919)
+    err = np.abs(got - exp).max()
+    assert err <= tol, "max abs err %g" % err
+    got2 = net.forward_onehot(torch.from_numpy(_onehot(codes)).cuda(), precision=precision).cpu().numpy()
+    assert np.abs(got2 - exp).max() <= tol
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+def test_deepsea_scaled_weights_saturation(torch, precision, tol):
+    """up-scaled conv weights exercise saturation and large diffs."""
+    from selene_b200.nets import B200Net
+    layers = O.deepsea_layers(1000, 919, seed=3, scale=3.0)
+    net = B200Net(layers, 1000)
+    codes = _rand_codes(4, 1000, 12)
+    exp = O.stack_forward(_onehot(codes), layers)
+    got = net.forward_codes(torch.from_numpy(codes).cuda(), precision=precision).cpu().numpy()
+    assert exp.std() > 0.05  # the scaling really spreads the outputs
+    assert np.abs(got - exp).max() <= tol
+
+
+def test_forward_substitution_rows(torch, deepsea):
+    layers, net = deepsea
+    codes = _rand_codes(2, 1000, 13)
+    src = np.array([0, 0, 1, 1, 0], np.int32)
+    pos = np.array([-1, 499, 0, 999, 7], np.int32)
+    sub = np.array([0, 2, 4, 1, 3], np.uint8)
+    rows = codes[src].copy()
+    for i in range(5):
+        if pos[i] >= 0:
+            rows[i, pos[i]] = sub[i]
+    exp = O.stack_forward(_onehot(rows), layers)
+    t = lambda a: torch.from_numpy(a).cuda()
+    got = net.forward_codes(t(codes), t(src), t(pos), t(sub), n=5, precision="fp32").cpu().numpy()
+    assert np.abs(got - exp).max() <= 1e-5
+
+
+def test_fused_scores_interleaved_and_baseline(torch, deepsea):
+    from selene_b200 import _lib
+    layers, net = deepsea
+    codes = _rand_codes(3, 1000, 14)
+    t = lambda a: torch.from_numpy(a).cuda()
+    # interleaved ref/alt: rows (ref0, alt0, ref1, alt1, ref2, alt2)
+    src = np.repeat(np.arange(3, dtype=np.int32), 2)
+    pos = np.full(6, 499, np.int32)
+    sub = np.array([codes[0, 499], (codes[0, 499] + 1) % 4, 1, 2, 4, 0], np.uint8)
+    rows = codes[src].copy()
+    rows[np.arange(6), 499] = sub
+    pred = O.stack_forward(_onehot(rows), layers)
+    ref, alt = pred[0::2].copy(), pred[1::2].copy()
+    res = net.forward_score(t(codes), t(src), t(pos), t(sub), 6, _lib.SB_PAIR_INTERLEAVED, precision="fp32",
+                            want=("abs_diffs", "diffs", "logits", "ref_predictions", "alt_predictions"))
+    assert np.abs(res["abs_diffs"].cpu().numpy() - O.abs_diff_score(alt, ref)).max() <= 1e-5
+    assert np.abs(res["diffs"].cpu().numpy() - O.diff_score(alt, ref)).max() <= 1e-5
+    lg = O.logit_score(alt, ref)
+    assert np.abs(res["logits"].cpu().numpy() - lg).max() <= 1e-4
+    assert np.abs(res["ref_predictions"].cpu().numpy() - ref).max() <= 1e-5
+    # baseline mode (ISM): every row scored against one baseline row
+    base = t(pred[0:1].copy())
+    res = net.forward_score(t(codes), t(src), t(pos), t(sub), 6, _lib.SB_PAIR_BASELINE, precision="fp32",
+                            base_pred=base, want=("abs_diffs", "logits"))
+    assert np.abs(res["abs_diffs"].cpu().numpy() - np.abs(pred[0:1] - pred)).max() <= 1e-5
+
+
+def test_score_pairs_clamp_semantics(torch):
+    """logit_score_handler.py:118-124: 0 -> 1e-24, >= 1 -> 0.999999, float32 logit."""
+    from selene_b200 import _lib
+    ref = np.array([[0.0, 1.0, 0.5, 0.25, 1e-30, 0.9999999]], np.float32)
+    alt = np.array([[0.5, 0.5, 0.0, 1.0, 0.7, 0.1]], np.float32)
+    exp_abs, exp_diff = O.abs_diff_score(alt.copy(), ref.copy()), O.diff_score(alt.copy(), ref.copy())
+    exp_logit = O.logit_score(alt.copy(), ref.copy())
+    t = lambda a: torch.from_numpy(a).cuda()
+    outs = [torch.empty((1, 6), device="cuda") for _ in range(3)]
+    _lib.check(_lib.load().sb_score_pairs(_lib.ptr(t(ref)), _lib.ptr(t(alt)), None, 1, 1, 6, _lib.ptr(outs[0]),
+                                          _lib.ptr(outs[1]), _lib.ptr(outs[2]), 0, _lib.stream_ptr()),
+               "sb_score_pairs")
+    assert np.array_equal(outs[0].cpu().numpy(), exp_abs)
+    assert np.array_equal(outs[1].cpu().numpy(), exp_diff)
+    assert np.allclose(outs[2].cpu().numpy(), exp_logit, rtol=2e-6, atol=1e-5)
