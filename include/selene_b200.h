@@ -129,7 +129,9 @@ int sb_ism_expand(const uint8_t* codes /* dev (n_src,L) */, int L, const int32_t
  * substitution, :195-200, built from the UNMODIFIED window); ref_match[i] = (genome row == VCF
  * ref row).  strand_rc applies get_reverse_complement_encoding (_common.py:37-62) to both
  * (model_predict.py:1102-1110).  ref_out / alt_out / codes_out / ref_match / flags_out may be NULL.
- * codes_out receives the (n,L) '+'-strand window codes for sb_net_forward_*. */
+ * codes_out receives the (n,L) UNSUBSTITUTED window codes with the strand already applied (reverse
+ * complemented rows for strand_rc != 0), ready for sb_net_forward_* with the substitution given as
+ * (sub_pos = var_row, or L-1-var_row on the minus strand; sub_code = base, complemented likewise). */
 int sb_snv_pairs(const sb_genome* g, const int32_t* chrom, const int64_t* start,
                  const uint8_t* ref_code, const uint8_t* alt_code, const uint8_t* strand_rc, int n,
                  int L, int var_row, const uint8_t perm[4], int out_dtype, void* ref_out,
@@ -180,6 +182,14 @@ int sb_net_destroy(sb_net* net);
 int sb_net_n_outputs(const sb_net* net);
 /* FLOPs (2 x MACs) of one forward of one sequence */
 double sb_net_flops_per_seq(const sb_net* net);
+
+/* Per-layer device timing for roofline reports: when enabled, every layer launch is bracketed by
+ * CUDA events on the launching stream; sb_net_layer_time sums them (synchronising on the events)
+ * since the last sb_net_set_timing call. */
+int sb_net_set_timing(sb_net* net, int enable);
+int sb_net_n_layers(const sb_net* net);
+double sb_net_layer_flops_per_seq(const sb_net* net, int layer);
+int sb_net_layer_time(sb_net* net, int layer, double* total_ms, int* launches);
 
 #define SB_PREC_FP32 0 /* CUDA-core FFMA path, fp32 end to end (<= 1e-5 abs vs torch CPU)          */
 #define SB_PREC_BF16 1 /* tcgen05 path: bf16 operands, fp32 accumulate in TMEM (<= 2e-2 abs)        */

@@ -52,6 +52,10 @@ SIGNATURES = {
     "sb_net_destroy": (_I, [_P]),
     "sb_net_n_outputs": (_I, [_P]),
     "sb_net_flops_per_seq": (C.c_double, [_P]),
+    "sb_net_set_timing": (_I, [_P, _I]),
+    "sb_net_n_layers": (_I, [_P]),
+    "sb_net_layer_flops_per_seq": (C.c_double, [_P, _I]),
+    "sb_net_layer_time": (_I, [_P, _I, _P, _P]),
     "sb_net_workspace_bytes": (C.c_size_t, [_P, _L, _I]),
     "sb_net_forward_codes": (_I, [_P, _P, _P, _P, _P, _L, _I, _P, C.c_size_t, _P, _P]),
     "sb_net_forward_onehot": (_I, [_P, _P, _L, _I, _P, C.c_size_t, _P, _P]),

@@ -252,7 +252,10 @@ __global__ void __launch_bounds__(256) snv_pairs_kernel(
         const int code = window_code(g, coff, clen, st, L, false, i, &upn);
         if (code > 3) flags |= SB_FLAG_HAS_UNK;
         if (upn) flags |= SB_FLAG_HAS_UPPER_N;
-        if (codes_out) codes_out[(int64_t)v * L + i] = (uint8_t)code;
+        if (codes_out) {  // strand-applied, unsubstituted window codes for sb_net_forward_*
+            const int oc = rc ? L - 1 - i : i;
+            codes_out[(int64_t)v * L + oc] = (uint8_t)(rc ? (code < 4 ? 3 - code : 4) : code);
+        }
         if (i == var_row && ref_match) ref_match[v] = (uint8_t)(code == rcode);
         if (MODE != 0) {
             int rc_ref = (i == var_row) ? rcode : code;

@@ -48,6 +48,10 @@ struct sb_net {
     double flops_per_seq;
     bool force_per_tap;
     std::vector<NetLayer> layers;
+    // optional per-layer device timing (bench.py's roofline leg): one event pair per launch
+    bool timing;
+    std::vector<std::vector<cudaEvent_t>> ev;  // per layer: start0, stop0, start1, stop1, ...
+    std::vector<size_t> ev_used;
 };
 
 namespace {
@@ -297,6 +301,7 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
     net->flops_per_seq = 0.0;
     const char* env = getenv("SB_TC_PER_TAP");
     net->force_per_tap = env && env[0] == '1';
+    net->timing = false;
 
     int t = L, c = 4;          // current activation: t rows of c channels per sequence
     bool seen_fc = false;
@@ -420,6 +425,39 @@ extern "C" int sb_net_destroy(sb_net* net) {
     return SB_OK;
 }
 
+extern "C" int sb_net_set_timing(sb_net* net, int enable) {
+    SB_REQUIRE(net, "sb_net_set_timing: null handle");
+    net->timing = enable != 0;
+    for (auto& u : net->ev_used) u = 0;
+    return SB_OK;
+}
+
+extern "C" int sb_net_n_layers(const sb_net* net) { return net ? (int)net->layers.size() : -1; }
+
+extern "C" double sb_net_layer_flops_per_seq(const sb_net* net, int layer) {
+    if (!net || layer < 0 || layer >= (int)net->layers.size()) return 0.0;
+    const NetLayer& N = net->layers[(size_t)layer];
+    return 2.0 * N.t_conv * (double)N.cout * N.cin * (N.type == SB_LAYER_CONV ? N.k : 1);
+}
+
+extern "C" int sb_net_layer_time(sb_net* net, int layer, double* total_ms, int* launches) {
+    SB_REQUIRE(net && total_ms && launches, "sb_net_layer_time: null argument");
+    SB_REQUIRE(layer >= 0 && layer < (int)net->layers.size(), "sb_net_layer_time: bad layer %d", layer);
+    *total_ms = 0.0;
+    *launches = 0;
+    if ((size_t)layer >= net->ev.size()) return SB_OK;
+    const auto& v = net->ev[(size_t)layer];
+    const size_t u = net->ev_used[(size_t)layer];
+    for (size_t i = 0; i + 1 < u; i += 2) {
+        SB_CHECK_CUDA(cudaEventSynchronize(v[i + 1]));
+        float ms = 0.f;
+        SB_CHECK_CUDA(cudaEventElapsedTime(&ms, v[i], v[i + 1]));
+        *total_ms += ms;
+        *launches += 1;
+    }
+    return SB_OK;
+}
+
 extern "C" int sb_net_n_outputs(const sb_net* net) { return net ? net->n_out : -1; }
 extern "C" double sb_net_flops_per_seq(const sb_net* net) { return net ? net->flops_per_seq : 0.0; }
 
@@ -467,6 +505,26 @@ struct RowSource {
     const float* onehot;                                                                        // generic input
 };
 
+void time_begin(sb_net* net, size_t li, cudaStream_t s) {
+    if (!net->timing) return;
+    if (net->ev.size() < net->layers.size()) { net->ev.resize(net->layers.size()); net->ev_used.assign(net->layers.size(), 0); }
+    auto& v = net->ev[li];
+    size_t& u = net->ev_used[li];
+    if (u + 2 > v.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        v.push_back(a);
+        v.push_back(b);
+    }
+    cudaEventRecord(v[u], s);
+}
+void time_end(sb_net* net, size_t li, cudaStream_t s) {
+    if (!net->timing) return;
+    cudaEventRecord(net->ev[li][net->ev_used[li] + 1], s);
+    net->ev_used[li] += 2;
+}
+
 // Runs rows [r0, r0+m) through the network; leaves fp32 logits (row stride ldl) in ws logits buffer.
 int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int precision, uint8_t* ws,
               const WsPlan& plan, float** logits_out, int* ldl_out, cudaStream_t stream) {
@@ -480,6 +538,7 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
     int cur = 0;
 
     // ---- layer 0
+    time_begin(net, 0, stream);
     {
         const NetLayer& N = net->layers[0];
         const int out_ld = bf ? N.out_ld_b : N.cout;
@@ -523,10 +582,13 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
         }
     }
 
+    time_end(net, 0, stream);
+
     // ---- remaining layers
     for (size_t li = 1; li < net->layers.size(); ++li) {
         const NetLayer& N = net->layers[li];
         const bool last = li + 1 == net->layers.size();
+        time_begin(net, li, stream);
         if (bf) {
             SbTcLayer T;
             memset(&T, 0, sizeof(T));
@@ -578,6 +640,7 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
                 SB_CHECK_LAUNCH();
             }
         }
+        time_end(net, li, stream);
         cur ^= 1;
     }
     *logits_out = logits;

@@ -1,0 +1,424 @@
+"""``AnalyzeSequences`` — drop-in for ``selene_sdk.predict.AnalyzeSequences`` (reference:
+selene_sdk/predict/model_predict.py:42-1153) for the two scoring entry points on the hot path:
+``in_silico_mutagenesis`` (:662-799) and ``variant_effect_prediction`` (:952-1141).
+
+The per-mutant / per-variant Python loops of the reference (:636-657, :1054-1129) are replaced by
+whole-job device calls: windows and mutants are described by (code row, substituted position, base)
+triples, the conv stack consumes them directly, and scores come out of the fused epilogue.  Batches
+of ``batch_size`` exist only where the reference's behaviour depends on them (the in-place clamp of
+the ISM baseline, §9.21 of SURVEY.md).  File outputs keep the reference's names, columns and number
+formats (handler.py:15-114,190-235; write_ref_alt_handler.py:83-108).
+"""
+import io
+import math
+import os
+import warnings
+
+import numpy as np
+
+from .. import _lib
+from ..nets import B200Net, layers_from_module
+from ..sequences import Genome, codes_of_string
+from ._in_silico_mutagenesis import ism_mutations_device
+from ._variant_effect_prediction import read_vcf_file, build_ref_alt_strings, _get_ref_idxs
+
+ISM_COLS = ["pos", "ref", "alt"]                                                  # model_predict.py:39
+VARIANTEFFECT_COLS = ["chrom", "pos", "name", "ref", "alt", "strand", "ref_match", "contains_unk"]  # :40
+_CODE = {"A": 0, "C": 1, "G": 2, "T": 3, "a": 0, "c": 1, "g": 2, "t": 3}
+
+
+def _is_lua_trained_model(model):
+    """selene_sdk/utils/utils.py:16-31."""
+    import torch
+    if hasattr(model, 'from_lua'):
+        return model.from_lua
+    check_model = model
+    if hasattr(model, 'model'):
+        check_model = model.model
+    elif type(model) == torch.nn.DataParallel and hasattr(model, 'module'):
+        check_model = model.module
+    else:
+        for m in model.modules():
+            if "Conv2d" in m.__class__.__name__:
+                return True
+    return False
+
+
+# --------------------------------------------------------------------------------------------------
+# writers (same files, columns and number formats as predict_handlers/handler.py)
+# --------------------------------------------------------------------------------------------------
+def _scores_filepath(output_path_prefix, handler_filename):
+    """handler.py:190-203."""
+    output_path, filename_prefix = None, None
+    if not os.path.isdir(output_path_prefix):
+        output_path, filename_prefix = os.path.split(output_path_prefix)
+    else:
+        output_path = output_path_prefix
+    if filename_prefix is not None:
+        handler_filename = "{0}_{1}".format(filename_prefix, handler_filename)
+    return output_path, filename_prefix, os.path.join(output_path, handler_filename)
+
+
+def write_tsv(path, columns_for_ids, features, ids, data, append=False):
+    """Rows ``id columns + "{:.2e}" per value`` (handler.py:36-42,99-114)."""
+    buf = io.StringIO()
+    np.savetxt(buf, np.asarray(data, dtype=np.float64), fmt="%.2e", delimiter="\t")
+    lines = buf.getvalue().split("\n")
+    with open(path, "a" if append else "w") as fh:
+        if not append:
+            fh.write("{0}\n".format("\t".join(list(columns_for_ids) + list(features))))
+        for info, line in zip(ids, lines):
+            fh.write("{0}\t{1}\n".format("\t".join(str(i) for i in info), line))
+
+
+def write_hdf5(path, data):
+    """Dataset ``data`` float64 (n_rows, n_features) (handler.py:205-218)."""
+    import h5py
+    with h5py.File(path, "w") as fh:
+        fh.create_dataset("data", data=np.asarray(data, dtype=np.float64))
+
+
+def write_row_labels(path, columns_for_ids, ids):
+    with open(path, "w") as fh:
+        fh.write("{0}\n".format("\t".join(columns_for_ids)))
+        for info in ids:
+            fh.write("{0}\n".format("\t".join(str(i) for i in info)))
+
+
+def _write_outputs(results, ids, features, cols, output_path_prefix, output_format):
+    """results: ordered list of (handler_filename, prefix_override or None, array)."""
+    labels_written = False
+    for name, prefix, arr in results:
+        opp = output_path_prefix if prefix is None else prefix
+        out_dir, fprefix, sp = _scores_filepath(opp, name)
+        if output_format == "tsv":
+            write_tsv(sp + ".tsv", cols, features, ids, arr)
+        else:
+            write_hdf5(sp + ".h5", arr)
+            if not labels_written:
+                lf = "row_labels.txt"
+                if fprefix is not None:
+                    if fprefix[-4:] in (".ref", ".alt"):
+                        fprefix = fprefix[:-4]
+                    lf = "{0}_{1}".format(fprefix, lf)
+                write_row_labels(os.path.join(out_dir, lf), cols, ids)
+                labels_written = True
+
+
+class AnalyzeSequences(object):
+    """Score sequences and variants with a trained sequence-based model on a B200.
+
+    Parameters follow model_predict.py:42-131: ``model`` is the ``torch.nn.Module`` (e.g.
+    ``DeepSEA(1000, 919)``), ``trained_model_path`` optional weights (``state_dict`` or a checkpoint
+    dict with a ``state_dict`` key), ``sequence_length``, ``features``, ``batch_size``,
+    ``reference_sequence`` (a :class:`selene_b200.sequences.Genome` instance or the class).
+    ``use_cuda`` must stay True: there is no CPU path.  ``precision``: ``"bf16"`` (tcgen05, default)
+    or ``"fp32"`` (accuracy mode)."""
+
+    def __init__(self, model, trained_model_path=None, sequence_length=None, features=None, batch_size=64,
+                 use_cuda=True, data_parallel=False, reference_sequence=Genome, write_mem_limit=1500,
+                 precision="bf16", device=None):
+        import torch
+        if not use_cuda:
+            raise ValueError("selene_b200 has no CPU path: use_cuda must be True")
+        if trained_model_path is not None:
+            ck = torch.load(trained_model_path, map_location="cpu")
+            state = ck["state_dict"] if isinstance(ck, dict) and "state_dict" in ck else ck
+            # selene_sdk/utils/utils.py:111-126: weights are matched to the model's own keys by position
+            own = model.state_dict()
+            if len(own) != len(state):
+                raise ValueError("The model and the weights file do not have the same number of tensors")
+            model.load_state_dict({k: v for k, v in zip(own.keys(), state.values())})
+        model.eval()
+        self.model = model
+        self.sequence_length = sequence_length
+        self._start_radius = sequence_length // 2
+        self._end_radius = self._start_radius
+        if sequence_length % 2 != 0:
+            self._start_radius += 1
+        self.batch_size = batch_size
+        self.features = list(features)
+        self.reference_sequence = reference_sequence
+        self.precision = precision
+        if type(self.reference_sequence) == Genome and not self.reference_sequence._initialized:
+            self.reference_sequence._unpicklable_init()
+        if type(self.reference_sequence) == Genome and _is_lua_trained_model(model):
+            Genome.update_bases_order(['A', 'G', 'C', 'T'])     # model_predict.py:179-181
+        else:
+            Genome.update_bases_order(['A', 'C', 'G', 'T'])     # :182-183
+        self._write_mem_limit = write_mem_limit
+        # the weights are re-normalised for models that do it on every forward (heartenn.py:73-78)
+        if hasattr(model, "_renorm") or model.__class__.__name__ == "HeartENN":
+            with torch.no_grad():
+                for m in model.modules():
+                    if isinstance(m, (torch.nn.Conv1d, torch.nn.Linear)):
+                        m.weight.data.renorm_(2, 0, 0.9)
+        self.net = B200Net(layers_from_module(model), sequence_length, perm=Genome.perm(), device=device)
+        if self.net.n_outputs != len(self.features):
+            raise ValueError("model predicts %d features, %d feature names given" %
+                             (self.net.n_outputs, len(self.features)))
+
+    # ----------------------------------------------------------------------------------------------
+    # in-memory scoring (what the file-level methods and bench.py's e2e leg call)
+    # ----------------------------------------------------------------------------------------------
+    def _want(self, save_data):
+        save_data = sorted(set(save_data) & set(["diffs", "abs_diffs", "logits", "predictions"]))
+        if len(save_data) == 0:
+            raise ValueError("'save_data' parameter must be a list that contains one of "
+                             "['diffs', 'abs_diffs', 'logits', 'predictions'].")
+        return save_data
+
+    def prepare_snvs(self, chroms, positions, ref_codes, alt_codes, strands=None, pinned=None):
+        """Host -> device ingest of an SNV list (the only H2D traffic of the VEP path): chromosome
+        names or indices, 1-based positions, canonical base codes, optional strands.  Returns a dict of
+        CUDA tensors describing the 2n interleaved (ref, alt) model rows."""
+        import torch
+        G = self.reference_sequence
+        G._unpicklable_init()
+        L = self.sequence_length
+        dev = torch.device("cuda", int(G.device))
+        n = len(positions)
+        var_row = _get_ref_idxs(L, 1)[0]
+        if len(chroms) and isinstance(chroms[0], str):
+            cidx = G.chrom_indices(chroms)
+        else:
+            cidx = np.asarray(chroms, dtype=np.int32)
+        starts = np.asarray(positions, dtype=np.int64) - self._start_radius
+        ref = np.asarray(ref_codes, dtype=np.uint8)
+        alt = np.asarray(alt_codes, dtype=np.uint8)
+        rc = np.zeros(n, dtype=np.uint8)
+        if strands is not None:
+            rc = np.fromiter(((1 if s in ('-', 1, True) else 0) for s in strands), dtype=np.uint8, count=n)
+        # model rows (ref_i, alt_i): code row i with the VCF ref / the alt forced at the variant row;
+        # on the minus strand the finished encodings are reverse-complemented (model_predict.py:1102-1110),
+        # i.e. the row is mirrored and the forced base complemented
+        comp = np.array([3, 2, 1, 0, 4], dtype=np.uint8)
+        sub = np.empty(2 * n, dtype=np.uint8)
+        sub[0::2] = np.where(rc == 1, comp[np.minimum(ref, 4)], ref)
+        sub[1::2] = np.where(rc == 1, comp[np.minimum(alt, 4)], alt)
+        pos = np.repeat(np.where(rc == 1, L - 1 - var_row, var_row).astype(np.int32), 2)
+        src = np.repeat(np.arange(n, dtype=np.int32), 2)
+
+        def up(a):
+            t = torch.from_numpy(np.ascontiguousarray(a))
+            if pinned:
+                t = t.pin_memory()
+            return t.to(dev, non_blocking=True)
+        host = dict(chrom=cidx.astype(np.int32), start=starts, ref=ref, alt=alt, src=src, pos=pos, sub=sub)
+        out = {k: up(v) for k, v in host.items()}
+        out.update(n=n, var_row=var_row, rc=up(rc) if rc.any() else None,
+                   h2d_bytes=int(sum(v.nbytes for v in host.values()) + (rc.nbytes if rc.any() else 0)))
+        return out
+
+    def score_prepared(self, prep, save_data=("abs_diffs", "logits"), outs=None):
+        """Device-resident leg of SNV scoring: ``sb_snv_pairs`` (window codes, ref_match, flags) then the
+        fused forward + score.  Returns dict of CUDA tensors."""
+        want = self._want(save_data)
+        G = self.reference_sequence
+        res = G.snv_pairs(prep["chrom"], prep["start"], prep["ref"], prep["alt"], self.sequence_length,
+                          prep["var_row"], strands=prep["rc"], want_onehot=False, want_codes=True)
+        req = [s for s in want if s != "predictions"]
+        if "predictions" in want:
+            req += ["ref_predictions", "alt_predictions"]
+        out = self.net.forward_score(res["codes"], prep["src"], prep["pos"], prep["sub"], 2 * prep["n"],
+                                     _lib.SB_PAIR_INTERLEAVED, precision=self.precision, want=tuple(req),
+                                     outs=outs)
+        out["ref_match"] = res["ref_match"]
+        out["flags"] = res["flags"]
+        return out
+
+    def score_snvs(self, chroms, positions, ref_codes, alt_codes, strands=None,
+                   save_data=("abs_diffs", "logits"), to_host=True):
+        """Scores SNVs given as host arrays.  Returns dict with the requested score arrays (n, F) plus
+        ``ref_match`` and ``contains_unk`` (bool), computed as model_predict.py:1054-1124."""
+        prep = self.prepare_snvs(chroms, positions, ref_codes, alt_codes, strands)
+        out = self.score_prepared(prep, save_data)
+        out["ref_match"] = out["ref_match"].bool()
+        out["contains_unk"] = (out.pop("flags") & _lib.SB_FLAG_HAS_UPPER_N).bool()
+        if to_host:
+            out = {k: v.cpu().numpy() for k, v in out.items()}
+        return out
+
+    def score_code_pairs(self, ref_codes, alt_codes, save_data=("abs_diffs", "logits"), to_host=True):
+        """Scores explicit (ref row, alt row) code pairs: uint8 arrays (n, L).  Used for indels / MNVs
+        whose windows the host builds string-wise (_variant_effect_prediction.py:146-266)."""
+        import torch
+        want = self._want(save_data)
+        n, L = ref_codes.shape
+        inter = np.empty((2 * n, L), dtype=np.uint8)
+        inter[0::2], inter[1::2] = ref_codes, alt_codes
+        codes = torch.from_numpy(inter).cuda()
+        req = [s for s in want if s != "predictions"]
+        if "predictions" in want:
+            req += ["ref_predictions", "alt_predictions"]
+        out = self.net.forward_score(codes, None, None, None, 2 * n, _lib.SB_PAIR_INTERLEAVED,
+                                     precision=self.precision, want=tuple(req))
+        if to_host:
+            out = {k: v.cpu().numpy() for k, v in out.items()}
+        return out
+
+    def ism_scores(self, sequence, save_data=("abs_diffs", "logits"), start_position=0, end_position=None,
+                   to_host=True):
+        """ISM of one (already padded/truncated, upper-cased) sequence.  Returns (mutation list as
+        (pos int array, alt code array), dict of arrays, baseline prediction (1, F))."""
+        import torch
+        want = self._want(save_data)
+        if end_position is None:
+            end_position = self.sequence_length
+        pos, alt, codes = ism_mutations_device(sequence, start_position, end_position, self.reference_sequence)
+        base = self.net.forward_codes(codes, precision=self.precision)          # (1, F) baseline
+        m = int(pos.numel())
+        req = [s for s in want if s != "predictions"]
+        if "predictions" in want:
+            req.append("alt_predictions")
+        base_pair, base_index = base, None
+        if "logits" in want:
+            # logit_score_handler.py:118-124 clamps the shared baseline array in place during the first
+            # batch, so batches after the first see the clamped baseline in EVERY handler (§9.21)
+            clamped = torch.where(base == 0, torch.full_like(base, 1e-24), base)
+            clamped = torch.where(clamped >= 1, torch.full_like(base, 0.999999), clamped)
+            base_pair = torch.cat([base, clamped], dim=0).contiguous()
+            base_index = (torch.arange(m, device=base.device) >= self.batch_size).to(torch.int32)
+        out = self.net.forward_score(codes, torch.zeros(m, dtype=torch.int32, device=codes.device), pos, alt, m,
+                                     _lib.SB_PAIR_BASELINE, precision=self.precision, base_pred=base_pair,
+                                     base_index=base_index, want=tuple(req))
+        if "logits" in want:
+            base = base_pair[1:2]
+        if to_host:
+            out = {k: v.cpu().numpy() for k, v in out.items()}
+            return (pos.cpu().numpy(), alt.cpu().numpy()), out, base.cpu().numpy()
+        return (pos, alt), out, base
+
+    # ----------------------------------------------------------------------------------------------
+    # reference entry points
+    # ----------------------------------------------------------------------------------------------
+    def in_silico_mutagenesis(self, sequence, save_data, output_path_prefix="ism", mutate_n_bases=1,
+                              output_format="tsv", start_position=0, end_position=None):
+        """model_predict.py:662-799 (``mutate_n_bases`` is ignored there too: hard-wired to 1, :763-764)."""
+        if end_position is None:
+            end_position = self.sequence_length
+        if start_position >= end_position:
+            raise ValueError(("Starting positions must be less than the ending "
+                              "positions. Found a starting position of {0} with "
+                              "an ending position of {1}.").format(start_position, end_position))
+        if start_position < 0:
+            raise ValueError("Negative starting positions are not supported.")
+        if end_position < 0:
+            raise ValueError("Negative ending positions are not supported.")
+        if start_position >= self.sequence_length:
+            raise ValueError(("Starting positions must be less than the sequence length."
+                              " Found a starting position of {0} with a sequence length "
+                              "of {1}.").format(start_position, self.sequence_length))
+        if end_position > self.sequence_length:
+            raise ValueError(("Ending positions must be less than or equal to the sequence "
+                              "length. Found an ending position of {0} with a sequence "
+                              "length of {1}.").format(end_position, self.sequence_length))
+        if (end_position - start_position) < mutate_n_bases:
+            raise ValueError(("Fewer bases exist in the substring specified by the starting "
+                              "and ending positions than need to be mutated. There are only "
+                              "{0} currently, but {1} bases must be mutated at a "
+                              "time").format(end_position - start_position, mutate_n_bases))
+        path_dirs, _ = os.path.split(output_path_prefix)
+        if path_dirs:
+            os.makedirs(path_dirs, exist_ok=True)
+        n = len(sequence)
+        if n < self.sequence_length:
+            diff = (self.sequence_length - n) / 2
+            pad_l, pad_r = int(np.floor(diff)), math.ceil(diff)
+            sequence = (self.reference_sequence.UNK_BASE * pad_l) + sequence + \
+                (self.reference_sequence.UNK_BASE * pad_r)
+        elif n > self.sequence_length:
+            start = int((n - self.sequence_length) // 2)
+            sequence = sequence[start:int(start + self.sequence_length)]
+        sequence = str.upper(sequence)
+        want = self._want(save_data)
+        (pos, alt), out, base = self.ism_scores(sequence, want, start_position, end_position)
+        ids = [(str(int(p)), sequence[int(p)], "ACGT"[int(a)]) for p, a in zip(pos, alt)]
+        results = []
+        for s in want:
+            if s == "predictions":
+                arr = out["alt_predictions"]
+                if output_format == "tsv":
+                    # model_predict.py:789-792: the baseline row leads the predictions TSV
+                    arr = np.concatenate([base, arr], axis=0)
+                    _out_dir, _p, sp = _scores_filepath(output_path_prefix, "predictions")
+                    write_tsv(sp + ".tsv", ISM_COLS, self.features,
+                              [("input_sequence", "NA", "NA")] + ids, arr)
+                    continue
+                results.append(("predictions", None, arr))
+                _out_dir, _p, sp = _scores_filepath("{0}_ref".format(output_path_prefix), "predictions")
+                write_hdf5(sp + ".h5", base)
+                write_row_labels(os.path.join(_out_dir, "{0}_row_labels.txt".format(_p)), ["name"],
+                                 [("input_sequence",)])
+            else:
+                results.append((s, None, out[s]))
+        _write_outputs(results, ids, self.features, ISM_COLS, output_path_prefix, output_format)
+
+    def variant_effect_prediction(self, vcf_file, save_data, output_dir=None, output_format="tsv",
+                                  strand_index=None, require_strand=False):
+        """model_predict.py:952-1141."""
+        path, filename = os.path.split(vcf_file)
+        output_path_prefix = '.'.join(filename.split('.')[:-1])
+        if output_dir:
+            os.makedirs(output_dir, exist_ok=True)
+        else:
+            output_dir = path
+        output_path_prefix = os.path.join(output_dir, output_path_prefix)
+        variants = read_vcf_file(vcf_file, strand_index=strand_index, require_strand=require_strand,
+                                 output_NAs_to_file="{0}.NA".format(output_path_prefix),
+                                 seq_context=(self._start_radius, self._end_radius),
+                                 reference_sequence=self.reference_sequence)
+        want = self._want(save_data)
+        n = len(variants)
+        F = len(self.features)
+        names = [s for s in want if s != "predictions"]
+        if "predictions" in want:
+            names += ["ref_predictions", "alt_predictions"]
+        arrays = {k: np.zeros((n, F), dtype=np.float32) for k in names}
+        match = np.ones(n, dtype=bool)
+        unk = np.zeros(n, dtype=bool)
+        snv = np.fromiter((len(v[3]) == 1 and len(v[4]) == 1 and v[4] not in "*-" for v in variants),
+                          dtype=bool, count=n)
+        idx = np.nonzero(snv)[0]
+        if len(idx):
+            r = self.score_snvs([variants[i][0] for i in idx], [variants[i][1] for i in idx],
+                                [_CODE.get(variants[i][3], 4) for i in idx],
+                                [_CODE.get(variants[i][4], 4) for i in idx],
+                                strands=[variants[i][5] for i in idx], save_data=want)
+            for k in names:
+                arrays[k][idx] = r[k]
+            match[idx], unk[idx] = r["ref_match"], r["contains_unk"]
+        idx = np.nonzero(~snv)[0]
+        if len(idx):
+            refs, alts = [], []
+            for i in idx:
+                rs, als, m, u = build_ref_alt_strings(variants[i], self.reference_sequence, self.sequence_length,
+                                                      self._start_radius, self._end_radius)
+                refs.append(codes_of_string(rs)); alts.append(codes_of_string(als))
+                match[i], unk[i] = m, u
+            r = self.score_code_pairs(np.stack(refs), np.stack(alts), save_data=want)
+            for k in names:
+                arrays[k][idx] = r[k]
+        for i, v in enumerate(variants):
+            if unk[i]:
+                warnings.warn("For variant ({0}, {1}, {2}, {3}, {4}, {5}), reference sequence contains "
+                              "unknown base(s)--will be marked `True` in the `contains_unk` column of the "
+                              ".tsv or the row_labels .txt file.".format(*v))
+            if not match[i]:
+                warnings.warn("For variant ({0}, {1}, {2}, {3}, {4}, {5}), reference does not match the "
+                              "reference genome. Predictions/scores associated with this variant--where we "
+                              "use '{3}' in the input sequence--will be marked `False` in the `ref_match` "
+                              "column of the .tsv or the row_labels .txt file".format(*v))
+        ids = [tuple(v) + (bool(match[i]), bool(unk[i])) for i, v in enumerate(variants)]
+        results = []
+        out_dir, prefix = os.path.split(output_path_prefix)
+        for s in want:
+            if s == "predictions":
+                # write_ref_alt_handler.py:83-108: <prefix>.ref_predictions.* and <prefix>.alt_predictions.*
+                for tag in ("ref", "alt"):
+                    p = os.path.join(out_dir, "{0}.{1}".format(prefix, tag) if prefix else tag)
+                    results.append(("predictions", p, arrays[tag + "_predictions"]))
+            else:
+                results.append((s, None, arrays[s]))
+        _write_outputs(results, ids, self.features, VARIANTEFFECT_COLS, output_path_prefix, output_format)
+        return None

@@ -203,11 +203,22 @@ class Genome(object):
         state["_initialized"] = False
         return state
 
+    @classmethod
+    def from_sequences(cls, names, sequences, device=None):
+        """Genome over in-memory sequences (uint8 ASCII arrays or str) instead of a FASTA file."""
+        g = cls(input_path=None, device=device)
+        g._memory_records = [(n, np.frombuffer(s.encode("latin-1"), dtype=np.uint8) if isinstance(s, str)
+                              else np.asarray(s, dtype=np.uint8)) for n, s in zip(names, sequences)]
+        g._unpicklable_init()
+        return g
+
     def _unpicklable_init(self):
         if self._initialized:
             return
         import torch
-        recs = read_fasta(self.input_path)
+        recs = getattr(self, "_memory_records", None)
+        if recs is None:
+            recs = read_fasta(self.input_path)
         self._seqs = {name: seq for name, seq in recs}
         self.chrs = sorted(self._seqs.keys())
         self.len_chrs = {c: len(self._seqs[c]) for c in self.chrs}

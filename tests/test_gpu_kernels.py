@@ -358,7 +358,8 @@ def test_score_pairs_clamp_semantics(torch):
     exp_logit = O.logit_score(alt.copy(), ref.copy())
     t = lambda a: torch.from_numpy(a).cuda()
     outs = [torch.empty((1, 6), device="cuda") for _ in range(3)]
-    _lib.check(_lib.load().sb_score_pairs(_lib.ptr(t(ref)), _lib.ptr(t(alt)), None, 1, 1, 6, _lib.ptr(outs[0]),
+    ref_d, alt_d = t(ref), t(alt)  # keep the device buffers alive across the call
+    _lib.check(_lib.load().sb_score_pairs(_lib.ptr(ref_d), _lib.ptr(alt_d), None, 1, 1, 6, _lib.ptr(outs[0]),
                                           _lib.ptr(outs[1]), _lib.ptr(outs[2]), 0, _lib.stream_ptr()),
                "sb_score_pairs")
     assert np.array_equal(outs[0].cpu().numpy(), exp_abs)
