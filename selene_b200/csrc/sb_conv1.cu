@@ -1,0 +1,310 @@
+// selene_b200 — first convolution (4 -> cout channels, <= 8 taps) straight from base codes on tcgen05.
+//
+// Replaces torch.conv1d + relu + max_pool1d of models/deepsea.py:22-25 for one-hot input.  The input is
+// never materialised as floats: each CTA builds the im2col rows of its tile in shared memory directly
+// from the uint8 codes (one 64-bit pattern per tap: 1.0 in the slot of the base, or 0.25 x 4 for an
+// unknown base), in the un-swizzled K-major core-matrix layout tcgen05.mma reads.  K = taps*4 <= 32, so
+// the tensor work is tiny; the kernel is bounded by its epilogue.  To keep the epilogue free of
+// cross-lane traffic the max-pool is folded into the MMA schedule: row i of accumulator q holds conv
+// position pool*i + q, so the `pool` members of a pooling window sit in the SAME TMEM lane of `pool`
+// different column blocks and the pooled value is a per-thread max.
+//
+//   tile            = 128 pooled positions of one sequence (DeepSEA: 2 tiles per 1000-bp sequence)
+//   accumulators    = 2 stages x pool x 64 columns of TMEM (<= 512)
+//   warps 0-3       : build A for the NEXT tile, then drain the current tile's accumulators
+//                     (tcgen05.ld -> max over q -> +bias -> ReLU -> bf16 -> 2 x 16-byte stores per chunk)
+//   warp 4 (1 lane) : issues tcgen05.mma (pool x K/16 per 64-channel pass), commits to mbarriers
+#include "sb_common.cuh"
+
+namespace {
+
+constexpr int kRows = 128;          // pooled positions per tile
+constexpr int kPassN = 64;          // channels per pass
+constexpr int kKPad = 32;           // padded K (8 taps x 4 bases)
+constexpr int kRowBytes = kKPad * 2;                 // 64
+constexpr int kATileBytes = kRows * kRowBytes;       // 8192 per q
+constexpr int kMaxPool = 4;
+constexpr int kMaxCodes = kRows * kMaxPool + 16;     // codes staged per tile
+
+struct Conv1Params {
+    const uint8_t* codes;
+    const int32_t* src;
+    const int32_t* sub_pos;
+    const uint8_t* sub_code;
+    long long row0;
+    long long n_rows;
+    int L, taps, pool, t_pool, cout, out_ld, relu, n_pass, tiles_per_seq;
+    const uint4* wpacked;   // n_pass*64 rows x 32 K in the smem core-matrix layout
+    const float* bias;      // n_pass*64
+    __nv_bfloat16* out;
+};
+
+// un-swizzled K-major layout: 8-row x 16-byte core matrices; K-adjacent core matrices 128 B apart
+// (LBO), M/N-adjacent 8-row groups 512 B apart (SBO)
+__device__ __forceinline__ uint64_t desc_nosw(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(128 >> 4) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+__device__ __forceinline__ uint64_t tap_pattern(int code) {
+    return code < 4 ? (0x3F80ull << (16 * code)) : 0x3E803E803E803E80ull;
+}
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(160, 1) conv1_tc_kernel(const Conv1Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                               ~static_cast<uintptr_t>(1023));
+    // layout: [A buf0: 4 x 8 KB][A buf1: 4 x 8 KB][B: n_pass x 4 KB][bias][codes x2][barriers]
+    uint8_t* a_buf = smem;
+    uint8_t* b_smem = smem + 2 * kMaxPool * kATileBytes;
+    float* bias_s = reinterpret_cast<float*>(b_smem + p.n_pass * kPassN * kRowBytes);
+    uint8_t* codes_s = reinterpret_cast<uint8_t*>(bias_s + p.n_pass * kPassN);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(
+        (reinterpret_cast<uintptr_t>(codes_s + kMaxCodes) + 15) & ~static_cast<uintptr_t>(15));
+    uint64_t* a_full = bars;        // [2]
+    uint64_t* tfull = bars + 2;     // [2]
+    uint64_t* tempty = bars + 4;    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long n_tiles = p.n_rows * p.tiles_per_seq;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            sb_mbar_init(&a_full[i], 128);
+            sb_mbar_init(&tfull[i], 1);
+            sb_mbar_init(&tempty[i], 128);
+        }
+        sb_fence_mbar_init();
+    }
+    if (warp == 4) sb_tmem_alloc(tmem_slot, 512);
+    // weights + bias -> smem (once per CTA)
+    {
+        const int n16 = p.n_pass * kPassN * kRowBytes / 16;
+        uint4* dst = reinterpret_cast<uint4*>(b_smem);
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(p.wpacked + i);
+        for (int i = threadIdx.x; i < p.n_pass * kPassN; i += blockDim.x) bias_s[i] = __ldg(p.bias + i);
+    }
+    sb_fence_proxy_async();
+    sb_tc_fence_before();
+    __syncthreads();
+    sb_tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int ksteps = (p.taps * 4 + 15) / 16;
+
+    if (warp == 4) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = sb_umma_idesc_bf16(kRows, kPassN);
+            const uint32_t a_addr = sb_smem_u32(a_buf);
+            const uint32_t b_addr = sb_smem_u32(b_smem);
+            uint32_t gpass = 0;
+            int it = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                sb_mbar_wait(&a_full[buf], (it >> 1) & 1);
+                sb_tc_fence_after();
+                for (int pass = 0; pass < p.n_pass; ++pass, ++gpass) {
+                    const uint32_t stage = gpass & 1;
+                    sb_mbar_wait(&tempty[stage], ((gpass >> 1) & 1) ^ 1);
+                    sb_tc_fence_after();
+                    for (int q = 0; q < p.pool; ++q) {
+                        const uint32_t d = tmem_base + stage * 256 + q * kPassN;
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            // one K step = 2 core matrices = 256 B along K
+                            const uint64_t da = desc_nosw(a_addr + (buf * kMaxPool + q) * kATileBytes + ks * 256);
+                            const uint64_t db = desc_nosw(b_addr + pass * (kPassN * kRowBytes) + ks * 256);
+                            sb_umma_bf16(d, da, db, idesc, ks > 0 ? 1u : 0u);
+                        }
+                    }
+                    sb_umma_commit(&tfull[stage]);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== A builder + epilogue (warps 0..3, thread = pooled row) =====================
+        const int i = threadIdx.x;  // 0..127
+        const int n_codes = kRows * p.pool + 8;
+
+        auto build = [&](long long tile, int buf) {
+            const long long seq = tile / p.tiles_per_seq;
+            const int tin = (int)(tile - seq * p.tiles_per_seq);
+            const long long row = p.row0 + seq;
+            const long long srow = p.src ? (long long)p.src[row] : row;
+            const uint8_t* crow = p.codes + srow * p.L;
+            const int sp = p.sub_pos ? p.sub_pos[row] : -1;
+            const int sc = (p.sub_pos && p.sub_code) ? p.sub_code[row] : 4;
+            const int p0 = tin * kRows * p.pool;
+            uint8_t* cs = codes_s;
+            for (int k = i; k < n_codes; k += 128) {
+                const int pos = p0 + k;
+                int c = 4;
+                if (pos < p.L) {
+                    c = __ldg(crow + pos);
+                    if (pos == sp) c = sc;
+                    if (c > 4) c = 4;
+                }
+                cs[k] = (uint8_t)c;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // this thread's pool + 7 codes
+            uint64_t pat[kMaxPool + 7];
+#pragma unroll
+            for (int k = 0; k < kMaxPool + 7; ++k) {
+                const int c = (k < p.pool + 7) ? cs[p.pool * i + k] : 4;
+                pat[k] = tap_pattern(c);
+            }
+            uint8_t* a_row = a_buf + (size_t)buf * kMaxPool * kATileBytes + (i >> 3) * 512 + (i & 7) * 16;
+#pragma unroll
+            for (int q = 0; q < kMaxPool; ++q) {
+                if (q < p.pool) {
+#pragma unroll
+                    for (int kc = 0; kc < 4; ++kc) {
+                        const uint64_t lo = (2 * kc < p.taps) ? pat[q + 2 * kc] : 0ull;
+                        const uint64_t hi = (2 * kc + 1 < p.taps) ? pat[q + 2 * kc + 1] : 0ull;
+                        *reinterpret_cast<uint4*>(a_row + q * kATileBytes + kc * 128) =
+                            make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+                    }
+                }
+            }
+            sb_fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core
+            sb_mbar_arrive(&a_full[buf]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // codes_s may be overwritten by the next build
+        };
+
+        uint32_t gpass = 0;
+        int it = 0;
+        long long tile = blockIdx.x;
+        if (tile < n_tiles) build(tile, 0);
+        for (; tile < n_tiles; tile += gridDim.x, ++it) {
+            const long long next = tile + gridDim.x;
+            if (next < n_tiles) build(next, (it + 1) & 1);
+            const long long seq = tile / p.tiles_per_seq;
+            const int tin = (int)(tile - seq * p.tiles_per_seq);
+            const int tp = tin * kRows + i;
+            const bool valid = tp < p.t_pool;
+            __nv_bfloat16* orow = p.out + (seq * p.t_pool + tp) * (long long)p.out_ld;
+            for (int pass = 0; pass < p.n_pass; ++pass, ++gpass) {
+                const uint32_t stage = gpass & 1;
+                sb_mbar_wait(&tfull[stage], (gpass >> 1) & 1);
+                sb_tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + stage * 256;
+#pragma unroll
+                for (int c = 0; c < kPassN / 16; ++c) {
+                    uint32_t r0[16];
+                    sb_tmem_ld16(taddr + c * 16, r0);
+                    float v[16];
+                    if (p.pool == 1) {
+                        sb_tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]);
+                    } else if (p.pool == 2) {
+                        uint32_t r1[16];
+                        sb_tmem_ld16(taddr + kPassN + c * 16, r1);
+                        sb_tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
+                    } else {
+                        uint32_t r1[16], r2[16], r3[16];
+                        sb_tmem_ld16(taddr + kPassN + c * 16, r1);
+                        sb_tmem_ld16(taddr + 2 * kPassN + c * 16, r2);
+                        sb_tmem_ld16(taddr + 3 * kPassN + c * 16, r3);
+                        sb_tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            v[j] = fmaxf(fmaxf(__uint_as_float(r0[j]), __uint_as_float(r1[j])),
+                                         fmaxf(__uint_as_float(r2[j]), __uint_as_float(r3[j])));
+                    }
+                    const int nb = pass * kPassN + c * 16;
+                    const float* bs = bias_s + nb;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        v[j] += bs[j];
+                        if (p.relu) v[j] = fmaxf(v[j], 0.f);
+                    }
+#pragma unroll
+                    for (int g = 0; g < 2; ++g)
+                        if (valid && nb + 8 * g + 8 <= p.out_ld)
+                            *reinterpret_cast<uint4*>(orow + nb + 8 * g) =
+                                make_uint4(pack2(v[8 * g], v[8 * g + 1]), pack2(v[8 * g + 2], v[8 * g + 3]),
+                                           pack2(v[8 * g + 4], v[8 * g + 5]), pack2(v[8 * g + 6], v[8 * g + 7]));
+                }
+                sb_tc_fence_before();
+                sb_mbar_arrive(&tempty[stage]);
+            }
+        }
+    }
+
+    sb_tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        sb_tc_fence_after();
+        sb_tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace
+
+// Host: pack conv weights (cout, 4, taps) fp32 into the smem core-matrix layout, bf16, K = tap*4 + base.
+// Returns the number of bytes written (n_pass * 64 rows * 64 B).
+size_t sb_conv1_pack_weights(const float* w, int cout, int taps, const uint8_t perm[4], uint16_t* out,
+                             uint16_t (*to_bf16)(float)) {
+    const int n_pass = (cout + kPassN - 1) / kPassN;
+    const size_t elems = (size_t)n_pass * kPassN * kKPad;
+    for (size_t i = 0; i < elems; ++i) out[i] = 0;
+    for (int n = 0; n < cout; ++n)
+        for (int tap = 0; tap < taps; ++tap)
+            for (int b = 0; b < 4; ++b) {
+                const int k = tap * 4 + b;
+                const size_t off = (size_t)(n >> 3) * 256 + (size_t)(k >> 3) * 64 + (size_t)(n & 7) * 8 + (k & 7);
+                out[off] = to_bf16(w[((size_t)n * 4 + perm[b]) * taps + tap]);
+            }
+    return elems * 2;
+}
+
+int sb_conv1_tc_supported(int taps, int pool, int cout) {
+    return taps >= 1 && taps <= 8 && (pool == 1 || pool == 2 || pool == 4) && cout >= 1 && cout <= 1024;
+}
+
+int sb_conv1_tc_launch(const uint8_t* codes, const int32_t* src, const int32_t* sub_pos, const uint8_t* sub_code,
+                       long long row0, long long n_rows, int L, int taps, int pool, int t_pool, int cout, int out_ld,
+                       int relu, const void* wpacked, const float* bias_padded, void* out, int device,
+                       cudaStream_t stream) {
+    if (n_rows <= 0) return SB_OK;
+    Conv1Params p;
+    p.codes = codes; p.src = src; p.sub_pos = sub_pos; p.sub_code = sub_code;
+    p.row0 = row0; p.n_rows = n_rows;
+    p.L = L; p.taps = taps; p.pool = pool; p.t_pool = t_pool; p.cout = cout; p.out_ld = out_ld; p.relu = relu;
+    p.n_pass = (cout + kPassN - 1) / kPassN;
+    p.tiles_per_seq = (t_pool + kRows - 1) / kRows;
+    p.wpacked = reinterpret_cast<const uint4*>(wpacked);
+    p.bias = bias_padded;
+    p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    size_t smem = 1024 + 2 * kMaxPool * kATileBytes + (size_t)p.n_pass * kPassN * (kRowBytes + 4) + kMaxCodes +
+                  16 + 64 + 16;
+    if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM: each CTA owns all 512 TMEM columns
+    SB_REQUIRE(smem <= 220 * 1024, "sb_conv1_tc_launch: %zu bytes of shared memory needed", smem);
+    static size_t attr = 0;
+    if (smem > attr) {
+        SB_CHECK_CUDA(cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    const long long tiles = n_rows * p.tiles_per_seq;
+    const int sms = sb_sm_count(device);
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    conv1_tc_kernel<<<grid, 160, smem, stream>>>(p);
+    SB_COUNT_LAUNCH();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}

@@ -35,6 +35,8 @@ struct NetLayer {
     int a_ld, k_full, w_ld, k_full_tap, w_ld_tap, block_n, n_tiles_n, out_ld_b;
     // first layer from codes
     float* lut;  // dev (k x 5 x cout)
+    uint16_t* w1_packed;  // dev, tcgen05 core-matrix layout (sb_conv1.cu); null if unsupported
+    float* bias1_padded;  // dev, n_pass*64
 };
 
 }  // namespace
@@ -53,6 +55,15 @@ struct sb_net {
     std::vector<std::vector<cudaEvent_t>> ev;  // per layer: start0, stop0, start1, stop1, ...
     std::vector<size_t> ev_used;
 };
+
+// sb_conv1.cu
+size_t sb_conv1_pack_weights(const float* w, int cout, int taps, const uint8_t perm[4], uint16_t* out,
+                             uint16_t (*to_bf16)(float));
+int sb_conv1_tc_supported(int taps, int pool, int cout);
+int sb_conv1_tc_launch(const uint8_t* codes, const int32_t* src, const int32_t* sub_pos, const uint8_t* sub_code,
+                       long long row0, long long n_rows, int L, int taps, int pool, int t_pool, int cout, int out_ld,
+                       int relu, const void* wpacked, const float* bias_padded, void* out, int device,
+                       cudaStream_t stream);
 
 namespace {
 
@@ -370,6 +381,16 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
                     lut[((size_t)j * 5 + 4) * S.cout + o] = s4;
                 }
             int rc = upload(&N.lut, lut); if (rc) return rc;
+            const char* force_lut = getenv("SB_CONV1_LUT");
+            if (sb_conv1_tc_supported(S.k, N.pool, S.cout) && !(force_lut && force_lut[0] == '1')) {
+                const int n_pass = (S.cout + 63) / 64;
+                std::vector<uint16_t> wp((size_t)n_pass * 64 * 32, 0);
+                sb_conv1_pack_weights(S.weight, S.cout, S.k, perm, wp.data(), f32_to_bf16_bits);
+                rc = upload(&N.w1_packed, wp); if (rc) return rc;
+                std::vector<float> bp((size_t)n_pass * 64, 0.f);
+                for (int o = 0; o < S.cout; ++o) bp[o] = S.bias[o];
+                rc = upload(&N.bias1_padded, bp); if (rc) return rc;
+            }
         }
 
         // ---- bf16 / tcgen05 path (every layer but the first)
@@ -419,7 +440,7 @@ extern "C" int sb_net_destroy(sb_net* net) {
     if (!net) return SB_OK;
     cudaSetDevice(net->device);
     for (auto& N : net->layers) {
-        cudaFree(N.wf); cudaFree(N.biasf); cudaFree(N.wb); cudaFree(N.wb_tap); cudaFree(N.biasb); cudaFree(N.lut);
+        cudaFree(N.wf); cudaFree(N.biasf); cudaFree(N.wb); cudaFree(N.wb_tap); cudaFree(N.biasb); cudaFree(N.lut); cudaFree(N.w1_packed); cudaFree(N.bias1_padded);
     }
     delete net;
     return SB_OK;
@@ -546,7 +567,12 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
             const size_t smem = (size_t)N.k * 5 * N.cout * sizeof(float) + (size_t)round_up(net->L, 16);
             SB_REQUIRE(smem <= 220 * 1024, "first-layer lookup table (%zu B) does not fit shared memory", smem);
             int threads = round_up(out_ld < 512 ? out_ld : 512, 32);
-            if (bf) {
+            if (bf && N.w1_packed) {
+                int rc = sb_conv1_tc_launch(in.codes, in.src, in.sub_pos, in.sub_code, r0, m, net->L, N.k, N.pool,
+                                            N.t_pool, N.cout, out_ld, N.relu, N.w1_packed, N.bias1_padded, act[cur],
+                                            dev, stream);
+                if (rc) return rc;
+            } else if (bf) {
                 SB_CHECK_CUDA(cudaFuncSetAttribute(conv_codes_kernel<__nv_bfloat16>,
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 conv_codes_kernel<__nv_bfloat16><<<(unsigned)m, threads, smem, stream>>>(
@@ -559,8 +585,10 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
                     in.codes, in.src, in.sub_pos, in.sub_code, r0, net->L, N.k, N.cout, out_ld, N.relu, N.pool,
                     N.t_pool, N.lut, N.biasf, reinterpret_cast<float*>(act[cur]));
             }
-            SB_COUNT_LAUNCH();
-            SB_CHECK_LAUNCH();
+            if (!(bf && N.w1_packed)) {
+                SB_COUNT_LAUNCH();
+                SB_CHECK_LAUNCH();
+            }
         } else {
             // generic (n, L, 4) fp32 input: dense fp32 conv, then pool/compact (+ convert)
             const float* x = in.onehot + r0 * net->L * 4;

@@ -304,6 +304,10 @@ def test_deepsea_scaled_weights_saturation(torch, precision, tol):
     got = net.forward_codes(torch.from_numpy(codes).cuda(), precision=precision).cpu().numpy()
     assert exp.std() > 0.05  # the scaling really spreads the outputs
     assert np.abs(got - exp).max() <= tol
+    # a structural bug (tap order, channel permutation, pooling window) would leave the outputs near
+    # 0.5 and still pass an absolute gate at default init; relative to the signal it cannot hide
+    assert np.abs(got - exp).max() <= 0.12 * exp.std()
+    assert np.corrcoef(got.ravel(), exp.ravel())[0, 1] > 0.999
 
 
 def test_forward_substitution_rows(torch, deepsea):
