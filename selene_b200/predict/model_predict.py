@@ -369,6 +369,19 @@ class AnalyzeSequences(object):
                                  seq_context=(self._start_radius, self._end_radius),
                                  reference_sequence=self.reference_sequence)
         want = self._want(save_data)
+        # one process per GPU: every rank scores a contiguous shard of the variant list and rank 0
+        # gathers the score tiles once (selene_b200/sharding.py); single-process runs skip all of it
+        all_variants, rank, world = variants, 0, 1
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                rank, world = dist.get_rank(), dist.get_world_size()
+        except ImportError:
+            pass
+        if world > 1:
+            from ..sharding import shard_range
+            lo, hi = shard_range(len(all_variants), rank, world)
+            variants = all_variants[lo:hi]
         n = len(variants)
         F = len(self.features)
         names = [s for s in want if s != "predictions"]
@@ -409,6 +422,20 @@ class AnalyzeSequences(object):
                               "reference genome. Predictions/scores associated with this variant--where we "
                               "use '{3}' in the input sequence--will be marked `False` in the `ref_match` "
                               "column of the .tsv or the row_labels .txt file".format(*v))
+        if world > 1:
+            import torch
+            from ..sharding import gather_tiles
+            dev = torch.device("cuda", int(self.net.device))
+            n_all = len(all_variants)
+            for k in list(arrays.keys()):
+                g = gather_tiles(torch.from_numpy(arrays[k]).to(dev), n_all, dst=0)
+                arrays[k] = g.cpu().numpy() if g is not None else None
+            mu = torch.from_numpy(np.stack([match, unk], axis=1).astype(np.float32)).to(dev)
+            g = gather_tiles(mu, n_all, dst=0)
+            if rank != 0:
+                return None
+            match, unk = g[:, 0].cpu().numpy() > 0.5, g[:, 1].cpu().numpy() > 0.5
+            variants = all_variants
         ids = [tuple(v) + (bool(match[i]), bool(unk[i])) for i, v in enumerate(variants)]
         results = []
         out_dir, prefix = os.path.split(output_path_prefix)
