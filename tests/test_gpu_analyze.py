@@ -1,0 +1,106 @@
+"""GPU end-to-end tests of the reference-facing entry points: AnalyzeSequences.in_silico_mutagenesis
+and .variant_effect_prediction write the reference's files with the reference's numbers (oracle)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, ".."))
+sys.path.insert(0, HERE)
+from oracle import selene_oracle as O  # noqa: E402
+import sb_helpers as H  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+FEATS = ["f%d" % i for i in range(919)]
+
+
+def _deepsea():
+    import torch
+    import torch.nn as nn
+
+    class DeepSEA(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv_net = nn.Sequential(
+                nn.Conv1d(4, 320, 8), nn.ReLU(inplace=True), nn.MaxPool1d(4, 4), nn.Dropout(p=0.2),
+                nn.Conv1d(320, 480, 8), nn.ReLU(inplace=True), nn.MaxPool1d(4, 4), nn.Dropout(p=0.2),
+                nn.Conv1d(480, 960, 8), nn.ReLU(inplace=True), nn.Dropout(p=0.5))
+            self.classifier = nn.Sequential(nn.Linear(960 * 53, 919), nn.ReLU(inplace=True),
+                                            nn.Linear(919, 919), nn.Sigmoid())
+    torch.manual_seed(0)
+    return DeepSEA()
+
+
+def _read_tsv(path, n_id):
+    lines = open(path).read().rstrip("\n").split("\n")
+    header = lines[0].split("\t")
+    ids = [tuple(l.split("\t")[:n_id]) for l in lines[1:]]
+    data = np.array([[float(x) for x in l.split("\t")[n_id:]] for l in lines[1:]])
+    return header, ids, data
+
+
+def test_ism_files_match_oracle(tmp_path):
+    from selene_b200.predict.model_predict import AnalyzeSequences
+    from selene_b200.sequences import Genome
+    az = AnalyzeSequences(_deepsea(), sequence_length=1000, features=FEATS, reference_sequence=Genome,
+                          precision="fp32")
+    r = np.random.default_rng(0)
+    seq = "".join(np.array(list("ACGT"))[r.integers(0, 4, 990)].tolist())
+    seq = seq[:100] + "N" + seq[101:200] + "acgt" + seq[204:]       # one unknown, some lowercase, needs padding
+    prefix = str(tmp_path / "out" / "ism")
+    az.in_silico_mutagenesis(seq, ["abs_diffs", "logits", "predictions"], output_path_prefix=prefix)
+    padded = ("N" * 5 + seq + "N" * 5).upper()
+    muts, absd, logits, base = O.ism_scores(padded, O.deepsea_layers(1000, 919, seed=0))
+    exp_ids = [(str(m[0][0]), padded[m[0][0]], m[0][1]) for m in muts]
+    for name, exp in (("abs_diffs", absd), ("logits", logits)):
+        header, ids, data = _read_tsv(prefix + "_%s.tsv" % name, 3)
+        assert header == ["pos", "ref", "alt"] + FEATS and ids == exp_ids
+        assert data.shape == exp.shape
+        assert np.abs(data - exp).max() <= 1e-5 + 6e-3 * np.abs(exp).max()    # "{:.2e}" keeps 3 digits
+    header, ids, data = _read_tsv(prefix + "_predictions.tsv", 3)
+    assert ids[0] == ("input_sequence", "NA", "NA") and ids[1:] == exp_ids
+    assert np.abs(data[0] - base[0]).max() <= 6e-3
+
+
+def test_vep_files_match_oracle(tmp_path):
+    from selene_b200.predict.model_predict import AnalyzeSequences
+    from selene_b200.sequences import Genome
+    g = H.synth_genome()
+    fa = str(tmp_path / "g.fa")
+    H.write_fasta(g, fa)
+    Genome.update_bases_order(['A', 'C', 'G', 'T'])
+    G = Genome(fa)
+    az = AnalyzeSequences(_deepsea(), sequence_length=1000, features=FEATS, reference_sequence=G, precision="fp32")
+    rng = np.random.default_rng(8)
+    rows, variants = [], []
+    for i in range(20):
+        c = sorted(g.keys())[rng.integers(0, 3)]
+        pos = int(rng.integers(600, len(g[c]) - 600))
+        ref = g[c][pos - 1].upper()
+        ref = ref if ref in "ACGT" and rng.random() > 0.2 else "ACGT"[rng.integers(0, 4)]
+        alt = "ACGT"[rng.integers(0, 4)]
+        strand = "+-"[rng.integers(0, 2)]
+        rows.append("%s\t%d\trs%d\t%s\t%s\t%s\n" % (c, pos, i, ref, alt, strand))
+        variants.append((c, pos, ref, alt, strand))
+    rows.append("chr1\t700\tmnv\tAC\tGT\t+\n")              # MNV: host-built windows
+    variants.append(("chr1", 700, "AC", "GT", "+"))
+    rows.append("chr1\t10\toob\tA\tC\t+\n")                  # out of bounds -> .NA file
+    vcf = str(tmp_path / "in.vcf")
+    open(vcf, "w").write("#CHROM\tPOS\tID\tREF\tALT\tSTRAND\n" + "".join(rows))
+    out_dir = str(tmp_path / "vep")
+    with pytest.warns(UserWarning):
+        az.variant_effect_prediction(vcf, ["abs_diffs", "logits", "predictions"], output_dir=out_dir, strand_index=5)
+    absd, logits, match, unk = O.vep_scores(g, variants, O.deepsea_layers(1000, 919, seed=0), 1000)
+    header, ids, data = _read_tsv(os.path.join(out_dir, "in_abs_diffs.tsv"), 8)
+    assert header[:8] == ["chrom", "pos", "name", "ref", "alt", "strand", "ref_match", "contains_unk"]
+    assert [i[6] for i in ids] == [str(bool(m)) for m in match]
+    assert [i[7] for i in ids] == [str(bool(u)) for u in unk]
+    assert [(i[0], int(i[1]), i[3], i[4], i[5]) for i in ids] == variants
+    assert np.abs(data - absd).max() <= 1e-5 + 6e-3 * np.abs(absd).max()
+    _, _, data = _read_tsv(os.path.join(out_dir, "in_logits.tsv"), 8)
+    assert np.abs(data - logits).max() <= 1e-4 + 6e-3 * np.abs(logits).max()
+    assert os.path.exists(os.path.join(out_dir, "in.ref_predictions.tsv"))
+    assert os.path.exists(os.path.join(out_dir, "in.alt_predictions.tsv"))
+    assert open(os.path.join(out_dir, "in.NA")).read().count("\n") == 1

@@ -196,3 +196,19 @@ def test_batchnorm_folding_matches_torch_eval():
         exp = net(torch.tensor(x).transpose(1, 2)).numpy()
     got = O.stack_forward(x, layers_from_module(net))
     assert np.abs(got - exp).max() < 1e-5
+
+
+def test_indel_windows_match_reference_goldens():
+    """Insertions, deletions and MNVs: build_ref_alt_strings vs ref/alt tensors produced by the
+    unmodified reference (_process_alt / _handle_standard_ref, tests/golden/make_golden.py)."""
+    from selene_b200.predict._variant_effect_prediction import build_ref_alt_strings
+    gold = np.load(os.path.join(HERE, "golden", "reference_outputs.npz"))
+    g = H.synth_genome()
+    G = _FakeGenome(g)
+    L = 200
+    for i, line in enumerate(gold["indel_variants"]):
+        c, pos, ref, alt, strand = str(line).split("\t")
+        rs, als, m, u = build_ref_alt_strings((c, int(pos), ".", ref, alt, strand), G, L, L // 2, L // 2)
+        assert np.array_equal(O.sequence_to_encoding(rs), gold["indel_ref_onehot"][i]), line
+        assert np.array_equal(O.sequence_to_encoding(als), gold["indel_alt_onehot"][i]), line
+        assert m == bool(gold["indel_match"][i]) and u == bool(gold["indel_unk"][i])
