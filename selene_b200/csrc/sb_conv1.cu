@@ -33,7 +33,7 @@ struct Conv1Params {
     const uint8_t* sub_code;
     long long row0;
     long long n_rows;
-    int L, taps, pool, t_pool, cout, out_ld, relu, n_pass, tiles_per_seq;
+    int L, taps, pool, t_pool, out_pitch, cout, out_ld, relu, n_pass, tiles_per_seq;
     const uint4* wpacked;   // n_pass*64 rows x 32 K in the smem core-matrix layout
     const float* bias;      // n_pass*64
     __nv_bfloat16* out;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(160, 1) conv1_tc_kernel(const Conv1Params p) {
             const int tin = (int)(tile - seq * p.tiles_per_seq);
             const int tp = tin * kRows + i;
             const bool valid = tp < p.t_pool;
-            __nv_bfloat16* orow = p.out + (seq * p.t_pool + tp) * (long long)p.out_ld;
+            __nv_bfloat16* orow = p.out + (seq * p.out_pitch + tp) * (long long)p.out_ld;
             for (int pass = 0; pass < p.n_pass; ++pass, ++gpass) {
                 const uint32_t stage = gpass & 1;
                 sb_mbar_wait(&tfull[stage], (gpass >> 1) & 1);
@@ -278,14 +278,14 @@ int sb_conv1_tc_supported(int taps, int pool, int cout) {
 }
 
 int sb_conv1_tc_launch(const uint8_t* codes, const int32_t* src, const int32_t* sub_pos, const uint8_t* sub_code,
-                       long long row0, long long n_rows, int L, int taps, int pool, int t_pool, int cout, int out_ld,
-                       int relu, const void* wpacked, const float* bias_padded, void* out, int device,
+                       long long row0, long long n_rows, int L, int taps, int pool, int t_pool, int out_pitch, int cout,
+                       int out_ld, int relu, const void* wpacked, const float* bias_padded, void* out, int device,
                        cudaStream_t stream) {
     if (n_rows <= 0) return SB_OK;
     Conv1Params p;
     p.codes = codes; p.src = src; p.sub_pos = sub_pos; p.sub_code = sub_code;
     p.row0 = row0; p.n_rows = n_rows;
-    p.L = L; p.taps = taps; p.pool = pool; p.t_pool = t_pool; p.cout = cout; p.out_ld = out_ld; p.relu = relu;
+    p.L = L; p.taps = taps; p.pool = pool; p.t_pool = t_pool; p.out_pitch = out_pitch > 0 ? out_pitch : t_pool; p.cout = cout; p.out_ld = out_ld; p.relu = relu;
     p.n_pass = (cout + kPassN - 1) / kPassN;
     p.tiles_per_seq = (t_pool + kRows - 1) / kRows;
     p.wpacked = reinterpret_cast<const uint4*>(wpacked);

@@ -24,6 +24,8 @@ namespace {
 struct NetLayer {
     int type, cin, cout, k, relu, pool;
     int t_in, t_conv, t_pool;  // per-sequence rows in / valid conv rows / rows out (FC: 1,1,1)
+    int pitch_in, pitch_out;   // bf16 path: rows per sequence of the in/out buffers (t_in rounded up to this
+                               // layer's pool / the next layer's pitch_in) so pool windows never straddle sequences
     // fp32 path
     float* wf;     // dev (k_f32 x ldw_f32): row = K index (tap*cin + c), col = cout (padded to x4)
     float* biasf;  // dev (ldw_f32)
@@ -61,8 +63,8 @@ size_t sb_conv1_pack_weights(const float* w, int cout, int taps, const uint8_t p
                              uint16_t (*to_bf16)(float));
 int sb_conv1_tc_supported(int taps, int pool, int cout);
 int sb_conv1_tc_launch(const uint8_t* codes, const int32_t* src, const int32_t* sub_pos, const uint8_t* sub_code,
-                       long long row0, long long n_rows, int L, int taps, int pool, int t_pool, int cout, int out_ld,
-                       int relu, const void* wpacked, const float* bias_padded, void* out, int device,
+                       long long row0, long long n_rows, int L, int taps, int pool, int t_pool, int out_pitch, int cout,
+                       int out_ld, int relu, const void* wpacked, const float* bias_padded, void* out, int device,
                        cudaStream_t stream);
 
 namespace {
@@ -83,7 +85,8 @@ template <typename OutT>
 __global__ void __launch_bounds__(512) conv_codes_kernel(
     const uint8_t* __restrict__ codes, const int32_t* __restrict__ src, const int32_t* __restrict__ sub_pos,
     const uint8_t* __restrict__ sub_code, long long row0, int L, int k, int cout, int out_ld, int relu, int pool,
-    int t_pool, const float* __restrict__ lut, const float* __restrict__ bias, OutT* __restrict__ out) {
+    int t_pool, int out_pitch, const float* __restrict__ lut, const float* __restrict__ bias,
+    OutT* __restrict__ out) {
     extern __shared__ uint8_t smem_raw[];
     float* tab = reinterpret_cast<float*>(smem_raw);             // k*5*cout
     uint8_t* sc = smem_raw + (size_t)k * 5 * cout * sizeof(float);  // L codes
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(512) conv_codes_kernel(
         sc[i] = (uint8_t)(c > 4 ? 4 : c);
     }
     __syncthreads();
-    OutT* orow = out + (long long)blockIdx.x * t_pool * out_ld;
+    OutT* orow = out + (long long)blockIdx.x * out_pitch * out_ld;
     for (int n = threadIdx.x; n < out_ld; n += blockDim.x) {
         if (n >= cout) {
             for (int tp = 0; tp < t_pool; ++tp) orow[(long long)tp * out_ld + n] = to_out<OutT>(0.f);
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
 // max-pool + compaction of the "full" conv output (rows = seq*t_in + t) into (seq, t_pool, c)
 template <typename OutT>
 __global__ void __launch_bounds__(256) pool_compact_kernel(const float* __restrict__ full, int ldf, int t_in,
-                                                           int pool, int t_pool, int c_valid, int out_ld,
+                                                           int pool, int t_pool, int out_pitch, int c_valid, int out_ld,
                                                            long long n_seq, OutT* __restrict__ out) {
     const long long total = n_seq * t_pool * out_ld;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(256) pool_compact_kernel(const float* __restri
             m = -INFINITY;
             for (int q = 0; q < pool; ++q) m = fmaxf(m, full[(s * t_in + (long long)tp * pool + q) * ldf + c]);
         }
-        out[i] = to_out<OutT>(m);
+        out[(s * out_pitch + tp) * out_ld + c] = to_out<OutT>(m);
     }
 }
 
@@ -431,6 +434,15 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
         else { seen_fc = true; t = 1; c = S.cout; }
     }
     SB_REQUIRE(seen_fc, "sb_net_create: network must end in FC layers");
+    for (size_t li = 0; li < net->layers.size(); ++li) {
+        NetLayer& N = net->layers[li];
+        N.pitch_in = N.type == SB_LAYER_CONV ? round_up(N.t_in, N.pool) : 1;
+    }
+    for (size_t li = 0; li < net->layers.size(); ++li) {
+        NetLayer& N = net->layers[li];
+        const bool next_conv = li + 1 < net->layers.size() && net->layers[li + 1].type == SB_LAYER_CONV;
+        N.pitch_out = next_conv ? net->layers[li + 1].pitch_in : N.t_pool;
+    }
     net->n_out = c;
     *out = net;
     return SB_OK;
@@ -499,7 +511,7 @@ WsPlan plan_ws(const sb_net* net, long long n, int precision, bool generic) {
     for (size_t li = 0; li < net->layers.size(); ++li) {
         const NetLayer& N = net->layers[li];
         const int ld = precision == SB_PREC_BF16 ? N.out_ld_b : N.cout;
-        const size_t bytes = (size_t)ch * N.t_pool * ld * es;
+        const size_t bytes = (size_t)ch * (precision == SB_PREC_BF16 ? N.pitch_out : N.t_pool) * ld * es;
         if (bytes > act) act = bytes;
         if (precision == SB_PREC_FP32 && li > 0) {
             const size_t fb = (size_t)ch * N.t_in * N.cout * 4;
@@ -569,21 +581,21 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
             int threads = round_up(out_ld < 512 ? out_ld : 512, 32);
             if (bf && N.w1_packed) {
                 int rc = sb_conv1_tc_launch(in.codes, in.src, in.sub_pos, in.sub_code, r0, m, net->L, N.k, N.pool,
-                                            N.t_pool, N.cout, out_ld, N.relu, N.w1_packed, N.bias1_padded, act[cur],
-                                            dev, stream);
+                                            N.t_pool, N.pitch_out, N.cout, out_ld, N.relu, N.w1_packed,
+                                            N.bias1_padded, act[cur], dev, stream);
                 if (rc) return rc;
             } else if (bf) {
                 SB_CHECK_CUDA(cudaFuncSetAttribute(conv_codes_kernel<__nv_bfloat16>,
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 conv_codes_kernel<__nv_bfloat16><<<(unsigned)m, threads, smem, stream>>>(
                     in.codes, in.src, in.sub_pos, in.sub_code, r0, net->L, N.k, N.cout, out_ld, N.relu, N.pool,
-                    N.t_pool, N.lut, N.biasf, reinterpret_cast<__nv_bfloat16*>(act[cur]));
+                    N.t_pool, N.pitch_out, N.lut, N.biasf, reinterpret_cast<__nv_bfloat16*>(act[cur]));
             } else {
                 SB_CHECK_CUDA(cudaFuncSetAttribute(conv_codes_kernel<float>,
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 conv_codes_kernel<float><<<(unsigned)m, threads, smem, stream>>>(
                     in.codes, in.src, in.sub_pos, in.sub_code, r0, net->L, N.k, N.cout, out_ld, N.relu, N.pool,
-                    N.t_pool, N.lut, N.biasf, reinterpret_cast<float*>(act[cur]));
+                    N.t_pool, N.t_pool, N.lut, N.biasf, reinterpret_cast<float*>(act[cur]));
             }
             if (!(bf && N.w1_packed)) {
                 SB_COUNT_LAUNCH();
@@ -601,10 +613,11 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
             const long long total = m * N.t_pool * out_ld;
             if (bf)
                 pool_compact_kernel<__nv_bfloat16><<<grid_for(total, dev), 256, 0, stream>>>(
-                    full, N.cout, N.t_in, N.pool, N.t_pool, N.cout, out_ld, m, reinterpret_cast<__nv_bfloat16*>(act[cur]));
+                    full, N.cout, N.t_in, N.pool, N.t_pool, N.pitch_out, N.cout, out_ld, m,
+                    reinterpret_cast<__nv_bfloat16*>(act[cur]));
             else
                 pool_compact_kernel<float><<<grid_for(total, dev), 256, 0, stream>>>(
-                    full, N.cout, N.t_in, N.pool, N.t_pool, N.cout, out_ld, m, reinterpret_cast<float*>(act[cur]));
+                    full, N.cout, N.t_in, N.pool, N.t_pool, N.t_pool, N.cout, out_ld, m, reinterpret_cast<float*>(act[cur]));
             SB_COUNT_LAUNCH();
             SB_CHECK_LAUNCH();
         }
@@ -621,17 +634,15 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
             SbTcLayer T;
             memset(&T, 0, sizeof(T));
             T.a = act[cur];
-            T.rows_a = m * N.t_in;
+            T.rows_a = m * (long long)N.pitch_in;
             T.a_ld = N.a_ld;
             T.bias = N.biasb; T.block_n = N.block_n; T.n_tiles_n = N.n_tiles_n;
             T.n_rows_w = N.cout;
-            T.t_in = N.t_in; T.t_conv = N.t_conv; T.pool = N.pool; T.relu = N.relu;
+            T.t_in = N.pitch_in; T.t_conv = N.t_conv; T.pool = N.pool; T.relu = N.relu;
+            T.out_pitch = N.pitch_out;
             T.out_f32 = last ? 1 : 0;
             T.out = last ? (void*)logits : act[cur ^ 1];
             T.out_ld = last ? ldl : N.out_ld_b;
-            const bool fusable = (N.t_in % N.pool) == 0;
-            SB_REQUIRE(fusable, "layer %zu: t_in %d not a multiple of pool %d (unsupported on the bf16 path)", li,
-                       N.t_in, N.pool);
             bool per_tap = net->force_per_tap && N.type == SB_LAYER_CONV;
             int rc = SB_OK;
             for (int attempt = 0; attempt < 2; ++attempt) {
@@ -663,7 +674,8 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
                 SB_REQUIRE(!last, "network cannot end in a conv layer");
                 const long long total = m * N.t_pool * N.cout;
                 pool_compact_kernel<float><<<grid_for(total, dev), 256, 0, stream>>>(
-                    full, N.cout, N.t_in, N.pool, N.t_pool, N.cout, N.cout, m, reinterpret_cast<float*>(act[cur ^ 1]));
+                    full, N.cout, N.t_in, N.pool, N.t_pool, N.t_pool, N.cout, N.cout, m,
+                    reinterpret_cast<float*>(act[cur ^ 1]));
                 SB_COUNT_LAUNCH();
                 SB_CHECK_LAUNCH();
             }

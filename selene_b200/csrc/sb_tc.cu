@@ -39,7 +39,7 @@ constexpr int kTmemCols = 512;
 
 struct TcParams {
     long long rows_a;
-    int t_in, t_conv, pool, t_pool;
+    int t_in, t_conv, pool, t_pool, out_pitch;
     int out_ld, relu, out_f32;
     int block_n, n_tiles_n, n_tiles_m, num_k_blocks;
     int chunks_per_tap;  // 0: overlapping-stride A view; >0: per-tap boxes
@@ -166,7 +166,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const int t = (int)(rg - seq * p.t_in);
             const int tp = t / p.pool;
             const bool valid = (rg < p.rows_a) && (tp < p.t_pool);
-            const long long out_row = seq * p.t_pool + tp;
+            const long long out_row = seq * p.out_pitch + tp;
 
             sb_mbar_wait(&tfull_bar[as], aphase);
             sb_tc_fence_after();
@@ -331,6 +331,7 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream) {
     p.t_conv = L.t_conv;
     p.pool = L.pool;
     p.t_pool = L.t_conv / L.pool;
+    p.out_pitch = L.out_pitch > 0 ? L.out_pitch : p.t_pool;
     p.out_ld = L.out_ld;
     p.relu = L.relu;
     p.out_f32 = L.out_f32;

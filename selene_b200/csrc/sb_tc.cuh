@@ -30,6 +30,7 @@ struct SbTcLayer {
     int out_f32;         // 0: bf16 output, 1: fp32 output
     void* out;           // dev, (sequences * t_pool) x out_ld
     int out_ld;          // bf16: multiple of 8; fp32: multiple of 4
+    int out_pitch;       // rows per sequence in `out` (>= t_pool; the consumer's padded t_in); 0 = t_pool
 };
 
 int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream);

@@ -102,6 +102,8 @@ def layers_from_module(model):
             pending_bn = (scale, shift)
         elif isinstance(m, (nn.Dropout, nn.Sigmoid, nn.Identity, nn.Flatten)):
             continue
+        elif m.__class__.__name__ in ("Lambda", "LambdaBase"):
+            continue  # reshape helpers of models/seqweaver.py:9-23,44-55
         else:
             raise ValueError("unsupported module %s" % type(m).__name__)
     if pending_bn is not None:

@@ -369,3 +369,36 @@ def test_score_pairs_clamp_semantics(torch):
     assert np.array_equal(outs[0].cpu().numpy(), exp_abs)
     assert np.array_equal(outs[1].cpu().numpy(), exp_diff)
     assert np.allclose(outs[2].cpu().numpy(), exp_logit, rtol=2e-6, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------
+# the other conv stacks of the reference: HeartENN (BatchNorm folding, renorm, odd row pitches,
+# 60/80/240 channels) and Seqweaver (Conv2d (1,8) kernels, 160/320/480 channels)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("arch", ["heartenn", "seqweaver"])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+def test_other_conv_stacks_vs_torch(torch, arch, precision, tol):
+    import sb_models as M
+    from selene_b200.nets import B200Net, layers_from_module
+    torch.manual_seed(5)
+    if arch == "heartenn":
+        model = M.HeartENN(1000, 90)
+        M.randomize_batchnorm(model, 1)
+        with torch.no_grad():     # make the renorm of heartenn.py:73-78 bite, then apply it once as the host does
+            model.conv_net[0].weight.mul_(4.0)
+            for m in model.modules():
+                if isinstance(m, (torch.nn.Conv1d, torch.nn.Linear)):
+                    m.weight.data.renorm_(2, 0, 0.9)
+    else:
+        model = M.Seqweaver(217)
+    model.eval()
+    codes = _rand_codes(5, 1000, 21)
+    x = _onehot(codes)
+    with torch.no_grad():
+        exp = model(torch.tensor(x).transpose(1, 2)).numpy()
+    net = B200Net(layers_from_module(model), 1000)
+    got = net.forward_codes(torch.from_numpy(codes).cuda(), precision=precision).cpu().numpy()
+    assert got.shape == exp.shape
+    assert np.abs(got - exp).max() <= tol, np.abs(got - exp).max()
+    if precision == "bf16":
+        assert np.corrcoef(got.ravel(), exp.ravel())[0, 1] > 0.99
