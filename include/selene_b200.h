@@ -163,6 +163,15 @@ int sb_label_bins(const sb_intervals* iv, const int32_t* chrom, const int32_t* b
 /* ------------------------------------------------------------------------------------------ */
 #define SB_LAYER_CONV 1  /* Conv1d(cin,cout,k) valid, + bias, optional ReLU, optional MaxPool(pool) */
 #define SB_LAYER_FC 2    /* Linear(cin,cout) + bias, optional ReLU                                  */
+#define SB_LAYER_BILSTM 3 /* bidirectional single-layer LSTM(cin -> cout hidden); output 2*cout channels
+                           * [forward | backward] per position, flattened position-major for a following
+                           * FC.  Weights in torch layout, gate order i,f,g,o: weight = weight_ih_l0
+                           * (4*cout, cin), bias = bias_ih_l0, aux[0] = weight_hh_l0 (4*cout, cout),
+                           * aux[1] = bias_hh_l0, aux[2..5] = the same four tensors of the reverse
+                           * direction.  THE RECURRENCE RUNS OVER THE ROWS OF A BATCH, independently for
+                           * every position — that is what models/danQ.py:42-52 computes (it hands a
+                           * (positions, batch, channels) tensor to a batch_first LSTM), so
+                           * results depend on how rows are grouped: see sb_net_set_recurrence. */
 
 typedef struct {
     int32_t type;          /* SB_LAYER_*                                                           */
@@ -171,6 +180,7 @@ typedef struct {
     int32_t pool;          /* MaxPool1d(kernel=stride=pool) after ReLU; 0/1 = none                  */
     const float* weight;   /* host; torch layout: conv (cout,cin,k), fc (cout,cin)                  */
     const float* bias;     /* host (cout)                                                           */
+    const float* aux[6];   /* host; SB_LAYER_BILSTM only (see above), else ignored                  */
 } sb_layer;
 
 /* A network = conv layers on a (B, 4, L) one-hot input, flatten (channel-major, torch .view order:
@@ -182,6 +192,13 @@ int sb_net_destroy(sb_net* net);
 int sb_net_n_outputs(const sb_net* net);
 /* FLOPs (2 x MACs) of one forward of one sequence */
 double sb_net_flops_per_seq(const sb_net* net);
+
+/* Row grouping for SB_LAYER_BILSTM networks: rows are taken in consecutive blocks of
+ * group*interleave rows; inside a block, chain c (0 <= c < interleave) is rows c, c+interleave, ... and the
+ * LSTM state runs along each chain (forward direction first row to last, backward the reverse), starting
+ * from zero.  group = the reference caller's batch_size; interleave = 2 for interleaved ref/alt rows (the
+ * reference predicts the ref batch and the alt batch separately), else 1.  Default: group 64, interleave 1. */
+int sb_net_set_recurrence(sb_net* net, int group, int interleave);
 
 /* Per-layer device timing for roofline reports: when enabled, every layer launch is bracketed by
  * CUDA events on the launching stream; sb_net_layer_time sums them (synchronising on the events)

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libselene_b200.so")
 SB_OK = 0
 SB_F32, SB_BF16, SB_U8, SB_I64, SB_F64 = 0, 1, 2, 3, 4
 SB_FLAG_HAS_UPPER_N, SB_FLAG_HAS_UNK = 1, 2
-SB_LAYER_CONV, SB_LAYER_FC = 1, 2
+SB_LAYER_CONV, SB_LAYER_FC, SB_LAYER_BILSTM = 1, 2, 3
 SB_PREC_FP32, SB_PREC_BF16 = 0, 1
 SB_PAIR_INTERLEAVED, SB_PAIR_BASELINE = 0, 1
 
@@ -24,7 +24,7 @@ class SbError(RuntimeError):
 class sb_layer(C.Structure):
     _fields_ = [("type", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("k", C.c_int32),
                 ("relu", C.c_int32), ("pool", C.c_int32),
-                ("weight", C.c_void_p), ("bias", C.c_void_p)]
+                ("weight", C.c_void_p), ("bias", C.c_void_p), ("aux", C.c_void_p * 6)]
 
 
 _P = C.c_void_p
@@ -52,6 +52,7 @@ SIGNATURES = {
     "sb_net_destroy": (_I, [_P]),
     "sb_net_n_outputs": (_I, [_P]),
     "sb_net_flops_per_seq": (C.c_double, [_P]),
+    "sb_net_set_recurrence": (_I, [_P, _I, _I]),
     "sb_net_set_timing": (_I, [_P, _I]),
     "sb_net_n_layers": (_I, [_P]),
     "sb_net_layer_flops_per_seq": (C.c_double, [_P, _I]),

@@ -17,6 +17,7 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <algorithm>
 #include <vector>
 
 namespace {
@@ -39,6 +40,13 @@ struct NetLayer {
     float* lut;  // dev (k x 5 x cout)
     uint16_t* w1_packed;  // dev, tcgen05 core-matrix layout (sb_conv1.cu); null if unsupported
     float* bias1_padded;  // dev, n_pass*64
+    // SB_LAYER_BILSTM: the generic fields above hold the input projection (cin -> 8*hidden, both
+    // directions, bias = b_ih + b_hh); these hold the recurrent matrices (hidden -> 4*hidden) per direction
+    int hidden;
+    float* whh_f[2];            // dev (hidden x 4*hidden): row = K index
+    __nv_bfloat16* whh_b[2];    // dev (4*hidden x hidden_ld) K-major
+    float* zero_bias;           // dev, zeros (padded for the tcgen05 tiles)
+    int hh_block_n, hh_n_tiles_n, hidden_ld;
 };
 
 }  // namespace
@@ -51,6 +59,8 @@ struct sb_net {
     uint8_t perm[4];
     double flops_per_seq;
     bool force_per_tap;
+    int rec_group, rec_interleave;   // row grouping of BiLSTM recurrences (sb_net_set_recurrence)
+    bool has_lstm;
     std::vector<NetLayer> layers;
     // optional per-layer device timing (bench.py's roofline leg): one event pair per launch
     bool timing;
@@ -265,6 +275,60 @@ __global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ x,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// BiLSTM cell update for one step of every chain (torch gate order i, f, g, o)
+//   unit = (chain, position); chain = (block, c); row(chain, s) = block*G*I + c + I*s
+// ---------------------------------------------------------------------------------------------
+template <typename HT, typename OutT>
+__global__ void __launch_bounds__(256) lstm_cell_kernel(
+    const float* __restrict__ gates_f, const float* __restrict__ gates_b, int ld_gates, const float* __restrict__ xw,
+    int H, int T, int G, int I, long long m_rows, int step, long long n_units, HT* __restrict__ h_f,
+    HT* __restrict__ h_b, int h_ld, float* __restrict__ c_f, float* __restrict__ c_b, OutT* __restrict__ out,
+    int out_ld) {
+    const long long total = n_units * H * 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int j = (int)(idx % H);
+        long long r = idx / H;
+        const int dir = (int)(r & 1);
+        const long long unit = r >> 1;
+        const int p = (int)(unit % T);
+        const long long chain = unit / T;
+        const long long block = chain / I;
+        const int c = (int)(chain - block * I);
+        const long long first = block * G * I + c;
+        if (first >= m_rows) continue;
+        long long len = (m_rows - first + I - 1) / I;
+        if (len > G) len = G;
+        if (step >= len) continue;
+        const long long sidx = dir == 0 ? step : len - 1 - step;
+        const long long row = first + I * sidx;
+        const float* g = (dir == 0 ? gates_f : gates_b) + unit * ld_gates;
+        const float* x = xw + (row * T + p) * (long long)(8 * H) + (long long)dir * 4 * H;
+        float pi = x[j], pf = x[H + j], pg = x[2 * H + j], po = x[3 * H + j];
+        float* cs = (dir == 0 ? c_f : c_b) + unit * H + j;
+        float c_old = 0.f;
+        if (step > 0) {
+            pi += g[j]; pf += g[H + j]; pg += g[2 * H + j]; po += g[3 * H + j];
+            c_old = *cs;
+        }
+        const float ig = 1.f / (1.f + expf(-pi));
+        const float fg = 1.f / (1.f + expf(-pf));
+        const float gg = tanhf(pg);
+        const float og = 1.f / (1.f + expf(-po));
+        const float c_new = fg * c_old + ig * gg;
+        const float h_new = og * tanhf(c_new);
+        *cs = c_new;
+        (dir == 0 ? h_f : h_b)[unit * h_ld + j] = to_out<HT>(h_new);
+        out[(row * T + p) * (long long)out_ld + (long long)dir * H + j] = to_out<OutT>(h_new);
+    }
+}
+
+__global__ void __launch_bounds__(256) zero_u32_kernel(uint32_t* p, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = 0u;
+}
+
 int grid_for(long long total, int device) {
     long long b = (total + 255) / 256;
     const long long cap = (long long)sb_sm_count(device) * 16;
@@ -316,9 +380,14 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
     const char* env = getenv("SB_TC_PER_TAP");
     net->force_per_tap = env && env[0] == '1';
     net->timing = false;
+    net->rec_group = 64;
+    net->rec_interleave = 1;
+    net->has_lstm = false;
 
     int t = L, c = 4;          // current activation: t rows of c channels per sequence
     bool seen_fc = false;
+    bool prev_lstm = false;    // the FC right after a BiLSTM flattens position-major (danQ.py:46-50)
+    std::vector<float> lstm_w, lstm_b;
     for (int li = 0; li < n_layers; ++li) {
         const sb_layer& S = layers[li];
         SB_REQUIRE(S.weight && S.bias, "sb_net_create: layer %d has null weights", li);
@@ -339,29 +408,57 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
             SB_REQUIRE(N.pool == 1, "sb_net_create: FC layer %d cannot pool", li);
             N.k = 1; N.t_in = 1; N.t_conv = 1; N.t_pool = 1;
             net->flops_per_seq += 2.0 * (double)S.cout * S.cin;
+        } else if (S.type == SB_LAYER_BILSTM) {
+            SB_REQUIRE(!seen_fc && li > 0, "sb_net_create: BiLSTM layer %d must follow a conv layer", li);
+            SB_REQUIRE(S.cin == c, "sb_net_create: layer %d expects %d input channels, has %d", li, S.cin, c);
+            for (int a = 0; a < 6; ++a) SB_REQUIRE(S.aux[a], "sb_net_create: BiLSTM layer %d lacks aux[%d]", li, a);
+            const int H = S.cout;
+            N.hidden = H; N.k = 1; N.t_in = t; N.t_conv = t; N.t_pool = t; N.pool = 1; N.relu = 0;
+            N.cout = 8 * H;  // the input projection for both directions
+            lstm_w.assign((size_t)8 * H * S.cin, 0.f);
+            lstm_b.assign((size_t)8 * H, 0.f);
+            for (int d = 0; d < 2; ++d) {
+                const float* wih = d == 0 ? S.weight : S.aux[2];
+                const float* bih = d == 0 ? S.bias : S.aux[3];
+                const float* bhh = d == 0 ? S.aux[1] : S.aux[5];
+                for (int o = 0; o < 4 * H; ++o) {
+                    lstm_b[(size_t)d * 4 * H + o] = bih[o] + bhh[o];
+                    for (int cc = 0; cc < S.cin; ++cc)
+                        lstm_w[((size_t)d * 4 * H + o) * S.cin + cc] = wih[(size_t)o * S.cin + cc];
+                }
+            }
+            net->flops_per_seq += 2.0 * t * (8.0 * H * S.cin + 8.0 * H * H);
+            net->has_lstm = true;
         } else {
             sb_set_error("sb_net_create: unknown layer type %d", S.type);
             delete net;
             return SB_ERR_ARG;
         }
+        const bool is_lstm = S.type == SB_LAYER_BILSTM;
+        const float* Wsrc = is_lstm ? lstm_w.data() : S.weight;
+        const float* Bsrc = is_lstm ? lstm_b.data() : S.bias;
+        const int cout_eff = N.cout;
 
         // ---- logical K ordering shared by both paths: K index = tap * C + channel, where for the FC after
         //      the conv stack "tap" is the position t and "channel" the conv channel (torch flattens c*T + t)
-        const int taps = (S.type == SB_LAYER_CONV) ? S.k : (seen_fc ? 1 : t);
-        const int ch = (S.type == SB_LAYER_CONV) ? S.cin : (seen_fc ? S.cin : c);
+        const bool conv_like = S.type == SB_LAYER_CONV || is_lstm;
+        const int kk = is_lstm ? 1 : S.k;
+        const int taps = conv_like ? kk : (seen_fc ? 1 : t);
+        const int ch = conv_like ? S.cin : (seen_fc ? S.cin : c);
         auto w_at = [&](int o, int tap, int cc) -> float {
-            if (S.type == SB_LAYER_CONV) return S.weight[((size_t)o * S.cin + cc) * S.k + tap];
-            if (seen_fc) return S.weight[(size_t)o * S.cin + cc];
-            return S.weight[(size_t)o * S.cin + (size_t)cc * t + tap];  // flatten index c*T + t
+            if (conv_like) return Wsrc[((size_t)o * S.cin + cc) * kk + tap];
+            if (seen_fc) return Wsrc[(size_t)o * S.cin + cc];
+            if (prev_lstm) return Wsrc[(size_t)o * S.cin + (size_t)tap * c + cc];  // flatten index t*C + c
+            return Wsrc[(size_t)o * S.cin + (size_t)cc * t + tap];  // flatten index c*T + t
         };
 
         // ---- fp32 path
         N.k_f32 = taps * ch;
-        N.ldw_f32 = round_up(S.cout, 4);
+        N.ldw_f32 = round_up(cout_eff, 4);
         {
             std::vector<float> wf((size_t)N.k_f32 * N.ldw_f32, 0.f), bf((size_t)N.ldw_f32, 0.f);
-            for (int o = 0; o < S.cout; ++o) {
-                bf[o] = S.bias[o];
+            for (int o = 0; o < cout_eff; ++o) {
+                bf[o] = Bsrc[o];
                 for (int tap = 0; tap < taps; ++tap)
                     for (int cc = 0; cc < ch; ++cc) wf[((size_t)tap * ch + cc) * N.ldw_f32 + o] = w_at(o, tap, cc);
             }
@@ -397,14 +494,14 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
         }
 
         // ---- bf16 / tcgen05 path (every layer but the first)
-        N.out_ld_b = round_up(S.cout, 8);
+        N.out_ld_b = round_up(cout_eff, 8);
         if (li > 0) {
             const int a_ld_ch = round_up(ch, 8);   // channel stride of the incoming activation buffer
             N.a_ld = (S.type == SB_LAYER_FC) ? taps * a_ld_ch : a_ld_ch;
             N.k_full = taps * a_ld_ch;
             N.w_ld = round_up(N.k_full, 8);
-            std::vector<uint16_t> wb((size_t)S.cout * N.w_ld, 0);
-            for (int o = 0; o < S.cout; ++o)
+            std::vector<uint16_t> wb((size_t)cout_eff * N.w_ld, 0);
+            for (int o = 0; o < cout_eff; ++o)
                 for (int tap = 0; tap < taps; ++tap)
                     for (int cc = 0; cc < ch; ++cc)
                         wb[(size_t)o * N.w_ld + (size_t)tap * a_ld_ch + cc] = f32_to_bf16_bits(w_at(o, tap, cc));
@@ -413,34 +510,59 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
                 const int cpk = (a_ld_ch + 63) / 64;
                 N.k_full_tap = taps * cpk * 64;
                 N.w_ld_tap = N.k_full_tap;
-                std::vector<uint16_t> wt((size_t)S.cout * N.w_ld_tap, 0);
-                for (int o = 0; o < S.cout; ++o)
+                std::vector<uint16_t> wt((size_t)cout_eff * N.w_ld_tap, 0);
+                for (int o = 0; o < cout_eff; ++o)
                     for (int tap = 0; tap < taps; ++tap)
                         for (int cc = 0; cc < ch; ++cc)
                             wt[(size_t)o * N.w_ld_tap + (size_t)tap * cpk * 64 + cc] = f32_to_bf16_bits(w_at(o, tap, cc));
                 rc = upload(reinterpret_cast<uint16_t**>(&N.wb_tap), wt); if (rc) return rc;
             }
             // N tiling: fewest tiles of <= 256 columns, each a multiple of 16
-            const int nt = (S.cout + 255) / 256;
+            const int nt = (cout_eff + 255) / 256;
             N.n_tiles_n = nt;
-            N.block_n = round_up((S.cout + nt - 1) / nt, 16);
+            N.block_n = round_up((cout_eff + nt - 1) / nt, 16);
             std::vector<float> bb((size_t)N.n_tiles_n * N.block_n, 0.f);
-            for (int o = 0; o < S.cout; ++o) bb[o] = S.bias[o];
+            for (int o = 0; o < cout_eff; ++o) bb[o] = Bsrc[o];
             rc = upload(&N.biasb, bb); if (rc) return rc;
         }
 
+        if (is_lstm) {
+            const int H = N.hidden;
+            N.hidden_ld = round_up(H, 8);
+            N.out_ld_b = round_up(2 * H, 8);
+            const int nt = (4 * H + 255) / 256;
+            N.hh_n_tiles_n = nt;
+            N.hh_block_n = round_up((4 * H + nt - 1) / nt, 16);
+            std::vector<float> zb((size_t)std::max(nt * N.hh_block_n, round_up(4 * H, 4)), 0.f);
+            int rc = upload(&N.zero_bias, zb); if (rc) return rc;
+            for (int d = 0; d < 2; ++d) {
+                const float* whh = d == 0 ? S.aux[0] : S.aux[4];
+                const int ldw = round_up(4 * H, 4);
+                std::vector<float> wf((size_t)H * ldw, 0.f);
+                std::vector<uint16_t> wb((size_t)4 * H * N.hidden_ld, 0);
+                for (int o = 0; o < 4 * H; ++o)
+                    for (int k2 = 0; k2 < H; ++k2) {
+                        wf[(size_t)k2 * ldw + o] = whh[(size_t)o * H + k2];
+                        wb[(size_t)o * N.hidden_ld + k2] = f32_to_bf16_bits(whh[(size_t)o * H + k2]);
+                    }
+                rc = upload(&N.whh_f[d], wf); if (rc) return rc;
+                rc = upload(reinterpret_cast<uint16_t**>(&N.whh_b[d]), wb); if (rc) return rc;
+            }
+        }
         net->layers.push_back(N);
+        prev_lstm = false;
         if (S.type == SB_LAYER_CONV) { t = N.t_pool; c = S.cout; }
+        else if (is_lstm) { c = 2 * N.hidden; prev_lstm = true; }
         else { seen_fc = true; t = 1; c = S.cout; }
     }
     SB_REQUIRE(seen_fc, "sb_net_create: network must end in FC layers");
     for (size_t li = 0; li < net->layers.size(); ++li) {
         NetLayer& N = net->layers[li];
-        N.pitch_in = N.type == SB_LAYER_CONV ? round_up(N.t_in, N.pool) : 1;
+        N.pitch_in = N.type == SB_LAYER_FC ? 1 : round_up(N.t_in, N.pool);
     }
     for (size_t li = 0; li < net->layers.size(); ++li) {
         NetLayer& N = net->layers[li];
-        const bool next_conv = li + 1 < net->layers.size() && net->layers[li + 1].type == SB_LAYER_CONV;
+        const bool next_conv = li + 1 < net->layers.size() && net->layers[li + 1].type != SB_LAYER_FC;
         N.pitch_out = next_conv ? net->layers[li + 1].pitch_in : N.t_pool;
     }
     net->n_out = c;
@@ -453,8 +575,18 @@ extern "C" int sb_net_destroy(sb_net* net) {
     cudaSetDevice(net->device);
     for (auto& N : net->layers) {
         cudaFree(N.wf); cudaFree(N.biasf); cudaFree(N.wb); cudaFree(N.wb_tap); cudaFree(N.biasb); cudaFree(N.lut); cudaFree(N.w1_packed); cudaFree(N.bias1_padded);
+        cudaFree(N.whh_f[0]); cudaFree(N.whh_f[1]); cudaFree(N.whh_b[0]); cudaFree(N.whh_b[1]); cudaFree(N.zero_bias);
     }
     delete net;
+    return SB_OK;
+}
+
+extern "C" int sb_net_set_recurrence(sb_net* net, int group, int interleave) {
+    SB_REQUIRE(net, "sb_net_set_recurrence: null handle");
+    SB_REQUIRE(group >= 1 && (interleave == 1 || interleave == 2), "sb_net_set_recurrence: bad group %d / interleave %d",
+               group, interleave);
+    net->rec_group = group;
+    net->rec_interleave = interleave;
     return SB_OK;
 }
 
@@ -499,18 +631,27 @@ namespace {
 int chunk_rows(int precision) { return precision == SB_PREC_BF16 ? 8192 : 256; }
 
 // bytes of the two ping-pong activation buffers, the fp32 "full" buffer and the logits buffer
-struct WsPlan { size_t act, full, logits, total; };
+struct WsPlan { size_t act, full, logits, lstm, total; long long n_units; };
 
-long long chunk_for(int precision, bool generic) { return generic ? 256 : chunk_rows(precision); }
+long long chunk_for(const sb_net* net, int precision, bool generic) {
+    long long c = generic ? 256 : chunk_rows(precision);
+    if (net->has_lstm) {  // chunks must hold whole recurrence blocks
+        const long long blk = (long long)net->rec_group * net->rec_interleave;
+        if (c > 2048) c = 2048;
+        c = c / blk * blk;
+        if (c < blk) c = blk;
+    }
+    return c;
+}
 
 WsPlan plan_ws(const sb_net* net, long long n, int precision, bool generic) {
-    const long long cr = chunk_for(precision, generic);
+    const long long cr = chunk_for(net, precision, generic);
     const long long ch = n < cr ? n : cr;
     size_t act = 0, full = 0;
     const size_t es = precision == SB_PREC_BF16 ? 2 : 4;
     for (size_t li = 0; li < net->layers.size(); ++li) {
         const NetLayer& N = net->layers[li];
-        const int ld = precision == SB_PREC_BF16 ? N.out_ld_b : N.cout;
+        const int ld = precision == SB_PREC_BF16 ? N.out_ld_b : (N.type == SB_LAYER_BILSTM ? 2 * N.hidden : N.cout);
         const size_t bytes = (size_t)ch * (precision == SB_PREC_BF16 ? N.pitch_out : N.t_pool) * ld * es;
         if (bytes > act) act = bytes;
         if (precision == SB_PREC_FP32 && li > 0) {
@@ -524,12 +665,27 @@ WsPlan plan_ws(const sb_net* net, long long n, int precision, bool generic) {
         const size_t fb = (size_t)ch * N0.t_in * N0.cout * 4;
         if (fb > full) full = fb;
     }
+    size_t lstm = 0;
+    long long n_units = 0;
+    for (size_t li = 0; li < net->layers.size(); ++li) {
+        const NetLayer& N = net->layers[li];
+        if (N.type != SB_LAYER_BILSTM) continue;
+        const long long blk = (long long)net->rec_group * net->rec_interleave;
+        const long long chains = ((ch + blk - 1) / blk) * net->rec_interleave;
+        n_units = chains * N.t_in;
+        const size_t xw = (size_t)ch * N.t_in * 8 * N.hidden * 4;
+        if (xw > full) full = xw;
+        // gates (2 x units x 4H fp32) + h (2 x units x H_ld, 4 B each) + c (2 x units x H fp32)
+        lstm = (size_t)n_units * (2 * 4 * N.hidden * 4 + 2 * N.hidden_ld * 4 + 2 * N.hidden * 4) + 4096;
+    }
     auto al = [](size_t b) { return (b + 1023) / 1024 * 1024 + 1024; };
     WsPlan p;
+    p.lstm = al(lstm);
+    p.n_units = n_units;
     p.act = al(act);
     p.full = al(full);
     p.logits = al((size_t)ch * round_up(net->n_out, 4) * 4);
-    p.total = 2 * p.act + p.full + p.logits + 4096;
+    p.total = 2 * p.act + p.full + p.logits + p.lstm + 4096;
     return p;
 }
 
@@ -556,6 +712,90 @@ void time_end(sb_net* net, size_t li, cudaStream_t s) {
     if (!net->timing) return;
     cudaEventRecord(net->ev[li][net->ev_used[li] + 1], s);
     net->ev_used[li] += 2;
+}
+
+// One BiLSTM layer over m rows (T positions each): input projection as one GEMM, then G sequential
+// steps of (recurrent GEMM per direction + cell update) batched over every (chain, position) unit.
+int run_lstm(sb_net* net, const NetLayer& N, const void* act_in, void* act_out, long long m, int precision,
+             float* xw, uint8_t* lstm_ws, cudaStream_t stream) {
+    const bool bf = precision == SB_PREC_BF16;
+    const int dev = net->device;
+    const int H = N.hidden, T = N.t_in, G = net->rec_group, I = net->rec_interleave;
+    const long long rows = m * T;
+    const long long blk = (long long)G * I;
+    const long long chains = ((m + blk - 1) / blk) * I;
+    const long long U = chains * T;
+    // ---- input projection for both directions: xw[row*T + p][dir*4H + gate*H + j]
+    if (bf) {
+        SbTcLayer P;
+        memset(&P, 0, sizeof(P));
+        P.a = act_in; P.rows_a = rows; P.a_ld = N.a_ld; P.k_full = N.k_full;
+        P.w = N.wb; P.n_rows_w = 8 * H; P.w_ld = N.w_ld;
+        P.bias = N.biasb; P.block_n = N.block_n; P.n_tiles_n = N.n_tiles_n;
+        P.t_in = 1; P.t_conv = 1; P.pool = 1; P.relu = 0; P.out_f32 = 1; P.out = xw; P.out_ld = 8 * H;
+        int rc = sb_tc_launch(P, dev, stream);
+        if (rc) return rc;
+    } else {
+        dim3 grid((unsigned)((rows + FBM - 1) / FBM), (unsigned)((8 * H + FBN - 1) / FBN));
+        gemm_f32_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(act_in), rows * N.cin, N.cin, rows,
+                                                  N.k_f32, N.wf, N.ldw_f32, N.biasf, 0, xw, 8 * H, 8 * H);
+        SB_COUNT_LAUNCH();
+        SB_CHECK_LAUNCH();
+    }
+    // ---- state buffers
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(lstm_ws) + 255) & ~(uintptr_t)255);
+    float* gates[2];
+    gates[0] = reinterpret_cast<float*>(base);
+    gates[1] = gates[0] + U * 4 * H;
+    uint8_t* hb = reinterpret_cast<uint8_t*>(gates[1] + U * 4 * H);
+    const size_t h_bytes = (size_t)U * N.hidden_ld * 4;   // sized for fp32, bf16 uses half
+    void* h[2] = {hb, hb + h_bytes};
+    float* cst[2];
+    cst[0] = reinterpret_cast<float*>(hb + 2 * h_bytes);
+    cst[1] = cst[0] + U * H;
+    zero_u32_kernel<<<grid_for((long long)(2 * h_bytes / 4), dev), 256, 0, stream>>>(reinterpret_cast<uint32_t*>(hb),
+                                                                                     (long long)(2 * h_bytes / 4));
+    SB_COUNT_LAUNCH();
+    SB_CHECK_LAUNCH();
+    long long steps = (m + I - 1) / I;
+    if (steps > G) steps = G;
+    const int ld4 = round_up(4 * H, 4);
+    for (int step = 0; step < (int)steps; ++step) {
+        if (step > 0) {
+            for (int d = 0; d < 2; ++d) {
+                if (bf) {
+                    SbTcLayer R;
+                    memset(&R, 0, sizeof(R));
+                    R.a = h[d]; R.rows_a = U; R.a_ld = N.hidden_ld; R.k_full = N.hidden_ld;
+                    R.w = N.whh_b[d]; R.n_rows_w = 4 * H; R.w_ld = N.hidden_ld;
+                    R.bias = N.zero_bias; R.block_n = N.hh_block_n; R.n_tiles_n = N.hh_n_tiles_n;
+                    R.t_in = 1; R.t_conv = 1; R.pool = 1; R.relu = 0; R.out_f32 = 1; R.out = gates[d]; R.out_ld = 4 * H;
+                    int rc = sb_tc_launch(R, dev, stream);
+                    if (rc) return rc;
+                } else {
+                    dim3 grid((unsigned)((U + FBM - 1) / FBM), (unsigned)((4 * H + FBN - 1) / FBN));
+                    gemm_f32_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(h[d]), U * N.hidden_ld,
+                                                              N.hidden_ld, U, H, N.whh_f[d], ld4, N.zero_bias, 0,
+                                                              gates[d], 4 * H, 4 * H);
+                    SB_COUNT_LAUNCH();
+                    SB_CHECK_LAUNCH();
+                }
+            }
+        }
+        const int g = grid_for(U * H * 2, dev);
+        if (bf)
+            lstm_cell_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, stream>>>(
+                gates[0], gates[1], 4 * H, xw, H, T, G, I, m, step, U, reinterpret_cast<__nv_bfloat16*>(h[0]),
+                reinterpret_cast<__nv_bfloat16*>(h[1]), N.hidden_ld, cst[0], cst[1],
+                reinterpret_cast<__nv_bfloat16*>(act_out), N.out_ld_b);
+        else
+            lstm_cell_kernel<float, float><<<g, 256, 0, stream>>>(
+                gates[0], gates[1], 4 * H, xw, H, T, G, I, m, step, U, reinterpret_cast<float*>(h[0]),
+                reinterpret_cast<float*>(h[1]), N.hidden_ld, cst[0], cst[1], reinterpret_cast<float*>(act_out), 2 * H);
+        SB_COUNT_LAUNCH();
+        SB_CHECK_LAUNCH();
+    }
+    return SB_OK;
 }
 
 // Runs rows [r0, r0+m) through the network; leaves fp32 logits (row stride ldl) in ws logits buffer.
@@ -630,6 +870,14 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
         const NetLayer& N = net->layers[li];
         const bool last = li + 1 == net->layers.size();
         time_begin(net, li, stream);
+        if (N.type == SB_LAYER_BILSTM) {
+            uint8_t* lstm_ws = base + 2 * plan.act + plan.full + plan.logits;
+            int rc = run_lstm(net, N, act[cur], act[cur ^ 1], m, precision, full, lstm_ws, stream);
+            if (rc) return rc;
+            time_end(net, li, stream);
+            cur ^= 1;
+            continue;
+        }
         if (bf) {
             SbTcLayer T;
             memset(&T, 0, sizeof(T));
@@ -718,7 +966,7 @@ static int forward_impl(sb_net* net, const RowSource& in, int64_t n, int precisi
     cudaStream_t s = (cudaStream_t)stream;
     const WsPlan plan = plan_ws(net, n, precision, generic);
     const int F = net->n_out;
-    long long chunk = chunk_for(precision, generic);
+    long long chunk = chunk_for(net, precision, generic);
     if (scoring && pair_mode == SB_PAIR_INTERLEAVED) {
         SB_REQUIRE(n % 2 == 0, "interleaved ref/alt rows need an even row count, got %lld", (long long)n);
         chunk &= ~1ll;

@@ -77,6 +77,18 @@ def layers_from_module(model):
                 w = w * scale[None, :]
                 pending_bn = None
             layers.append(layer("fc", w, b, 0, 1))
+        elif isinstance(m, nn.LSTM):
+            # models/danQ.py:29-31.  The reference feeds it (positions, batch, channels) with
+            # batch_first=True, so the recurrence runs over the ROWS OF THE BATCH;
+            # sb_net reproduces exactly that (sb_net_set_recurrence / B200Net.set_recurrence).
+            if not (m.bidirectional and m.num_layers == 1 and m.bias):
+                raise ValueError("only single-layer bidirectional LSTMs with bias are supported")
+            if pending_bn is not None:
+                raise ValueError("BatchNorm before an LSTM cannot be folded")
+            g = lambda n: getattr(m, n).detach().cpu().numpy().astype(np.float32)
+            layers.append(dict(type="bilstm", weight=g("weight_ih_l0"), bias=g("bias_ih_l0"), relu=0, pool=1,
+                               aux=[g("weight_hh_l0"), g("bias_hh_l0"), g("weight_ih_l0_reverse"),
+                                    g("bias_ih_l0_reverse"), g("weight_hh_l0_reverse"), g("bias_hh_l0_reverse")]))
         elif isinstance(m, nn.ReLU):
             if pending_bn is not None:
                 raise ValueError("BatchNorm followed by ReLU cannot be folded forward")
@@ -126,9 +138,16 @@ class B200Net(object):
             w = np.ascontiguousarray(l["weight"], dtype=np.float32)
             b = np.ascontiguousarray(l["bias"], dtype=np.float32)
             keep += [w, b]
-            arr[i].type = _lib.SB_LAYER_CONV if l["type"] == "conv" else _lib.SB_LAYER_FC
+            arr[i].type = {"conv": _lib.SB_LAYER_CONV, "fc": _lib.SB_LAYER_FC,
+                           "bilstm": _lib.SB_LAYER_BILSTM}[l["type"]]
             if l["type"] == "conv":
                 arr[i].cout, arr[i].cin, arr[i].k = w.shape[0], w.shape[1], w.shape[2]
+            elif l["type"] == "bilstm":
+                arr[i].cout, arr[i].cin, arr[i].k = w.shape[0] // 4, w.shape[1], 1
+                for a, t in enumerate(l["aux"]):
+                    t = np.ascontiguousarray(t, dtype=np.float32)
+                    keep.append(t)
+                    arr[i].aux[a] = t.ctypes.data
             else:
                 arr[i].cout, arr[i].cin, arr[i].k = w.shape[0], w.shape[1], 1
             arr[i].relu = int(l.get("relu", 0))
@@ -152,6 +171,12 @@ class B200Net(object):
             except Exception:
                 pass
             self._h = None
+
+    def set_recurrence(self, group, interleave=1):
+        """Row grouping of BiLSTM recurrences (DanQ): ``group`` = the caller's batch_size, ``interleave``
+        = 2 when rows are interleaved ref/alt pairs.  No effect on networks without an LSTM."""
+        _lib.check(self._lib.sb_net_set_recurrence(self._h, int(group), int(interleave)), "sb_net_set_recurrence")
+        self._ws = None  # workspace size depends on the grouping
 
     def _workspace(self, n, precision):
         import torch

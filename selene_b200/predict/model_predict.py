@@ -220,6 +220,7 @@ class AnalyzeSequences(object):
         req = [s for s in want if s != "predictions"]
         if "predictions" in want:
             req += ["ref_predictions", "alt_predictions"]
+        self.net.set_recurrence(self.batch_size, 2)   # ref and alt batches are predicted separately
         out = self.net.forward_score(res["codes"], prep["src"], prep["pos"], prep["sub"], 2 * prep["n"],
                                      _lib.SB_PAIR_INTERLEAVED, precision=self.precision, want=tuple(req),
                                      outs=outs)
@@ -248,6 +249,7 @@ class AnalyzeSequences(object):
         inter = np.empty((2 * n, L), dtype=np.uint8)
         inter[0::2], inter[1::2] = ref_codes, alt_codes
         codes = torch.from_numpy(inter).cuda()
+        self.net.set_recurrence(self.batch_size, 2)
         req = [s for s in want if s != "predictions"]
         if "predictions" in want:
             req += ["ref_predictions", "alt_predictions"]
@@ -266,6 +268,7 @@ class AnalyzeSequences(object):
         if end_position is None:
             end_position = self.sequence_length
         pos, alt, codes = ism_mutations_device(sequence, start_position, end_position, self.reference_sequence)
+        self.net.set_recurrence(self.batch_size, 1)
         base = self.net.forward_codes(codes, precision=self.precision)          # (1, F) baseline
         m = int(pos.numel())
         req = [s for s in want if s != "predictions"]

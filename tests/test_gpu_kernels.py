@@ -402,3 +402,35 @@ def test_other_conv_stacks_vs_torch(torch, arch, precision, tol):
     assert np.abs(got - exp).max() <= tol, np.abs(got - exp).max()
     if precision == "bf16":
         assert np.corrcoef(got.ravel(), exp.ravel())[0, 1] > 0.99
+
+
+# ------------------------------------------------------------------------------------------------
+# DanQ: conv(k=26)+pool13 -> BiLSTM whose recurrence runs over the batch rows (reference quirk) -> FC
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+def test_danq_batch_axis_recurrence_vs_torch(torch, precision, tol):
+    import sb_models as M
+    from selene_b200.nets import B200Net, layers_from_module
+    torch.manual_seed(9)
+    model = M.DanQ(1000, 919).eval()
+    codes = _rand_codes(7, 1000, 31)
+    x = torch.tensor(_onehot(codes)).transpose(1, 2)
+    net = B200Net(layers_from_module(model), 1000)
+    dev_codes = torch.from_numpy(codes).cuda()
+    with torch.no_grad():
+        whole = model(x).numpy()                                       # one predict() call of 7 rows
+        split = np.concatenate([model(x[:3]).numpy(), model(x[3:6]).numpy(), model(x[6:]).numpy()])
+    assert np.abs(whole - split).max() > 1e-4                          # the quirk is real: grouping matters
+    net.set_recurrence(7, 1)
+    got = net.forward_codes(dev_codes, precision=precision).cpu().numpy()
+    assert np.abs(got - whole).max() <= tol, np.abs(got - whole).max()
+    net.set_recurrence(3, 1)
+    got = net.forward_codes(dev_codes, precision=precision).cpu().numpy()
+    assert np.abs(got - split).max() <= tol, np.abs(got - split).max()
+    if precision == "fp32":
+        # interleaved ref/alt rows: the even rows form one chain, the odd rows another
+        net.set_recurrence(4, 2)
+        got = net.forward_codes(dev_codes[:6], precision=precision).cpu().numpy()
+        with torch.no_grad():
+            exp_even, exp_odd = model(x[0:6:2]).numpy(), model(x[1:6:2]).numpy()
+        assert np.abs(got[0::2] - exp_even).max() <= tol and np.abs(got[1::2] - exp_odd).max() <= tol
