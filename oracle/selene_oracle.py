@@ -376,3 +376,101 @@ def vep_scores(genome, variants, layers, sequence_length, batch_size=64, bases_a
     if refs:
         flush()
     return np.concatenate(absd), np.concatenate(logits), np.array(matches), np.array(unks)
+
+
+# ------------------------------------------------------------------------------------------------
+# stage 1 caller: RandomPositionsSampler (training config)
+# ------------------------------------------------------------------------------------------------
+def get_indices_and_probabilities(interval_lengths, indices):
+    """selene_sdk/utils/utils.py:34-67."""
+    select = np.array(interval_lengths)[indices]
+    weights = select / float(np.sum(select))
+    keep = [indices[i] for i, w in enumerate(weights) if w > 1e-10]
+    if len(keep) == len(indices):
+        return indices, weights.tolist()
+    return get_indices_and_probabilities(interval_lengths, keep)
+
+
+class RandomPositionsSamplerOracle(object):
+    """selene_sdk/samplers/random_positions_sampler.py:120-369 + online_sampler.py:121-216,
+    chromosome-holdout mode, on a dict genome and BED rows.  RNG streams exactly as the reference:
+    ``np.random.seed(seed)``, ``random.seed(seed + 1)`` (online_sampler.py:136-138); one
+    ``np.random.choice(indices, 200000, p=weights)`` cache per mode at first use for ALL modes
+    (:175-176,306-314); per draw ``np.random.randint(cstart, cend)`` then, after the label query,
+    ``random.randint(0, 1)`` for the strand (:277); rejected draws consume both."""
+    STRAND_SIDES = ('+', '-')
+
+    def __init__(self, genome, rows_by_chrom, features, seed=436, validation_holdout=('chr6', 'chr7'),
+                 test_holdout=('chr8', 'chr9'), exclude_chrs=('_',), sequence_length=1000,
+                 center_bin_to_predict=200, feature_thresholds=0.5, mode="train"):
+        import random
+        self._random = random
+        np.random.seed(seed)
+        random.seed(seed + 1)
+        self.genome, self.rows = genome, rows_by_chrom
+        self.features = list(features)
+        self.fid = {f: i for i, f in enumerate(self.features)}
+        self.thr = np.full(len(self.features), feature_thresholds, dtype=np.float32)
+        self.sequence_length = sequence_length
+        self.modes = ["train", "validate"] + (["test"] if test_holdout else [])
+        self.mode = mode
+        wr = int(sequence_length / 2)
+        self._start_window_radius, self._end_window_radius = wr, wr + (1 if sequence_length % 2 else 0)
+        br = int(center_bin_to_predict / 2)
+        self._start_radius, self._end_radius = br, br + (1 if center_bin_to_predict % 2 else 0)
+        by_mode = {m: [] for m in self.modes}
+        self.sample_from_intervals, self.interval_lengths = [], []
+        index = 0
+        for chrom in sorted(genome.keys()):
+            n = len(genome[chrom])
+            if any(e in chrom for e in exclude_chrs):
+                continue
+            if chrom in validation_holdout:
+                by_mode["validate"].append(index)
+            elif test_holdout and chrom in test_holdout:
+                by_mode["test"].append(index)
+            else:
+                by_mode["train"].append(index)
+            self.sample_from_intervals.append((chrom, sequence_length, n - sequence_length))
+            self.interval_lengths.append(n - 2 * sequence_length)
+            index += 1
+        self._from_mode = {m: get_indices_and_probabilities(self.interval_lengths, by_mode[m]) for m in self.modes}
+        self._cache = {}
+        for m in self.modes:
+            self._update_randcache(m)
+
+    def _update_randcache(self, mode):
+        ind, w = self._from_mode[mode]
+        self._cache[mode] = {"idx": np.random.choice(ind, size=200000, replace=True, p=w), "next": 0}
+
+    def _retrieve(self, chrom, position):
+        bs, be = position - self._start_radius, position + self._end_radius
+        targets = fast_get_feature_data(bs, be, self.thr, self.fid, query_rows(self.rows, chrom, bs, be))
+        ws, we = position - self._start_window_radius, position + self._end_window_radius
+        strand = self.STRAND_SIDES[self._random.randint(0, 1)]
+        seq = sequence_to_encoding(get_sequence_from_coords(self.genome, chrom, ws, we, strand))
+        if seq.shape[0] == 0 or np.mean(seq == 0.25) > 0.30:
+            return None
+        return seq, targets
+
+    def sample(self, batch_size=1, mode=None):
+        mode = mode or self.mode
+        sequences = np.zeros((batch_size, self.sequence_length, 4))
+        targets = np.zeros((batch_size, len(self.features)))
+        n = 0
+        while n < batch_size:
+            c = self._cache[mode]
+            if c["next"] == len(c["idx"]):
+                self._update_randcache(self.mode)   # the reference refreshes self.mode's cache (:352)
+                c = self._cache[mode]
+                c["next"] = 0
+            k = c["idx"][c["next"]]
+            c["next"] += 1
+            chrom, cstart, cend = self.sample_from_intervals[k]
+            position = np.random.randint(cstart, cend)
+            out = self._retrieve(chrom, position)
+            if not out:
+                continue
+            sequences[n], targets[n] = out
+            n += 1
+        return sequences, targets

@@ -198,7 +198,7 @@ class Genome(object):
     # -- lazy initialisation (genome.py:288-316) --------------------------------------------------
     def __getstate__(self):
         state = dict(self.__dict__)
-        for k in ("_handle", "_seqs", "_chrom_index", "chrs", "len_chrs", "_blacklist", "_chrom_off"):
+        for k in ("_handle", "_seqs", "_chrom_index", "chrs", "len_chrs", "_blacklist", "_chrom_off", "_unk_prefix"):
             state.pop(k, None)
         state["_initialized"] = False
         return state
@@ -338,6 +338,33 @@ class Genome(object):
                     break
             sequence.append(cls.UNK_BASE if base_pos == -1 else cls.BASES_ARR[base_pos])
         return "".join(sequence)
+
+    # -- host-side unknown-base counts (sampler rejection test without a device round trip) ----------
+    @init
+    def count_unknown(self, chrom, start, end):
+        """Number of positions in [start, end) of ``chrom`` whose character is outside ACGTacgt (what
+        ``sequence_to_encoding`` turns into 0.25 rows); positions outside the chromosome count too."""
+        n = self.len_chrs[chrom]
+        out = max(0, -start) + max(0, end - n)
+        start, end = max(start, 0), min(end, n)
+        if end <= start:
+            return out
+        if not hasattr(self, "_unk_prefix"):
+            self._unk_prefix = {}
+        if chrom not in self._unk_prefix:
+            unk = _CODE_LUT[self._seqs[chrom]] == 4
+            bits = np.packbits(unk, bitorder="little")
+            pop = np.unpackbits(bits.reshape(-1, 1), axis=1).sum(axis=1, dtype=np.int64)
+            self._unk_prefix[chrom] = (bits, np.concatenate([[0], np.cumsum(pop)]))
+        bits, prefix = self._unk_prefix[chrom]
+
+        def upto(x):  # unknown positions in [0, x)
+            b, r = x >> 3, x & 7
+            v = int(prefix[b])
+            if r:
+                v += bin(int(bits[b]) & ((1 << r) - 1)).count("1")
+            return v
+        return out + upto(end) - upto(start)
 
     # -- batched device API -------------------------------------------------------------------------
     def _window_args(self, chroms, starts, strands):

@@ -212,3 +212,21 @@ def test_indel_windows_match_reference_goldens():
         assert np.array_equal(O.sequence_to_encoding(rs), gold["indel_ref_onehot"][i]), line
         assert np.array_equal(O.sequence_to_encoding(als), gold["indel_alt_onehot"][i]), line
         assert m == bool(gold["indel_match"][i]) and u == bool(gold["indel_unk"][i])
+
+
+def test_count_unknown_host_prefix():
+    """Genome.count_unknown (the sampler's rejection test) against a direct count, without a GPU."""
+    from selene_b200.sequences.genome import Genome
+    g = H.synth_genome(n_chrom=1, length=3000, n_frac=0.1)
+    G = Genome.__new__(Genome)
+    seq = g["chr1"]
+    G._initialized = True
+    G._seqs = {"chr1": np.frombuffer(seq.encode(), np.uint8)}
+    G.len_chrs = {"chr1": len(seq)}
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        s = int(rng.integers(-50, len(seq)))
+        e = s + int(rng.integers(1, 400))
+        inner = seq[max(s, 0):min(e, len(seq))]
+        exp = sum(ch not in "ACGTacgt" for ch in inner) + max(0, -s) + max(0, e - len(seq))
+        assert G.count_unknown("chr1", s, e) == exp

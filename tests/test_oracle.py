@@ -217,3 +217,18 @@ def test_oracle_vs_compiled_reference_modules():
         rows = O.query_rows(by, c, s, e)
         assert np.array_equal(gfm._fast_get_feature_data(s, e, thr.copy(), fid, rows),
                               O.fast_get_feature_data(s, e, thr.copy(), fid, rows))
+
+
+def test_golden_sampler():
+    """RandomPositionsSampler: same RNG streams, same draws, same rejections as the reference."""
+    g = H.synth_genome(n_chrom=5, length=6000, n_frac=0.08)
+    rows = H.rows_by_chrom(H.synth_intervals(g, n_features=12, per_feature=120, seed=3))
+    s = O.RandomPositionsSamplerOracle(g, rows, ["f%d" % i for i in range(12)], seed=436,
+                                       validation_holdout=['chr4'], test_holdout=['chr5'])
+    a, ta = s.sample(16)
+    b, tb = s.sample(5, mode="validate")
+    assert np.array_equal(a.astype(np.float32), GOLD["sampler_seq_train"])
+    assert np.array_equal(ta.astype(np.float32), GOLD["sampler_tgt_train"])
+    assert np.array_equal(b.astype(np.float32), GOLD["sampler_seq_val"])
+    assert np.array_equal(tb.astype(np.float32), GOLD["sampler_tgt_val"])
+    assert (GOLD["sampler_seq_train"] == 0.25).any() and GOLD["sampler_tgt_train"].sum() > 0
