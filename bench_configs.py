@@ -1,0 +1,195 @@
+"""Secondary measurements (not the driver's contract — that is bench.py): the HBM-bound kernels
+against the measured copy bandwidth, and BASELINE.json's other configs (ISM latency, DanQ ISM,
+Seqweaver / HeartENN sweeps, sampler rate).  Prints one JSON object per line; run on a B200:
+
+    python bench_configs.py [--quick]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def timed(fn, warmup=3, iters=10):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    import torch
+    import bench as B
+    import sb_helpers as H
+    import sb_models as M
+    from selene_b200 import _lib
+    from selene_b200.sequences import Genome
+    from selene_b200.targets import GenomicFeatures
+    from selene_b200.nets import B200Net, layers_from_module
+    from selene_b200.predict.model_predict import AnalyzeSequences
+    from selene_b200.predict._in_silico_mutagenesis import ism_mutations_device, expand_mutants_device
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}
+    hbm = float(peaks["hbm_gbs"])
+    out = []
+
+    def emit(**kw):
+        print(json.dumps(kw))
+        sys.stdout.flush()
+        out.append(kw)
+
+    names, seqs = B.synth_genome_arrays(48.0 if args.quick else 240.0)
+    G = Genome.from_sequences(names, seqs)
+    Genome.update_bases_order(['A', 'C', 'G', 'T'])
+    per = len(seqs[0])
+    rng = np.random.default_rng(1)
+
+    # ---------------------------------------------------------------- kernel (a): encode windows
+    n = 65536
+    chrom = torch.from_numpy(rng.integers(0, len(names), n).astype(np.int32)).cuda()
+    start = torch.from_numpy(rng.integers(0, per - 1000, n).astype(np.int64)).cuda()
+    rc = torch.from_numpy(rng.integers(0, 2, n).astype(np.uint8)).cuda()
+    for dt, bpw in (("float32", 16375.0), ("bfloat16", 8375.0)):
+        t = timed(lambda: G.encode_windows(chrom, start, 1000, strands=rc, dtype=dt))
+        gbs = n * bpw / t / 1e9
+        emit(kernel="sb_encode_windows", dtype=dt, windows=n, L=1000, ms=t * 1e3, algorithmic_bytes_per_window=bpw,
+             achieved_gbs=gbs, peak_gbs=hbm, frac=gbs / hbm, windows_per_s=n / t)
+    # ---------------------------------------------------------------- ISM expansion (one-hot mutants)
+    r = np.random.default_rng(0)
+    seq = "".join(np.array(list("ACGT"))[r.integers(0, 4, 1000)].tolist())
+    pos, alt, codes = ism_mutations_device(seq)
+    reps = 8
+    pos_r, alt_r = pos.repeat(reps), alt.repeat(reps)
+    t = timed(lambda: expand_mutants_device(codes, pos_r, alt_r))
+    gbs = pos_r.numel() * 16000.0 / t / 1e9
+    emit(kernel="sb_ism_expand", mutants=int(pos_r.numel()), ms=t * 1e3, achieved_gbs=gbs, peak_gbs=hbm, frac=gbs / hbm)
+
+    # ---------------------------------------------------------------- kernel (b): labels
+    F = 919
+    nrows = 400000 if args.quick else 2000000
+    lr = np.random.default_rng(7)
+    c_i = lr.integers(0, len(names), nrows).astype(np.int32)
+    s_i = lr.integers(0, per - 3000, nrows).astype(np.int32)
+    ln = np.clip(lr.lognormal(np.log(300), 0.8, nrows), 50, 2000).astype(np.int32)
+    f_i = lr.integers(0, F, nrows).astype(np.int32)
+    import ctypes as C
+    lib = _lib.load()
+    h = C.c_void_p()
+    _lib.check(lib.sb_intervals_create(_lib.ptr(c_i), _lib.ptr(s_i), _lib.ptr(np.ascontiguousarray(s_i + ln)),
+                                       _lib.ptr(f_i), nrows, F, len(names), 0, C.byref(h)), "sb_intervals_create")
+    nq = 65536
+    qc = torch.from_numpy(lr.integers(0, len(names), nq).astype(np.int32)).cuda()
+    qs_np = lr.integers(0, per - 200, nq).astype(np.int32)
+    qs = torch.from_numpy(qs_np).cuda()
+    qe = torch.from_numpy(qs_np + 200).cuda()
+    thr = torch.full((F,), 99, dtype=torch.int32, device="cuda")
+    for dt, code, tdt, sz in (("uint8", _lib.SB_U8, torch.uint8, 1), ("float32", _lib.SB_F32, torch.float32, 4),
+                              ("int64", _lib.SB_I64, torch.int64, 8)):
+        o = torch.empty((nq, F), dtype=tdt, device="cuda")
+        t = timed(lambda: _lib.check(lib.sb_label_bins(h, _lib.ptr(qc), _lib.ptr(qs), _lib.ptr(qe), nq, _lib.ptr(thr),
+                                                       code, _lib.ptr(o), _lib.stream_ptr()), "sb_label_bins"))
+        hits = float(nrows) * 500.0 / (per * len(names))     # expected overlapping intervals per query
+        bytes_q = F * sz + 12.0 * hits
+        gbs = nq * bytes_q / t / 1e9
+        emit(kernel="sb_label_bins", out_dtype=dt, queries=nq, features=F, intervals=nrows, ms=t * 1e3,
+             algorithmic_bytes_per_query=bytes_q, achieved_gbs=gbs, peak_gbs=hbm, frac=gbs / hbm, queries_per_s=nq / t,
+             positives=float(o.float().mean().item()))
+    lib.sb_intervals_destroy(h)
+
+    # ---------------------------------------------------------------- config 1: DeepSEA ISM of one sequence
+    torch.manual_seed(0)
+    feats = ["f%d" % i for i in range(919)]
+    az = AnalyzeSequences(M.DeepSEA(1000, 919), sequence_length=1000, features=feats, reference_sequence=Genome)
+    for prec in ("bf16", "fp32"):
+        az.precision = prec
+        az.ism_scores(seq, ("abs_diffs", "logits"))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        k = 5 if prec == "bf16" else 2
+        for _ in range(k):
+            _, res, _ = az.ism_scores(seq, ("abs_diffs", "logits"))
+        dt_ = (time.perf_counter() - t0) / k
+        emit(config="1: DeepSEA ISM, one 1000-bp sequence, 3000 mutants, abs_diffs+logits to host", precision=prec,
+             seconds=dt_, mutants_per_s=3000 / dt_)
+
+    # ---------------------------------------------------------------- config 4: DanQ ISM
+    torch.manual_seed(0)
+    azd = AnalyzeSequences(M.DanQ(1000, 919), sequence_length=1000, features=feats, reference_sequence=Genome)
+    n_seq = 2 if args.quick else 6
+    azd.ism_scores(seq, ("abs_diffs",), to_host=False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(n_seq):
+        azd.ism_scores(seq, ("abs_diffs", "logits"), to_host=False)
+    torch.cuda.synchronize()
+    dt_ = (time.perf_counter() - t0) / n_seq
+    emit(config="4: DanQ ISM (batch-axis recurrence, groups of 64), per 1000-bp sequence of 3000 mutants", precision="bf16",
+         seconds_per_sequence=dt_, mutants_per_s=3000 / dt_, flops_per_seq=azd.net.flops_per_seq,
+         tflops=3000 / dt_ * azd.net.flops_per_seq / 1e12)
+
+    # ---------------------------------------------------------------- config 5: Seqweaver / HeartENN sweep
+    for name, model in (("Seqweaver(217)", M.Seqweaver(217)), ("HeartENN(1000, 90)", M.HeartENN(1000, 90))):
+        torch.manual_seed(0)
+        model.eval()
+        net = B200Net(layers_from_module(model), 1000)
+        for batch in (64, 256, 1024, 4096):
+            codes_b = torch.from_numpy(rng.integers(0, 4, (batch, 1000)).astype(np.uint8)).cuda()
+            src = torch.arange(batch, dtype=torch.int32, device="cuda").repeat_interleave(2)
+            p_ = torch.full((2 * batch,), 499, dtype=torch.int32, device="cuda")
+            sc = torch.from_numpy(rng.integers(0, 4, 2 * batch).astype(np.uint8)).cuda()
+            fn = lambda: net.forward_score(codes_b, src, p_, sc, 2 * batch, _lib.SB_PAIR_INTERLEAVED, precision="bf16",
+                                           want=("abs_diffs", "logits"))
+            t = timed(fn, warmup=2, iters=5)
+            tf = 2 * batch * net.flops_per_seq / t / 1e12
+            emit(config="5: %s VEP-style scoring" % name, variants_per_batch=batch, ms=t * 1e3,
+                 predictions_per_s=2 * batch / t, tflops=tf, tensor_frac_of_sustained=tf / float(peaks["bf16_tflops_sustained"]))
+
+    # ---------------------------------------------------------------- config 3 (sampling half): sampler rate
+    from selene_b200.samplers import RandomPositionsSampler
+    import gzip
+    bed = "/tmp/bench_feat.bed.gz"
+    order = np.lexsort((s_i, c_i))
+    with gzip.open(bed, "wt", compresslevel=1) as fh:
+        for k in order[:300000]:
+            fh.write("%s\t%d\t%d\tf%d\n" % (names[c_i[k]], s_i[k], s_i[k] + ln[k], f_i[k]))
+    smp = RandomPositionsSampler(G, bed, feats, seed=436, validation_holdout=['chr6', 'chr7'],
+                                 test_holdout=['chr8', 'chr9'], sequence_length=1000, center_bin_to_predict=200,
+                                 feature_thresholds=0.5)
+    smp.sample_device(64)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    nb = 20
+    for _ in range(nb):
+        smp.sample_device(64)
+    torch.cuda.synchronize()
+    dt_ = (time.perf_counter() - t0) / nb
+    emit(config="3 (sampling half): RandomPositionsSampler.sample_device(64), 919 features", seconds_per_batch=dt_,
+         samples_per_s=64 / dt_)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        smp.sample(64)
+    dt_ = (time.perf_counter() - t0) / 5
+    emit(config="3 (sampling half): RandomPositionsSampler.sample(64) -> float64 numpy (reference signature)",
+         seconds_per_batch=dt_, samples_per_s=64 / dt_)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
