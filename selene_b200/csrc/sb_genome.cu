@@ -104,38 +104,72 @@ __device__ __forceinline__ void store_onehot(void* out, int64_t base_index, int 
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-// One CTA per window.  MODE 0: codes only; 1: one-hot fp32; 2: one-hot bf16.
+// One WARP per window, grid-stride over windows.  MODE 0: codes only; 1: one-hot fp32; 2: one-hot bf16.
+// Lane l of iteration k owns BPL consecutive bases (1 for fp32, 2 for bf16, 16 for codes) so that every
+// store is one 16-byte store and a warp writes 512 contiguous bytes per instruction; the per-window
+// flags are a warp reduction (no block barrier, no shared memory).
 template <int MODE>
 __global__ void __launch_bounds__(256) window_kernel(GenomeView g, const int32_t* __restrict__ chrom,
                                                      const int64_t* __restrict__ start,
-                                                     const uint8_t* __restrict__ strand_rc, int L,
+                                                     const uint8_t* __restrict__ strand_rc, int n, int L,
                                                      Perm perm, void* __restrict__ out,
                                                      uint8_t* __restrict__ flags_out) {
-    const int w = blockIdx.x;
-    const int c = chrom[w];
-    const int64_t coff = g.chrom_off[c];
-    const int64_t clen = g.chrom_len[c];
-    const int64_t st = start[w];
-    const bool rc = strand_rc != nullptr && strand_rc[w] != 0;
-    int flags = 0;
-    for (int i = threadIdx.x; i < L; i += blockDim.x) {
-        bool upn;
-        const int code = window_code(g, coff, clen, st, L, rc, i, &upn);
-        if (code > 3) flags |= SB_FLAG_HAS_UNK;
-        if (upn) flags |= SB_FLAG_HAS_UPPER_N;
-        const int64_t o = (int64_t)w * L + i;
-        if (MODE == 0) {
-            reinterpret_cast<uint8_t*>(out)[o] = (uint8_t)code;
-        } else {
-            store_onehot<MODE == 2>(out, o, code, perm);
+    constexpr int BPL = MODE == 1 ? 1 : (MODE == 2 ? 2 : 16);
+    const int lane = threadIdx.x & 31;
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n; w += warps_total) {
+        const int c = chrom[w];
+        const int64_t coff = g.chrom_off[c];
+        const int64_t clen = g.chrom_len[c];
+        const int64_t st = start[w];
+        const bool rc = strand_rc != nullptr && strand_rc[w] != 0;
+        int flags = 0;
+        for (int i0 = lane * BPL; i0 < L; i0 += 32 * BPL) {
+            int codes[BPL];
+#pragma unroll
+            for (int b = 0; b < BPL; ++b) {
+                bool upn = false;
+                int code = 4;
+                if (i0 + b < L) {
+                    code = window_code(g, coff, clen, st, L, rc, i0 + b, &upn);
+                    if (code > 3) flags |= SB_FLAG_HAS_UNK;
+                    if (upn) flags |= SB_FLAG_HAS_UPPER_N;
+                }
+                codes[b] = code;
+            }
+            const int64_t o = (int64_t)w * L + i0;
+            if (MODE == 1) {
+                reinterpret_cast<float4*>(out)[o] = onehot_f32(codes[0], perm);
+            } else if (MODE == 2) {
+                // two bases = 16 bytes when both exist and the address is 16-byte aligned
+                uint2* p = reinterpret_cast<uint2*>(out) + o;
+                if (i0 + 1 < L && ((o & 1) == 0)) {
+                    const uint2 a = onehot_bf16(codes[0], perm), b2 = onehot_bf16(codes[1], perm);
+                    *reinterpret_cast<uint4*>(p) = make_uint4(a.x, a.y, b2.x, b2.y);
+                } else {
+                    p[0] = onehot_bf16(codes[0], perm);
+                    if (i0 + 1 < L) p[1] = onehot_bf16(codes[1], perm);
+                }
+            } else {
+                uint8_t* p = reinterpret_cast<uint8_t*>(out) + o;
+                if (i0 + 16 <= L && ((o & 15) == 0)) {
+                    uint32_t wd[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        wd[k] = (uint32_t)codes[4 * k] | ((uint32_t)codes[4 * k + 1] << 8) |
+                                ((uint32_t)codes[4 * k + 2] << 16) | ((uint32_t)codes[4 * k + 3] << 24);
+                    *reinterpret_cast<uint4*>(p) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+                } else {
+#pragma unroll
+                    for (int b = 0; b < BPL; ++b)
+                        if (i0 + b < L) p[b] = (uint8_t)codes[b];
+                }
+            }
         }
-    }
-    if (flags_out != nullptr) {  // uniform branch
-        const int any_unk = __syncthreads_or(flags & SB_FLAG_HAS_UNK);
-        const int any_upn = __syncthreads_or(flags & SB_FLAG_HAS_UPPER_N);
-        if (threadIdx.x == 0)
-            flags_out[w] = (uint8_t)((any_unk ? SB_FLAG_HAS_UNK : 0) |
-                                     (any_upn ? SB_FLAG_HAS_UPPER_N : 0));
+        if (flags_out != nullptr) {
+            flags = __reduce_or_sync(0xffffffffu, flags);
+            if (lane == 0) flags_out[w] = (uint8_t)flags;
+        }
     }
 }
 
@@ -296,6 +330,12 @@ static bool perm_ok(const uint8_t perm[4]) {
     }
     return seen == 15;
 }
+static int window_grid(int n, int device) {
+    const long long blocks = ((long long)n + 7) / 8;           // 8 warps (windows) per CTA
+    const long long cap = (long long)sb_sm_count(device) * 8;  // persistent: 8 CTAs of 256 threads per SM
+    return (int)(blocks < cap ? blocks : cap);
+}
+
 static GenomeView view_of(const sb_genome* g) {
     GenomeView v;
     v.packed = g->packed;
@@ -360,8 +400,8 @@ extern "C" int sb_genome_codes(const sb_genome* g, const int32_t* chrom, const i
     SB_REQUIRE(n >= 0 && L > 0, "sb_genome_codes: bad sizes n=%d L=%d", n, L);
     if (n == 0) return SB_OK;
     Perm p = {{0, 1, 2, 3}};
-    window_kernel<0><<<n, 256, 0, (cudaStream_t)stream>>>(view_of(g), chrom, start, strand_rc, L, p,
-                                                          codes_out, flags_out);
+    window_kernel<0><<<window_grid(n, g->device), 256, 0, (cudaStream_t)stream>>>(view_of(g), chrom, start, strand_rc,
+                                                                                  n, L, p, codes_out, flags_out);
     SB_COUNT_LAUNCH();
     SB_CHECK_LAUNCH();
     return SB_OK;
@@ -379,9 +419,11 @@ extern "C" int sb_encode_windows(const sb_genome* g, const int32_t* chrom, const
     const Perm p = make_perm(perm);
     cudaStream_t s = (cudaStream_t)stream;
     if (out_dtype == SB_F32)
-        window_kernel<1><<<n, 256, 0, s>>>(view_of(g), chrom, start, strand_rc, L, p, out, flags_out);
+        window_kernel<1><<<window_grid(n, g->device), 256, 0, s>>>(view_of(g), chrom, start, strand_rc, n, L, p, out,
+                                                                   flags_out);
     else
-        window_kernel<2><<<n, 256, 0, s>>>(view_of(g), chrom, start, strand_rc, L, p, out, flags_out);
+        window_kernel<2><<<window_grid(n, g->device), 256, 0, s>>>(view_of(g), chrom, start, strand_rc, n, L, p, out,
+                                                                   flags_out);
     SB_COUNT_LAUNCH();
     SB_CHECK_LAUNCH();
     return SB_OK;
