@@ -92,7 +92,8 @@ def main():
     import ctypes as C
     lib = _lib.load()
     h = C.c_void_p()
-    _lib.check(lib.sb_intervals_create(_lib.ptr(c_i), _lib.ptr(s_i), _lib.ptr(np.ascontiguousarray(s_i + ln)),
+    e_i = np.ascontiguousarray(s_i + ln)
+    _lib.check(lib.sb_intervals_create(_lib.ptr(c_i), _lib.ptr(s_i), _lib.ptr(e_i),
                                        _lib.ptr(f_i), nrows, F, len(names), 0, C.byref(h)), "sb_intervals_create")
     nq = 65536
     qc = torch.from_numpy(lr.integers(0, len(names), nq).astype(np.int32)).cuda()
