@@ -11,9 +11,12 @@
 //
 //   tile            = 128 pooled positions of one sequence (DeepSEA: 2 tiles per 1000-bp sequence)
 //   accumulators    = 2 stages x pool x 64 columns of TMEM (<= 512)
-//   warps 0-3       : build A for the NEXT tile, then drain the current tile's accumulators
-//                     (tcgen05.ld -> max over q -> +bias -> ReLU -> bf16 -> 2 x 16-byte stores per chunk)
-//   warp 4 (1 lane) : issues tcgen05.mma (pool x K/16 per 64-channel pass), commits to mbarriers
+//   warps 0-7       : build A for the NEXT tile (two warps per 32 rows, each half of the q blocks), then
+//                     drain the current tile's accumulators, the two warps of a TMEM lane quadrant taking
+//                     alternate 16-column chunks (tcgen05.ld -> max over q -> +bias -> ReLU -> bf16 ->
+//                     2 x 16-byte stores per chunk); eight warps because one epilogue warp per scheduler
+//                     leaves the issue slots 3/4 idle (ncu, r01)
+//   warp 8 (1 lane) : issues tcgen05.mma (pool x K/16 per 64-channel pass), commits to mbarriers
 #include "sb_common.cuh"
 
 namespace {
@@ -59,7 +62,7 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__global__ void __launch_bounds__(160, 1) conv1_tc_kernel(const Conv1Params p) {
+__global__ void __launch_bounds__(288, 1) conv1_tc_kernel(const Conv1Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                ~static_cast<uintptr_t>(1023));
@@ -81,13 +84,13 @@ __global__ void __launch_bounds__(160, 1) conv1_tc_kernel(const Conv1Params p) {
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
-            sb_mbar_init(&a_full[i], 128);
+            sb_mbar_init(&a_full[i], 256);
             sb_mbar_init(&tfull[i], 1);
-            sb_mbar_init(&tempty[i], 128);
+            sb_mbar_init(&tempty[i], 256);
         }
         sb_fence_mbar_init();
     }
-    if (warp == 4) sb_tmem_alloc(tmem_slot, 512);
+    if (warp == 8) sb_tmem_alloc(tmem_slot, 512);
     // weights + bias -> smem (once per CTA)
     {
         const int n16 = p.n_pass * kPassN * kRowBytes / 16;
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(160, 1) conv1_tc_kernel(const Conv1Params p) {
     const uint32_t tmem_base = *tmem_slot;
     const int ksteps = (p.taps * 4 + 15) / 16;
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = sb_umma_idesc_bf16(kRows, kPassN);
@@ -133,8 +136,9 @@ __global__ void __launch_bounds__(160, 1) conv1_tc_kernel(const Conv1Params p) {
         }
         __syncwarp();
     } else {
-        // ===================== A builder + epilogue (warps 0..3, thread = pooled row) =====================
-        const int i = threadIdx.x;  // 0..127
+        // ===================== A builder + epilogue (warps 0..7, thread = pooled row x half) ==============
+        const int i = threadIdx.x & 127;   // pooled row of the tile
+        const int half = threadIdx.x >> 7; // 0: warps 0-3, 1: warps 4-7
         const int n_codes = kRows * p.pool + 8;
 
         auto build = [&](long long tile, int buf) {
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(160, 1) conv1_tc_kernel(const Conv1Params p) {
             const int sc = (p.sub_pos && p.sub_code) ? p.sub_code[row] : 4;
             const int p0 = tin * kRows * p.pool;
             uint8_t* cs = codes_s;
-            for (int k = i; k < n_codes; k += 128) {
+            for (int k = threadIdx.x; k < n_codes; k += 256) {
                 const int pos = p0 + k;
                 int c = 4;
                 if (pos < p.L) {
@@ -157,7 +161,7 @@ __global__ void __launch_bounds__(160, 1) conv1_tc_kernel(const Conv1Params p) {
                 }
                 cs[k] = (uint8_t)c;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             // this thread's pool + 7 codes
             uint64_t pat[kMaxPool + 7];
 #pragma unroll
@@ -168,7 +172,9 @@ __global__ void __launch_bounds__(160, 1) conv1_tc_kernel(const Conv1Params p) {
             uint8_t* a_row = a_buf + (size_t)buf * kMaxPool * kATileBytes + (i >> 3) * 512 + (i & 7) * 16;
 #pragma unroll
             for (int q = 0; q < kMaxPool; ++q) {
-                if (q < p.pool) {
+                // the two halves split the q blocks between them (pool 4: {0,1} / {2,3}; pool 2: {0} / {1})
+                const bool mine = p.pool == 1 ? half == 0 : (q * 2 / p.pool) == half;
+                if (q < p.pool && mine) {
 #pragma unroll
                     for (int kc = 0; kc < 4; ++kc) {
                         const uint64_t lo = (2 * kc < p.taps) ? pat[q + 2 * kc] : 0ull;
@@ -180,7 +186,7 @@ __global__ void __launch_bounds__(160, 1) conv1_tc_kernel(const Conv1Params p) {
             }
             sb_fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core
             sb_mbar_arrive(&a_full[buf]);
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // codes_s may be overwritten by the next build
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // codes_s may be overwritten by the next build
         };
 
         uint32_t gpass = 0;
@@ -199,9 +205,10 @@ __global__ void __launch_bounds__(160, 1) conv1_tc_kernel(const Conv1Params p) {
                 const uint32_t stage = gpass & 1;
                 sb_mbar_wait(&tfull[stage], (gpass >> 1) & 1);
                 sb_tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + stage * 256;
+                const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + stage * 256;
 #pragma unroll
-                for (int c = 0; c < kPassN / 16; ++c) {
+                for (int cc = 0; cc < kPassN / 32; ++cc) {
+                    const int c = cc * 2 + half;   // this warp's 16-column chunks of the pass
                     uint32_t r0[16];
                     sb_tmem_ld16(taddr + c * 16, r0);
                     float v[16];
@@ -248,7 +255,7 @@ __global__ void __launch_bounds__(160, 1) conv1_tc_kernel(const Conv1Params p) {
 
     sb_tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         sb_tc_fence_after();
         sb_tmem_dealloc(tmem_base, 512);
     }
@@ -303,7 +310,7 @@ int sb_conv1_tc_launch(const uint8_t* codes, const int32_t* src, const int32_t* 
     const long long tiles = n_rows * p.tiles_per_seq;
     const int sms = sb_sm_count(device);
     const int grid = (int)(tiles < sms ? tiles : sms);
-    conv1_tc_kernel<<<grid, 160, smem, stream>>>(p);
+    conv1_tc_kernel<<<grid, 288, smem, stream>>>(p);
     SB_COUNT_LAUNCH();
     SB_CHECK_LAUNCH();
     return SB_OK;
