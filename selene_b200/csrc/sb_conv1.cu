@@ -57,22 +57,67 @@ __device__ __forceinline__ uint64_t tap_pattern(int code) {
     return code < 4 ? (0x3F80ull << (16 * code)) : 0x3E803E803E803E80ull;
 }
 
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   // FMNMX3
+    return r;
+}
+
+// 16 channels of one pooled row: pooled = max over the POOL accumulator blocks, then bias + ReLU as
+// max(m, -bias) + bias (one FMNMX3 absorbs the last pool member and the ReLU), bf16, two 16-byte stores
+template <int POOL>
+__device__ __forceinline__ void finish_chunk(const uint32_t (&r)[4][16], const float* __restrict__ bs, bool relu,
+                                             bool valid, int nb, int out_ld, __nv_bfloat16* __restrict__ orow);
+
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+template <int POOL>
+__device__ __forceinline__ void finish_chunk(const uint32_t (&r)[4][16], const float* __restrict__ bs, bool relu,
+                                             bool valid, int nb, int out_ld, __nv_bfloat16* __restrict__ orow) {
+    float v[16];
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bs + 4 * j4);
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = 4 * j4 + jj;
+            const float floor_ = relu ? -bb[jj] : -INFINITY;
+            float m;
+            if (POOL == 1) {
+                m = fmaxf(__uint_as_float(r[0][j]), floor_);
+            } else if (POOL == 2) {
+                m = max3(__uint_as_float(r[0][j]), __uint_as_float(r[1][j]), floor_);
+            } else {
+                m = max3(__uint_as_float(r[0][j]), __uint_as_float(r[1][j]), __uint_as_float(r[2][j]));
+                m = max3(m, __uint_as_float(r[3][j]), floor_);
+            }
+            v[j] = m + bb[jj];
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+        if (valid && nb + 8 * g + 8 <= out_ld)
+            *reinterpret_cast<uint4*>(orow + nb + 8 * g) =
+                make_uint4(pack2(v[8 * g], v[8 * g + 1]), pack2(v[8 * g + 2], v[8 * g + 3]),
+                           pack2(v[8 * g + 4], v[8 * g + 5]), pack2(v[8 * g + 6], v[8 * g + 7]));
+}
+
+template <int POOL>
 __global__ void __launch_bounds__(288, 1) conv1_tc_kernel(const Conv1Params p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                               ~static_cast<uintptr_t>(1023));
+    // pointer arithmetic on the __shared__ array (not an integer round trip) keeps the shared address
+    // space visible to the compiler: LDS/STS instead of generic LD/ST
+    uint8_t* smem = smem_raw + ((1024u - (sb_smem_u32(smem_raw) & 1023u)) & 1023u);
     // layout: [A buf0: 4 x 8 KB][A buf1: 4 x 8 KB][B: n_pass x 4 KB][bias][codes x2][barriers]
     uint8_t* a_buf = smem;
     uint8_t* b_smem = smem + 2 * kMaxPool * kATileBytes;
     float* bias_s = reinterpret_cast<float*>(b_smem + p.n_pass * kPassN * kRowBytes);
     uint8_t* codes_s = reinterpret_cast<uint8_t*>(bias_s + p.n_pass * kPassN);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(
-        (reinterpret_cast<uintptr_t>(codes_s + kMaxCodes) + 15) & ~static_cast<uintptr_t>(15));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(codes_s + kMaxCodes);   // kMaxCodes and everything before: x16
     uint64_t* a_full = bars;        // [2]
     uint64_t* tfull = bars + 2;     // [2]
     uint64_t* tempty = bars + 4;    // [2]
@@ -206,47 +251,20 @@ __global__ void __launch_bounds__(288, 1) conv1_tc_kernel(const Conv1Params p) {
                 sb_mbar_wait(&tfull[stage], (gpass >> 1) & 1);
                 sb_tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + stage * 256;
+                // this warp's two 16-column chunks of the pass; the second chunk's TMEM loads are in
+                // flight while the first is finished
+                const int c0 = half, c1 = half + 2;
+                uint32_t ra[4][16], rb[4][16];
 #pragma unroll
-                for (int cc = 0; cc < kPassN / 32; ++cc) {
-                    const int c = cc * 2 + half;   // this warp's 16-column chunks of the pass
-                    uint32_t r0[16];
-                    sb_tmem_ld16(taddr + c * 16, r0);
-                    float v[16];
-                    if (p.pool == 1) {
-                        sb_tmem_wait_ld();
+                for (int q = 0; q < POOL; ++q) sb_tmem_ld16(taddr + q * kPassN + c0 * 16, ra[q]);
+                sb_tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]);
-                    } else if (p.pool == 2) {
-                        uint32_t r1[16];
-                        sb_tmem_ld16(taddr + kPassN + c * 16, r1);
-                        sb_tmem_wait_ld();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(r0[j]), __uint_as_float(r1[j]));
-                    } else {
-                        uint32_t r1[16], r2[16], r3[16];
-                        sb_tmem_ld16(taddr + kPassN + c * 16, r1);
-                        sb_tmem_ld16(taddr + 2 * kPassN + c * 16, r2);
-                        sb_tmem_ld16(taddr + 3 * kPassN + c * 16, r3);
-                        sb_tmem_wait_ld();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            v[j] = fmaxf(fmaxf(__uint_as_float(r0[j]), __uint_as_float(r1[j])),
-                                         fmaxf(__uint_as_float(r2[j]), __uint_as_float(r3[j])));
-                    }
-                    const int nb = pass * kPassN + c * 16;
-                    const float* bs = bias_s + nb;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        v[j] += bs[j];
-                        if (p.relu) v[j] = fmaxf(v[j], 0.f);
-                    }
-#pragma unroll
-                    for (int g = 0; g < 2; ++g)
-                        if (valid && nb + 8 * g + 8 <= p.out_ld)
-                            *reinterpret_cast<uint4*>(orow + nb + 8 * g) =
-                                make_uint4(pack2(v[8 * g], v[8 * g + 1]), pack2(v[8 * g + 2], v[8 * g + 3]),
-                                           pack2(v[8 * g + 4], v[8 * g + 5]), pack2(v[8 * g + 6], v[8 * g + 7]));
-                }
+                for (int q = 0; q < POOL; ++q) sb_tmem_ld16(taddr + q * kPassN + c1 * 16, rb[q]);
+                finish_chunk<POOL>(ra, bias_s + pass * kPassN + c0 * 16, p.relu != 0, valid, pass * kPassN + c0 * 16,
+                                   p.out_ld, orow);
+                sb_tmem_wait_ld();
+                finish_chunk<POOL>(rb, bias_s + pass * kPassN + c1 * 16, p.relu != 0, valid, pass * kPassN + c1 * 16,
+                                   p.out_ld, orow);
                 sb_tc_fence_before();
                 sb_mbar_arrive(&tempty[stage]);
             }
@@ -304,13 +322,17 @@ int sb_conv1_tc_launch(const uint8_t* codes, const int32_t* src, const int32_t* 
     SB_REQUIRE(smem <= 220 * 1024, "sb_conv1_tc_launch: %zu bytes of shared memory needed", smem);
     static size_t attr = 0;
     if (smem > attr) {
-        SB_CHECK_CUDA(cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CHECK_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CHECK_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CHECK_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
     const long long tiles = n_rows * p.tiles_per_seq;
     const int sms = sb_sm_count(device);
     const int grid = (int)(tiles < sms ? tiles : sms);
-    conv1_tc_kernel<<<grid, 288, smem, stream>>>(p);
+    if (pool == 4) conv1_tc_kernel<4><<<grid, 288, smem, stream>>>(p);
+    else if (pool == 2) conv1_tc_kernel<2><<<grid, 288, smem, stream>>>(p);
+    else conv1_tc_kernel<1><<<grid, 288, smem, stream>>>(p);
     SB_COUNT_LAUNCH();
     SB_CHECK_LAUNCH();
     return SB_OK;
