@@ -28,6 +28,7 @@ constexpr int kRowBytes = kKPad * 2;                 // 64
 constexpr int kATileBytes = kRows * kRowBytes;       // 8192 per q
 constexpr int kMaxPool = 4;
 constexpr int kMaxCodes = kRows * kMaxPool + 16;     // codes staged per tile
+constexpr int kStagePitch = kPassN * 2 + 16;         // bytes per staged output row (+16: conflict-free)
 
 struct Conv1Params {
     const uint8_t* codes;
@@ -65,10 +66,6 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 
 // 16 channels of one pooled row: pooled = max over the POOL accumulator blocks, then bias + ReLU as
 // max(m, -bias) + bias (one FMNMX3 absorbs the last pool member and the ReLU), bf16, two 16-byte stores
-template <int POOL>
-__device__ __forceinline__ void finish_chunk(const uint32_t (&r)[4][16], const float* __restrict__ bs, bool relu,
-                                             bool valid, int nb, int out_ld, __nv_bfloat16* __restrict__ orow);
-
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -76,7 +73,7 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 
 template <int POOL>
 __device__ __forceinline__ void finish_chunk(const uint32_t (&r)[4][16], const float* __restrict__ bs, bool relu,
-                                             bool valid, int nb, int out_ld, __nv_bfloat16* __restrict__ orow) {
+                                             uint8_t* __restrict__ stage_row) {
     float v[16];
 #pragma unroll
     for (int j4 = 0; j4 < 4; ++j4) {
@@ -100,10 +97,9 @@ __device__ __forceinline__ void finish_chunk(const uint32_t (&r)[4][16], const f
     }
 #pragma unroll
     for (int g = 0; g < 2; ++g)
-        if (valid && nb + 8 * g + 8 <= out_ld)
-            *reinterpret_cast<uint4*>(orow + nb + 8 * g) =
-                make_uint4(pack2(v[8 * g], v[8 * g + 1]), pack2(v[8 * g + 2], v[8 * g + 3]),
-                           pack2(v[8 * g + 4], v[8 * g + 5]), pack2(v[8 * g + 6], v[8 * g + 7]));
+        *reinterpret_cast<uint4*>(stage_row + 16 * g) =
+            make_uint4(pack2(v[8 * g], v[8 * g + 1]), pack2(v[8 * g + 2], v[8 * g + 3]),
+                       pack2(v[8 * g + 4], v[8 * g + 5]), pack2(v[8 * g + 6], v[8 * g + 7]));
 }
 
 template <int POOL>
@@ -117,7 +113,8 @@ __global__ void __launch_bounds__(288, 1) conv1_tc_kernel(const Conv1Params p) {
     uint8_t* b_smem = smem + 2 * kMaxPool * kATileBytes;
     float* bias_s = reinterpret_cast<float*>(b_smem + p.n_pass * kPassN * kRowBytes);
     uint8_t* codes_s = reinterpret_cast<uint8_t*>(bias_s + p.n_pass * kPassN);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(codes_s + kMaxCodes);   // kMaxCodes and everything before: x16
+    uint8_t* stage_s = codes_s + kMaxCodes;                              // [2][128 rows][kStagePitch]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_s + 2 * kRows * kStagePitch);
     uint64_t* a_full = bars;        // [2]
     uint64_t* tfull = bars + 2;     // [2]
     uint64_t* tempty = bars + 4;    // [2]
@@ -243,9 +240,6 @@ __global__ void __launch_bounds__(288, 1) conv1_tc_kernel(const Conv1Params p) {
             if (next < n_tiles) build(next, (it + 1) & 1);
             const long long seq = tile / p.tiles_per_seq;
             const int tin = (int)(tile - seq * p.tiles_per_seq);
-            const int tp = tin * kRows + i;
-            const bool valid = tp < p.t_pool;
-            __nv_bfloat16* orow = p.out + (seq * p.out_pitch + tp) * (long long)p.out_ld;
             for (int pass = 0; pass < p.n_pass; ++pass, ++gpass) {
                 const uint32_t stage = gpass & 1;
                 sb_mbar_wait(&tfull[stage], (gpass >> 1) & 1);
@@ -260,13 +254,29 @@ __global__ void __launch_bounds__(288, 1) conv1_tc_kernel(const Conv1Params p) {
                 sb_tmem_wait_ld();
 #pragma unroll
                 for (int q = 0; q < POOL; ++q) sb_tmem_ld16(taddr + q * kPassN + c1 * 16, rb[q]);
-                finish_chunk<POOL>(ra, bias_s + pass * kPassN + c0 * 16, p.relu != 0, valid, pass * kPassN + c0 * 16,
-                                   p.out_ld, orow);
+                uint8_t* st = stage_s + (gpass & 1) * (kRows * kStagePitch);
+                finish_chunk<POOL>(ra, bias_s + pass * kPassN + c0 * 16, p.relu != 0, st + i * kStagePitch + c0 * 32);
                 sb_tmem_wait_ld();
-                finish_chunk<POOL>(rb, bias_s + pass * kPassN + c1 * 16, p.relu != 0, valid, pass * kPassN + c1 * 16,
-                                   p.out_ld, orow);
+                finish_chunk<POOL>(rb, bias_s + pass * kPassN + c1 * 16, p.relu != 0, st + i * kStagePitch + c1 * 32);
                 sb_tc_fence_before();
-                sb_mbar_arrive(&tempty[stage]);
+                sb_mbar_arrive(&tempty[stage]);      // accumulators are in registers/smem: release them early
+                // staged tile (128 rows x 64 channels) -> global with coalesced stores: a warp instruction
+                // writes 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                {
+                    const int nb = pass * kPassN;
+#pragma unroll
+                    for (int k = 0; k < (kRows * 8) / 256; ++k) {
+                        const int id = threadIdx.x + 256 * k;
+                        const int row = id >> 3, piece = id & 7;
+                        const int tpr = tin * kRows + row;
+                        if (tpr < p.t_pool && nb + piece * 8 + 8 <= p.out_ld) {
+                            const uint4 val = *reinterpret_cast<const uint4*>(st + row * kStagePitch + piece * 16);
+                            *reinterpret_cast<uint4*>(p.out + (seq * p.out_pitch + tpr) * (long long)p.out_ld + nb +
+                                                      piece * 8) = val;
+                        }
+                    }
+                }
             }
         }
     }
@@ -317,7 +327,7 @@ int sb_conv1_tc_launch(const uint8_t* codes, const int32_t* src, const int32_t* 
     p.bias = bias_padded;
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
     size_t smem = 1024 + 2 * kMaxPool * kATileBytes + (size_t)p.n_pass * kPassN * (kRowBytes + 4) + kMaxCodes +
-                  16 + 64 + 16;
+                  2 * kRows * kStagePitch + 64 + 64;
     if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM: each CTA owns all 512 TMEM columns
     SB_REQUIRE(smem <= 220 * 1024, "sb_conv1_tc_launch: %zu bytes of shared memory needed", smem);
     static size_t attr = 0;
