@@ -244,6 +244,30 @@ int sb_net_forward_score(sb_net* net, const uint8_t* codes, const int32_t* src,
                          void* workspace, size_t workspace_bytes, float* abs_diff, float* diff,
                          float* logit, float* pred_ref, float* pred_alt, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* training step (TrainModel.train, train_model.py:483-496): fp32                              */
+/* ------------------------------------------------------------------------------------------ */
+/* Allocates momentum buffers and gradient bookkeeping for the handle (conv / FC stacks). */
+int sb_net_train_init(sb_net* net);
+/* floats in the flat gradient vector (per layer: W as (K x ld) then bias (ld)) */
+size_t sb_net_n_params(const sb_net* net);
+/* dropout probability applied to the output of `layer` (after ReLU / pool) in sb_net_forward_backward */
+int sb_net_set_dropout(sb_net* net, int layer, float p);
+size_t sb_net_train_workspace_bytes(const sb_net* net, int64_t batch);
+/* forward in train mode + BCELoss(mean, logs clamped at -100) + backward.  x: dev (n, L, 4) fp32;
+ * targets: dev (n, F) fp32; dropout_masks: host array of n_layers dev pointers (already scaled by
+ * 1/(1-p)) or NULL entries / NULL to draw masks on the device from dropout_seed; grads: dev,
+ * sb_net_n_params floats (overwritten) — all-reduce them across ranks before sb_net_sgd_step for
+ * data-parallel training; loss: dev, 1 float. */
+int sb_net_forward_backward(sb_net* net, const float* x, const float* targets, int64_t n,
+                            const float* const* dropout_masks, unsigned long long dropout_seed,
+                            void* workspace, size_t workspace_bytes, float* grads, float* loss, void* stream);
+/* torch.optim.SGD(lr, momentum, weight_decay) update of the handle's fp32 weights (models/deepsea.py:66-74) */
+int sb_net_sgd_step(sb_net* net, const float* grads, float lr, float momentum, float weight_decay, void* stream);
+/* fp32 parameters (from_grads NULL) or gradients (from_grads = the flat vector) of one layer, to host,
+ * in torch layout: conv (cout, cin, k), fc (cout, cin); bias (cout).  Synchronises the device. */
+int sb_net_get_layer_params(const sb_net* net, int layer, const float* from_grads, float* w_host, float* b_host);
+
 /* Score two prediction matrices that already exist (handlers called on their own). */
 int sb_score_pairs(const float* ref /* dev (n_ref,F) */, const float* alt /* dev (n,F) */,
                    const int32_t* base_index /* dev (n) or NULL: ref row i (n_ref==n) or 0 */,

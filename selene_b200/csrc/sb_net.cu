@@ -47,11 +47,16 @@ struct NetLayer {
     __nv_bfloat16* whh_b[2];    // dev (4*hidden x hidden_ld) K-major
     float* zero_bias;           // dev, zeros (padded for the tcgen05 tiles)
     int hh_block_n, hh_n_tiles_n, hidden_ld;
+    int fc_prev_c, fc_prev_t;   // first FC after the conv stack: channels / positions it flattens (else 0)
 };
 
 }  // namespace
 
+struct sb_train_state;
+
 struct sb_net {
+    sb_train_state* train;          // sb_train.inl; null until sb_net_train_init
+    bool inference_weights_stale;   // set by sb_net_sgd_step: packed bf16 / lookup copies no longer match wf
     int device;
     int L;
     int n_layers;
@@ -372,6 +377,8 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
     SB_REQUIRE(layers[0].type == SB_LAYER_CONV && layers[0].cin == 4, "sb_net_create: first layer must be a 4-channel conv");
     SB_CHECK_CUDA(cudaSetDevice(device));
     sb_net* net = new sb_net();
+    net->train = nullptr;
+    net->inference_weights_stale = false;
     net->device = device;
     net->L = L;
     net->n_layers = n_layers;
@@ -407,6 +414,7 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
                        S.cin, c, t);
             SB_REQUIRE(N.pool == 1, "sb_net_create: FC layer %d cannot pool", li);
             N.k = 1; N.t_in = 1; N.t_conv = 1; N.t_pool = 1;
+            if (!seen_fc && !prev_lstm) { N.fc_prev_c = c; N.fc_prev_t = t; }
             net->flops_per_seq += 2.0 * (double)S.cout * S.cin;
         } else if (S.type == SB_LAYER_BILSTM) {
             SB_REQUIRE(!seen_fc && li > 0, "sb_net_create: BiLSTM layer %d must follow a conv layer", li);
@@ -959,6 +967,9 @@ static int forward_impl(sb_net* net, const RowSource& in, int64_t n, int precisi
                         float* pred, int pair_mode, const float* base_pred, const int32_t* base_index, bool scoring,
                         float* abs_diff, float* diff, float* logit, float* pred_ref, float* pred_alt, void* stream) {
     const bool generic = in.codes == nullptr;
+    SB_REQUIRE(!(net && net->inference_weights_stale),
+               "the weights were updated by sb_net_sgd_step: export them with sb_net_get_layer_params and create an "
+               "inference handle from them");
     int rc = check_common(net, n, precision, generic, ws, ws_bytes);
     if (rc) return rc;
     if (n == 0) return SB_OK;
@@ -1042,3 +1053,5 @@ extern "C" int sb_score_pairs(const float* ref, const float* alt, const int32_t*
     SB_CHECK_LAUNCH();
     return SB_OK;
 }
+
+#include "sb_train.inl"

@@ -1,0 +1,103 @@
+"""GPU parity of the training step (train_model.py:483-496; SGD of models/deepsea.py:66-74) against
+torch CPU autograd on the same DeepSEA weights, inputs, targets and dropout masks."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, ".."))
+sys.path.insert(0, HERE)
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch_reference(model, x_bl4, y, masks, lr, momentum, wd, steps):
+    """The reference step with Dropout replaced by multiplication with the supplied masks."""
+    import torch
+    import torch.nn.functional as F
+    conv = [model.conv_net[0], model.conv_net[4], model.conv_net[8]]
+    fc = [model.classifier[0], model.classifier[2]]
+    opt = torch.optim.SGD(model.parameters(), lr=lr, momentum=momentum, weight_decay=wd)
+    losses, grads = [], None
+    for _ in range(steps):
+        h = torch.tensor(x_bl4).transpose(1, 2)
+        for i, (c, pool) in enumerate(zip(conv, (4, 4, 1))):
+            h = F.relu(c(h))
+            if pool > 1:
+                h = F.max_pool1d(h, pool, pool)
+            if masks and i in masks:
+                h = h * torch.tensor(masks[i]).transpose(1, 2)      # mask given channel-last (n, t, c)
+        h = h.reshape(h.size(0), -1)
+        h = F.relu(fc[0](h))
+        p = torch.sigmoid(fc[1](h))
+        loss = torch.nn.BCELoss()(p, torch.tensor(y))
+        opt.zero_grad()
+        loss.backward()
+        if grads is None:
+            grads = [m.weight.grad.detach().numpy().copy() for m in conv + fc] + \
+                    [m.bias.grad.detach().numpy().copy() for m in conv + fc]
+        opt.step()
+        losses.append(float(loss))
+    return losses, grads
+
+
+@pytest.mark.parametrize("with_masks", [False, True])
+def test_train_step_matches_torch(with_masks):
+    import torch
+    import sb_models as M
+    from selene_b200.train_model import B200Trainer
+    torch.manual_seed(3)
+    model = M.DeepSEA(1000, 919)
+    rng = np.random.default_rng(5)
+    n = 4
+    codes = rng.integers(0, 4, (n, 1000))
+    x = np.zeros((n, 1000, 4), np.float32)
+    for b in range(4):
+        x[codes == b, b] = 1
+    y = (rng.random((n, 919)) < 0.1).astype(np.float32)
+    masks = None
+    if with_masks:
+        shapes = {0: (n, 248, 320, 0.2), 1: (n, 60, 480, 0.2), 2: (n, 53, 960, 0.5)}
+        masks = {k: ((rng.random(s[:3]) >= s[3]) / (1 - s[3])).astype(np.float32) for k, s in shapes.items()}
+    lr, mom, wd, steps = 0.05, 0.9, 1e-6, 3
+    tr = B200Trainer(model, 1000, lr=lr, momentum=mom, weight_decay=wd)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    md = {k: torch.from_numpy(v).cuda() for k, v in masks.items()} if masks else None
+    ref_losses, ref_grads = _torch_reference(model, x, y, masks, lr, mom, wd, steps)
+    got_losses = []
+    for s in range(steps):
+        tr.forward_backward(xd, yd, md)
+        if s == 0:
+            for li in range(5):
+                gw, gb = tr.layer_params(li, grads=True)
+                rw, rb = ref_grads[li], ref_grads[5 + li]
+                scale = max(np.abs(rw).max(), 1e-12)
+                assert np.abs(gw - rw).max() <= 2e-4 * scale + 1e-9, ("weight grad", li, np.abs(gw - rw).max(), scale)
+                assert np.abs(gb - rb).max() <= 2e-4 * max(np.abs(rb).max(), 1e-12) + 1e-9, ("bias grad", li)
+        tr.sgd_step()
+        got_losses.append(float(tr.loss.item()))
+    assert np.allclose(got_losses, ref_losses, rtol=2e-5, atol=1e-6), (got_losses, ref_losses)
+    mods = [model.conv_net[0], model.conv_net[4], model.conv_net[8], model.classifier[0], model.classifier[2]]
+    for li, m in enumerate(mods):
+        w, b = tr.layer_params(li)
+        rw = m.weight.detach().numpy()
+        assert np.abs(w - rw).max() <= 1e-5 * max(1.0, np.abs(rw).max()), ("weights after SGD", li)
+        assert np.abs(b - m.bias.detach().numpy()).max() <= 1e-5
+
+
+def test_device_dropout_statistics():
+    import torch
+    import sb_models as M
+    from selene_b200.train_model import B200Trainer
+    torch.manual_seed(0)
+    model = M.DeepSEA(1000, 919)
+    assert B200Trainer.dropout_of_module(model) == {0: 0.2, 1: 0.2, 2: 0.5}
+    tr = B200Trainer(model, 1000, dropout=B200Trainer.dropout_of_module(model))
+    x = torch.zeros((2, 1000, 4), device="cuda")
+    x[:, :, 0] = 1
+    y = torch.zeros((2, 919), device="cuda")
+    l1 = tr.step(x, y)
+    l2 = tr.step(x, y)
+    assert np.isfinite(l1) and np.isfinite(l2) and l2 < l1 + 1e-3
