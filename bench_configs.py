@@ -34,7 +34,10 @@ def timed(fn, warmup=3, iters=10):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default="", help="comma list of sections: encode,labels,ism,danq,sweep,sampler,train")
     args = ap.parse_args()
+    only = set(x for x in args.only.split(",") if x)
+    want = lambda name: not only or name in only
     import torch
     import bench as B
     import sb_helpers as H
@@ -62,11 +65,11 @@ def main():
     rng = np.random.default_rng(1)
 
     # ---------------------------------------------------------------- kernel (a): encode windows
-    n = 65536
+    n = 65536 if want('encode') else 0
     chrom = torch.from_numpy(rng.integers(0, len(names), n).astype(np.int32)).cuda()
     start = torch.from_numpy(rng.integers(0, per - 1000, n).astype(np.int64)).cuda()
     rc = torch.from_numpy(rng.integers(0, 2, n).astype(np.uint8)).cuda()
-    for dt, bpw in (("float32", 16375.0), ("bfloat16", 8375.0)):
+    for dt, bpw in ((("float32", 16375.0), ("bfloat16", 8375.0)) if want('encode') else ()):
         t = timed(lambda: G.encode_windows(chrom, start, 1000, strands=rc, dtype=dt))
         gbs = n * bpw / t / 1e9
         emit(kernel="sb_encode_windows", dtype=dt, windows=n, L=1000, ms=t * 1e3, algorithmic_bytes_per_window=bpw,
@@ -77,9 +80,10 @@ def main():
     pos, alt, codes = ism_mutations_device(seq)
     reps = 8
     pos_r, alt_r = pos.repeat(reps), alt.repeat(reps)
-    t = timed(lambda: expand_mutants_device(codes, pos_r, alt_r))
-    gbs = pos_r.numel() * 16000.0 / t / 1e9
-    emit(kernel="sb_ism_expand", mutants=int(pos_r.numel()), ms=t * 1e3, achieved_gbs=gbs, peak_gbs=hbm, frac=gbs / hbm)
+    if want('encode'):
+        t = timed(lambda: expand_mutants_device(codes, pos_r, alt_r))
+        gbs = pos_r.numel() * 16000.0 / t / 1e9
+        emit(kernel="sb_ism_expand", mutants=int(pos_r.numel()), ms=t * 1e3, achieved_gbs=gbs, peak_gbs=hbm, frac=gbs / hbm)
 
     # ---------------------------------------------------------------- kernel (b): labels
     F = 919
@@ -101,8 +105,8 @@ def main():
     qs = torch.from_numpy(qs_np).cuda()
     qe = torch.from_numpy(qs_np + 200).cuda()
     thr = torch.full((F,), 99, dtype=torch.int32, device="cuda")
-    for dt, code, tdt, sz in (("uint8", _lib.SB_U8, torch.uint8, 1), ("float32", _lib.SB_F32, torch.float32, 4),
-                              ("int64", _lib.SB_I64, torch.int64, 8)):
+    for dt, code, tdt, sz in ((("uint8", _lib.SB_U8, torch.uint8, 1), ("float32", _lib.SB_F32, torch.float32, 4),
+                               ("int64", _lib.SB_I64, torch.int64, 8)) if want('labels') else ()):
         o = torch.empty((nq, F), dtype=tdt, device="cuda")
         t = timed(lambda: _lib.check(lib.sb_label_bins(h, _lib.ptr(qc), _lib.ptr(qs), _lib.ptr(qe), nq, _lib.ptr(thr),
                                                        code, _lib.ptr(o), _lib.stream_ptr()), "sb_label_bins"))
@@ -118,7 +122,7 @@ def main():
     torch.manual_seed(0)
     feats = ["f%d" % i for i in range(919)]
     az = AnalyzeSequences(M.DeepSEA(1000, 919), sequence_length=1000, features=feats, reference_sequence=Genome)
-    for prec in ("bf16", "fp32"):
+    for prec in (("bf16", "fp32") if want('ism') else ()):
         az.precision = prec
         az.ism_scores(seq, ("abs_diffs", "logits"))
         torch.cuda.synchronize()
@@ -134,19 +138,24 @@ def main():
     torch.manual_seed(0)
     azd = AnalyzeSequences(M.DanQ(1000, 919), sequence_length=1000, features=feats, reference_sequence=Genome)
     n_seq = 2 if args.quick else 6
-    azd.ism_scores(seq, ("abs_diffs",), to_host=False)
+    if not want('danq'):
+        n_seq = 0
+    else:
+        azd.ism_scores(seq, ("abs_diffs",), to_host=False)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for i in range(n_seq):
         azd.ism_scores(seq, ("abs_diffs", "logits"), to_host=False)
     torch.cuda.synchronize()
-    dt_ = (time.perf_counter() - t0) / n_seq
-    emit(config="4: DanQ ISM (batch-axis recurrence, groups of 64), per 1000-bp sequence of 3000 mutants", precision="bf16",
+    dt_ = (time.perf_counter() - t0) / max(n_seq, 1)
+    if want('danq'):
+      emit(config="4: DanQ ISM (batch-axis recurrence, groups of 64), per 1000-bp sequence of 3000 mutants", precision="bf16",
          seconds_per_sequence=dt_, mutants_per_s=3000 / dt_, flops_per_seq=azd.net.flops_per_seq,
          tflops=3000 / dt_ * azd.net.flops_per_seq / 1e12)
 
     # ---------------------------------------------------------------- config 5: Seqweaver / HeartENN sweep
-    for name, model in (("Seqweaver(217)", M.Seqweaver(217)), ("HeartENN(1000, 90)", M.HeartENN(1000, 90))):
+    for name, model in ((("Seqweaver(217)", M.Seqweaver(217)), ("HeartENN(1000, 90)", M.HeartENN(1000, 90)))
+                        if want('sweep') else ()):
         torch.manual_seed(0)
         model.eval()
         net = B200Net(layers_from_module(model), 1000)
@@ -173,6 +182,35 @@ def main():
     smp = RandomPositionsSampler(G, bed, feats, seed=436, validation_holdout=['chr6', 'chr7'],
                                  test_holdout=['chr8', 'chr9'], sequence_length=1000, center_bin_to_predict=200,
                                  feature_thresholds=0.5)
+    if want('train'):
+        # ------------------------------------------------------------ config 3: training step, batch 64
+        from selene_b200.train_model import B200Trainer
+        torch.manual_seed(0)
+        mdl = M.DeepSEA(1000, 919)
+        tr = B200Trainer(mdl, 1000, lr=0.01, momentum=0.9, weight_decay=1e-6, dropout=B200Trainer.dropout_of_module(mdl))
+        xb, yb = smp.sample_device(64, seq_dtype="float32", label_dtype="float32")
+        for _ in range(2):
+            tr.step(xb, yb)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ns = 5
+        for _ in range(ns):
+            tr.forward_backward(xb, yb)
+            tr.sgd_step()
+        torch.cuda.synchronize()
+        dt_ = (time.perf_counter() - t0) / ns
+        emit(config="3: DeepSEA training step (fwd train-mode + BCE + bwd + SGD), batch 64, fp32 CUDA-core path",
+             seconds_per_step=dt_, samples_per_s=64 / dt_, tflops=64 * 3 * 1.0986e9 / dt_ / 1e12)
+        t0 = time.perf_counter()
+        for _ in range(ns):
+            xb, yb = smp.sample_device(64, seq_dtype="float32", label_dtype="float32")
+            tr.step(xb, yb)
+        torch.cuda.synchronize()
+        dt_ = (time.perf_counter() - t0) / ns
+        emit(config="3: sample + training step end to end (RandomPositionsSampler -> step), batch 64",
+             seconds_per_step=dt_, samples_per_s=64 / dt_)
+    if not want('sampler'):
+        return 0
     smp.sample_device(64)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
