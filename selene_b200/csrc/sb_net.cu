@@ -808,7 +808,8 @@ int run_lstm(sb_net* net, const NetLayer& N, const void* act_in, void* act_out, 
 
 // Runs rows [r0, r0+m) through the network; leaves fp32 logits (row stride ldl) in ws logits buffer.
 int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int precision, uint8_t* ws,
-              const WsPlan& plan, float** logits_out, int* ldl_out, cudaStream_t stream) {
+              const WsPlan& plan, float** logits_out, int* ldl_out, cudaStream_t stream,
+              const SbScoreEpilogue* fused = nullptr) {
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
     void* act[2] = {base, base + plan.act};
     float* full = reinterpret_cast<float*>(base + 2 * plan.act);
@@ -896,7 +897,7 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
             T.n_rows_w = N.cout;
             T.t_in = N.pitch_in; T.t_conv = N.t_conv; T.pool = N.pool; T.relu = N.relu;
             T.out_pitch = N.pitch_out;
-            T.out_f32 = last ? 1 : 0;
+            T.out_f32 = last ? (fused ? 2 : 1) : 0;
             T.out = last ? (void*)logits : act[cur ^ 1];
             T.out_ld = last ? ldl : N.out_ld_b;
             bool per_tap = net->force_per_tap && N.type == SB_LAYER_CONV;
@@ -907,7 +908,7 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
                 } else {
                     T.per_tap = 0; T.taps = N.k; T.w = N.wb; T.w_ld = N.w_ld; T.k_full = N.k_full;
                 }
-                rc = sb_tc_launch(T, dev, stream);
+                rc = sb_tc_launch(T, dev, stream, last ? fused : nullptr);
                 if (rc == SB_OK || per_tap || N.type != SB_LAYER_CONV) break;
                 per_tap = true;            // overlapping-stride tensor map refused: fall back to per-tap boxes
                 net->force_per_tap = true;
@@ -986,6 +987,24 @@ static int forward_impl(sb_net* net, const RowSource& in, int64_t n, int precisi
         const long long m = (n - r0) < chunk ? (n - r0) : chunk;
         float* lg = nullptr;
         int ldl = 0;
+        if (precision == SB_PREC_BF16) {
+            // kernel (d): sigmoid + scores are the epilogue of the last layer's tcgen05 kernel
+            SbScoreEpilogue E;
+            memset(&E, 0, sizeof(E));
+            E.F = F;
+            E.row0 = r0;
+            if (!scoring) { E.mode = 0; E.pred = pred; }
+            else {
+                E.mode = pair_mode == SB_PAIR_INTERLEAVED ? 1 : 2;
+                E.base_pred = base_pred; E.base_index = base_index;
+                E.abs_diff = abs_diff; E.diff = diff; E.logit = logit;
+                E.pred_ref = pair_mode == SB_PAIR_INTERLEAVED ? pred_ref : nullptr;
+                E.pred_alt = pred_alt;
+            }
+            rc = run_chunk(net, in, r0, m, precision, reinterpret_cast<uint8_t*>(ws), plan, &lg, &ldl, s, &E);
+            if (rc) return rc;
+            continue;
+        }
         rc = run_chunk(net, in, r0, m, precision, reinterpret_cast<uint8_t*>(ws), plan, &lg, &ldl, s);
         if (rc) return rc;
         if (!scoring) {

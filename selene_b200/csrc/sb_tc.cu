@@ -45,7 +45,27 @@ struct TcParams {
     int chunks_per_tap;  // 0: overlapping-stride A view; >0: per-tap boxes
     const float* bias;
     void* out;
+    SbScoreEpilogue sc;
 };
+
+__device__ __forceinline__ float tc_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+// logit_score_handler.py:118-124: clamp, then scipy.special.logit in float32
+__device__ __forceinline__ float tc_clamp(float p) { return p == 0.f ? 1e-24f : (p >= 1.f ? 0.999999f : p); }
+__device__ __forceinline__ float tc_logit(float p) { return logf(p / (1.f - p)); }
+
+// one (ref, alt) probability pair -> the requested score arrays at flat index `idx`
+__device__ __forceinline__ void tc_store_scores(const SbScoreEpilogue& sc, long long idx, float ref, float alt,
+                                                bool write_ref) {
+    if (sc.abs_diff) sc.abs_diff[idx] = fabsf(ref - alt);   // np.abs(baseline - batch)
+    if (sc.diff) sc.diff[idx] = alt - ref;                  // batch - baseline
+    if (sc.logit) {
+        ref = tc_clamp(ref);
+        alt = tc_clamp(alt);
+        sc.logit[idx] = tc_logit(alt) - tc_logit(ref);
+    }
+    if (write_ref && sc.pred_ref) sc.pred_ref[idx] = ref;   // clamped when logits were requested, as the
+    if (sc.pred_alt) sc.pred_alt[idx] = alt;                // reference's in-place clamp makes later handlers see
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -173,7 +193,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             const int n_chunks = p.block_n / 16;
             for (int c = 0; c < n_chunks; ++c) {
                 const int nb = n0 + c * 16;
-                if (nb >= p.out_ld) break;  // uniform
+                if (nb >= (p.out_f32 == 2 ? p.sc.F : p.out_ld)) break;  // uniform
                 uint32_t rr[16];
                 sb_tmem_ld16(taddr + c * 16, rr);
                 sb_tmem_wait_ld();
@@ -194,7 +214,47 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
-                if (p.out_f32) {
+                if (p.out_f32 == 2) {
+                    // ---- fused sigmoid + score epilogue (kernel (d)) ----
+                    const SbScoreEpilogue& sc = p.sc;
+                    const long long grow = sc.row0 + r;   // global row of this lane
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = tc_sigmoid(v[j]);
+                    if (sc.mode == 0) {
+                        if (valid)
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (nb + j < sc.F) sc.pred[grow * sc.F + nb + j] = v[j];
+                    } else if (sc.mode == 1) {
+                        // rows 2v / 2v+1 are adjacent lanes: exchange, then the even lane scores columns
+                        // 0-7 of the chunk and the odd lane columns 8-15
+                        const bool odd = lane & 1;
+                        float mine[8], other[8];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float o = __shfl_xor_sync(0xffffffffu, v[j], 1);
+                            if (j < 8) { if (!odd) { mine[j] = v[j]; other[j] = o; } }
+                            else { if (odd) { mine[j - 8] = v[j]; other[j - 8] = o; } }
+                        }
+                        if (valid) {
+                            const long long pair = grow >> 1;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int col = nb + (odd ? 8 : 0) + j;
+                                if (col < sc.F)
+                                    tc_store_scores(sc, pair * sc.F + col, odd ? other[j] : mine[j],
+                                                    odd ? mine[j] : other[j], true);
+                            }
+                        }
+                    } else if (valid) {
+                        const long long bi = sc.base_index ? (long long)sc.base_index[grow] : 0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (nb + j < sc.F)
+                                tc_store_scores(sc, grow * sc.F + nb + j, __ldg(sc.base_pred + bi * sc.F + nb + j), v[j],
+                                                false);
+                    }
+                } else if (p.out_f32) {
                     float* o = reinterpret_cast<float*>(p.out) + out_row * p.out_ld + nb;
 #pragma unroll
                     for (int g = 0; g < 4; ++g)
@@ -294,13 +354,14 @@ int make_tmap(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, 
 
 }  // namespace
 
-int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream) {
+int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbScoreEpilogue* score) {
     SB_REQUIRE(L.block_n >= 16 && L.block_n <= kMaxN && L.block_n % 16 == 0, "sb_tc_launch: bad block_n %d",
                L.block_n);
     SB_REQUIRE(L.a_ld % 8 == 0 && L.w_ld % 8 == 0, "sb_tc_launch: leading dimensions must be multiples of 8");
     SB_REQUIRE(L.pool == 1 || L.pool == 2 || L.pool == 4, "sb_tc_launch: pool %d unsupported", L.pool);
     SB_REQUIRE(L.t_in % L.pool == 0, "sb_tc_launch: t_in %d not a multiple of pool %d", L.t_in, L.pool);
-    SB_REQUIRE(L.out_f32 ? (L.out_ld % 4 == 0) : (L.out_ld % 8 == 0), "sb_tc_launch: bad out_ld %d", L.out_ld);
+    SB_REQUIRE(L.out_f32 == 2 ? score != nullptr : (L.out_f32 ? (L.out_ld % 4 == 0) : (L.out_ld % 8 == 0)),
+               "sb_tc_launch: bad out_ld %d / missing score epilogue", L.out_ld);
     SB_REQUIRE(!(L.out_f32 && L.pool != 1), "sb_tc_launch: fp32 output cannot pool");
     if (L.rows_a <= 0) return SB_OK;
 
@@ -341,6 +402,8 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream) {
     p.chunks_per_tap = chunks_per_tap;
     p.bias = L.bias;
     p.out = L.out;
+    memset(&p.sc, 0, sizeof(p.sc));
+    if (score) p.sc = *score;
 
     static bool attr_set = false;
     if (!attr_set) {

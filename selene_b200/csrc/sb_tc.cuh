@@ -27,10 +27,28 @@ struct SbTcLayer {
     int t_conv;          // valid conv outputs per sequence: t_in - taps + 1
     int pool;            // 1, 2 or 4 (requires t_in % pool == 0)
     int relu;
-    int out_f32;         // 0: bf16 output, 1: fp32 output
+    int out_f32;         // 0: bf16 output, 1: fp32 output, 2: fused sigmoid + score epilogue (`score`)
     void* out;           // dev, (sequences * t_pool) x out_ld
     int out_ld;          // bf16: multiple of 8; fp32: multiple of 4
     int out_pitch;       // rows per sequence in `out` (>= t_pool; the consumer's padded t_in); 0 = t_pool
 };
 
-int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream);
+// Fused epilogue of the LAST layer (out_f32 == 2): sigmoid of the accumulator rows, then either plain
+// predictions or ref/alt scores written straight from registers — logits and predictions never visit HBM
+// unless asked for.  Rows of the launch are rows [row0, row0 + rows_a) of the whole job.
+struct SbScoreEpilogue {
+    int mode;                 // 0: pred[row] = sigmoid; 1: interleaved (ref, alt) row pairs; 2: every row is an
+                              //    alt scored against base_pred[base_index[row]]
+    int F;                    // valid output columns (row stride of every output array)
+    long long row0;           // first global row of this launch
+    const float* base_pred;   // mode 2: (n_base, F)
+    const int32_t* base_index;  // mode 2: per global row, or NULL (row 0)
+    float* pred;              // mode 0: (rows, F)
+    float* abs_diff;          // modes 1/2, may be NULL: (pairs or rows, F)
+    float* diff;
+    float* logit;
+    float* pred_ref;          // mode 1 only
+    float* pred_alt;
+};
+
+int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbScoreEpilogue* score = nullptr);
