@@ -279,6 +279,12 @@ int sb_score_pairs(const float* ref /* dev (n_ref,F) */, const float* alt /* dev
 int sb_tc_gemm_selftest(const void* a_bf16, const void* b_bf16, int M, int N, int K, float* c,
                         void* stream);
 
+/* Self-test hook for the MN-major split-K weight-gradient GEMM: G (N, M) fp32 (zeroed by the caller) +=
+ * dY (rows, M)^T . X-view, where row r of the view is the N elements starting at x + r*x_ld (overlapping
+ * rows when N > x_ld, as for a multi-tap convolution).  M % 8 == 0, x_ld % 8 == 0. */
+int sb_tc_wgrad_selftest(const void* dy_bf16, const void* x_bf16, long long rows, int M, int x_ld, int N,
+                         float* g, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

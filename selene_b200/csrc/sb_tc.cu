@@ -421,6 +421,230 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbSc
 }
 
 // ---------------------------------------------------------------------------------------------
+// weight-gradient GEMM:  G[n][m] += sum_r  dY[r][m] * X[r*x_ld + n]        (m < M = cout, n < N = taps*cin)
+//
+// Both operands are contiguous along their M/N index and strided along the reduction index r (rows), i.e.
+// MN-major for tcgen05: TMA boxes of 64 (M/N) x 64 (rows) land in the 128-byte-swizzled MN-major atom
+// layout (8-row groups 1024 B apart = SBO, 64-element atoms 8192 B apart = LBO) and the instruction
+// descriptor carries a_major = b_major = MN.  The reduction is split over `splits` row ranges; partial
+// accumulators are added to the fp32 gradient with red.global.add (lanes = consecutive m = contiguous
+// floats of G's rows, so every red instruction covers 128 contiguous bytes).
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct WgParams {
+    int M, N;
+    long long rows;
+    int m_tiles, n_tiles, splits, kb_total;
+    float* g;       // (N x ldg) fp32
+    int ldg;
+};
+
+constexpr int kWgBlockN = 256;
+
+__device__ __forceinline__ uint64_t sb_umma_desc_mn_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(8192 >> 4) << 16;   // LBO: next 64-element M/N atom
+    d |= (uint64_t)(1024 >> 4) << 32;   // SBO: next group of 8 reduction rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const WgParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (sb_smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* aux = smem + kStages * kStageBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tfull_bar = empty_bar + kStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_items = p.m_tiles * p.n_tiles * p.splits;
+    const int kb_per = (p.kb_total + p.splits - 1) / p.splits;
+
+    if (warp == 0 && lane == 0) { sb_prefetch_tmap(&tmap_a); sb_prefetch_tmap(&tmap_b); }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kStages; ++i) { sb_mbar_init(&full_bar[i], 1); sb_mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { sb_mbar_init(&tfull_bar[i], 1); sb_mbar_init(&tempty_bar[i], 128); }
+        sb_fence_mbar_init();
+    }
+    if (warp == 2) sb_tmem_alloc(tmem_slot, kTmemCols);
+    sb_tc_fence_before();
+    __syncthreads();
+    sb_tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // item -> (m tile, n tile, split); n fastest so neighbouring CTAs share the dY tile
+    auto decode = [&](int item, int& mt, int& nt, int& kb0, int& kb1) {
+        nt = item % p.n_tiles;
+        const int rest = item / p.n_tiles;
+        mt = rest % p.m_tiles;
+        const int sp = rest / p.m_tiles;
+        kb0 = sp * kb_per;
+        kb1 = kb0 + kb_per < p.kb_total ? kb0 + kb_per : p.kb_total;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                int mt, nt, kb0, kb1;
+                decode(item, mt, nt, kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    sb_mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * kStageBytes;
+                    uint8_t* sb = sa + kABytes;
+                    sb_mbar_expect_tx(&full_bar[stage], kABytes + kBBytesMax);
+#pragma unroll
+                    for (int a = 0; a < 2; ++a)   // M = 128 = 2 atoms of 64
+                        sb_tma_load_2d(sa + a * 8192, &tmap_a, &full_bar[stage], mt * kBlockM + a * 64, kb * kBlockK);
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)   // N = 256 = 4 atoms of 64
+                        sb_tma_load_2d(sb + b * 8192, &tmap_b, &full_bar[stage], nt * kWgBlockN + b * 64, kb * kBlockK);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // bf16 x bf16 -> fp32, A and B MN-major (bits 15 / 16), M = 128, N = 256
+            const uint32_t idesc = sb_umma_idesc_bf16(kBlockM, kWgBlockN) | (1u << 15) | (1u << 16);
+            uint32_t stage = 0, phase = 0;
+            int it = 0;
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+                int mt, nt, kb0, kb1;
+                decode(item, mt, nt, kb0, kb1);
+                const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+                sb_mbar_wait(&tempty_bar[as], aphase ^ 1);
+                sb_tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * kMaxN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    sb_mbar_wait(&full_bar[stage], phase);
+                    sb_tc_fence_after();
+                    const uint32_t sa = sb_smem_u32(smem + stage * kStageBytes);
+                    const uint64_t da = sb_umma_desc_mn_sw128(sa);
+                    const uint64_t db = sb_umma_desc_mn_sw128(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k)   // 16 reduction rows = 2048 bytes
+                        sb_umma_bf16(tmem_d, da + (uint64_t)(128 * k), db + (uint64_t)(128 * k), idesc,
+                                     (kb > kb0 || k > 0) ? 1u : 0u);
+                    sb_umma_commit(&empty_bar[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                sb_umma_commit(&tfull_bar[as]);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int quad = warp & 3;
+        const int row_in_tile = quad * 32 + lane;
+        int it = 0;
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+            int mt, nt, kb0, kb1;
+            decode(item, mt, nt, kb0, kb1);
+            const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+            const int m = mt * kBlockM + row_in_tile;
+            sb_mbar_wait(&tfull_bar[as], aphase);
+            sb_tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * kMaxN;
+            if (kb1 > kb0) {
+                for (int c = 0; c < kWgBlockN / 16; ++c) {
+                    const int nb = nt * kWgBlockN + c * 16;
+                    if (nb >= p.N) break;
+                    uint32_t rr[16];
+                    sb_tmem_ld16(taddr + c * 16, rr);
+                    sb_tmem_wait_ld();
+                    if (m < p.M) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (nb + j < p.N) atomicAdd(p.g + (long long)(nb + j) * p.ldg + m, __uint_as_float(rr[j]));
+                    }
+                }
+            }
+            sb_tc_fence_before();
+            sb_mbar_arrive(&tempty_bar[as]);
+        }
+    }
+    sb_tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { sb_tc_fence_after(); sb_tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+}  // namespace
+
+// G (N x ldg, fp32) += dY^T . Xview ; dy: rows x M bf16 (row stride dy_ld), x: bf16 buffer whose row r is the
+// run of N elements starting at r*x_ld (overlapping when N > x_ld: taps > 1).
+int sb_tc_wgrad_launch(const void* dy, int dy_ld, const void* x, int x_ld, long long x_rows_alloc, long long rows,
+                       int M, int N, float* g, int ldg, int device, cudaStream_t stream) {
+    SB_REQUIRE(dy_ld % 8 == 0 && x_ld % 8 == 0, "sb_tc_wgrad_launch: leading dimensions must be multiples of 8");
+    if (rows <= 0) return SB_OK;
+    const int span = (N + x_ld - 1) / x_ld;                        // rows touched by one X row view
+    long long x_rows = x_rows_alloc - (span - 1);                  // keep every read inside the allocation
+    if (x_rows > rows) x_rows = rows;
+    SB_REQUIRE(x_rows > 0, "sb_tc_wgrad_launch: fewer rows than taps");
+    EncodeTiledFn fn = get_encode_fn();
+    SB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    CUtensorMap tm_a, tm_b;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)M, (cuuint64_t)rows};
+        cuuint64_t strides[1] = {(cuuint64_t)dy_ld * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)kBlockK};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = fn(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(dy), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(dY) failed with CUresult %d", (int)r);
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)x_rows};
+        cuuint64_t strides[1] = {(cuuint64_t)x_ld * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)kBlockK};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = fn(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(X) failed with CUresult %d", (int)r);
+    }
+    WgParams p;
+    p.M = M; p.N = N; p.rows = rows;
+    p.m_tiles = (M + kBlockM - 1) / kBlockM;
+    p.n_tiles = (N + kWgBlockN - 1) / kWgBlockN;
+    p.kb_total = (int)((rows + kBlockK - 1) / kBlockK);
+    const int sms = sb_sm_count(device);
+    int splits = (2 * sms) / (p.m_tiles * p.n_tiles);
+    if (splits < 1) splits = 1;
+    if (splits > p.kb_total) splits = p.kb_total;
+    p.splits = splits;
+    p.g = g; p.ldg = ldg;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        attr_set = true;
+    }
+    const long long items = (long long)p.m_tiles * p.n_tiles * p.splits;
+    const int grid = (int)(items < sms ? items : sms);
+    tc_wgrad_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tm_a, tm_b, p);
+    SB_COUNT_LAUNCH();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+extern "C" int sb_tc_wgrad_selftest(const void* dy_bf16, const void* x_bf16, long long rows, int M, int x_ld, int N,
+                                    float* g, void* stream) {
+    SB_REQUIRE(dy_bf16 && x_bf16 && g, "sb_tc_wgrad_selftest: null argument");
+    int dev = 0;
+    SB_CHECK_CUDA(cudaGetDevice(&dev));
+    return sb_tc_wgrad_launch(dy_bf16, M, x_bf16, x_ld, rows, rows, M, N, g, M, dev, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
 // self-test entry: plain C = A . B^T through the same kernel
 // ---------------------------------------------------------------------------------------------
 __global__ void zero_bias_kernel(float* b, int n) {

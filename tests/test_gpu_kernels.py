@@ -434,3 +434,29 @@ def test_danq_batch_axis_recurrence_vs_torch(torch, precision, tol):
         with torch.no_grad():
             exp_even, exp_odd = model(x[0:6:2]).numpy(), model(x[1:6:2]).numpy()
         assert np.abs(got[0::2] - exp_even).max() <= tol and np.abs(got[1::2] - exp_odd).max() <= tol
+
+
+# ------------------------------------------------------------------------------------------------
+# MN-major split-K wgrad GEMM (training)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,M,x_ld,N", [(64, 128, 256, 256), (200, 64, 64, 64), (1000, 480, 320, 2560),
+                                           (333, 960, 480, 3840), (64, 920, 1024, 1024), (4000, 96, 64, 512)])
+def test_tc_wgrad_selftest(torch, rows, M, x_ld, N):
+    from selene_b200 import _lib
+    lib = _lib.load()
+    gen = torch.Generator(device="cuda").manual_seed(rows + M + N)
+    dy = (torch.randn((rows, M), device="cuda", generator=gen) * 0.5).to(torch.bfloat16)
+    x = (torch.randn((rows, x_ld), device="cuda", generator=gen) * 0.5).to(torch.bfloat16)
+    g = torch.zeros((N, M), device="cuda", dtype=torch.float32)
+    _lib.check(lib.sb_tc_wgrad_selftest(_lib.ptr(dy), _lib.ptr(x), rows, M, x_ld, N, _lib.ptr(g), _lib.stream_ptr()),
+               "sb_tc_wgrad_selftest")
+    torch.cuda.synchronize()
+    # row r of the view = flat x[r*x_ld : r*x_ld + N], zero beyond the buffer / for rows whose view overruns
+    span = (N + x_ld - 1) // x_ld
+    flat = torch.cat([x.float().reshape(-1), torch.zeros(N, device="cuda")])
+    view = torch.stack([flat[r * x_ld: r * x_ld + N] for r in range(rows)])
+    if span > 1:
+        view[rows - (span - 1):] = 0
+    ref = view.t() @ dy.float()
+    err = (g - ref).abs().max().item()
+    assert err <= 3e-3 * max(1.0, ref.abs().max().item()), "max abs err %g" % err
