@@ -268,6 +268,15 @@ int sb_net_sgd_step(sb_net* net, const float* grads, float lr, float momentum, f
  * in torch layout: conv (cout, cin, k), fc (cout, cin); bias (cout).  Synchronises the device. */
 int sb_net_get_layer_params(const sb_net* net, int layer, const float* from_grads, float* w_host, float* b_host);
 
+/* The same step with the layer GEMMs (forward, dgrad, wgrad) on tcgen05: bf16 operands, fp32 accumulation,
+ * fp32 master weights and gradients; the 4-channel first conv stays on CUDA cores.  Same arguments and
+ * gradient layout as the fp32 functions above; use sb_net_sgd_step / sb_net_get_layer_params unchanged. */
+int sb_net_train_init_tc(sb_net* net);
+size_t sb_net_train_workspace_bytes_tc(const sb_net* net, int64_t batch);
+int sb_net_forward_backward_tc(sb_net* net, const float* x, const float* targets, int64_t n,
+                               const float* const* dropout_masks, unsigned long long dropout_seed,
+                               void* workspace, size_t workspace_bytes, float* grads, float* loss, void* stream);
+
 /* Score two prediction matrices that already exist (handlers called on their own). */
 int sb_score_pairs(const float* ref /* dev (n_ref,F) */, const float* alt /* dev (n,F) */,
                    const int32_t* base_index /* dev (n) or NULL: ref row i (n_ref==n) or 0 */,

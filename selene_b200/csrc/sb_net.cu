@@ -53,9 +53,12 @@ struct NetLayer {
 }  // namespace
 
 struct sb_train_state;
+struct sb_train_tc_state;
 
 struct sb_net {
     sb_train_state* train;          // sb_train.inl; null until sb_net_train_init
+    sb_train_tc_state* train_tc;    // sb_train_tc.inl; null until sb_net_train_init_tc
+    float* zero_bias_tc;            // dev zeros used as the bias of gradient GEMMs
     bool inference_weights_stale;   // set by sb_net_sgd_step: packed bf16 / lookup copies no longer match wf
     int device;
     int L;
@@ -378,6 +381,8 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
     SB_CHECK_CUDA(cudaSetDevice(device));
     sb_net* net = new sb_net();
     net->train = nullptr;
+    net->train_tc = nullptr;
+    net->zero_bias_tc = nullptr;
     net->inference_weights_stale = false;
     net->device = device;
     net->L = L;
@@ -1074,3 +1079,4 @@ extern "C" int sb_score_pairs(const float* ref, const float* alt, const int32_t*
 }
 
 #include "sb_train.inl"
+#include "sb_train_tc.inl"

@@ -1,0 +1,524 @@
+// selene_b200 — training step with the GEMMs on tcgen05 (bf16 operands, fp32 accumulation, fp32 master
+// weights and gradients).  Included by sb_net.cu after sb_train.inl.
+//
+// Same mathematics and layouts as sb_train.inl; per layer (index >= 1):
+//   forward  tc_layer_kernel (pool unfused so the pre-pool output is kept for the backward pass)
+//   dgrad    tc_layer_kernel over the shifted overlapping view of dY with the taps-flipped W^T
+//   wgrad    tc_wgrad_kernel (MN-major operands, split-K, red.add into the fp32 gradient)
+// The first conv (4 input channels) stays on CUDA cores: its forward is a 32-deep dot product per output
+// and its weight gradient a 32 x cout table accumulated in registers.
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ in, long long rows, int cols,
+                                                          int ld_in, bf16* __restrict__ out, int ld_out) {
+    const long long total = rows * ld_out;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = (int)(i % ld_out);
+        const long long r = i / ld_out;
+        out[i] = __float2bfloat16_rn(c < cols ? in[r * ld_in + c] : 0.f);
+    }
+}
+
+__global__ void __launch_bounds__(256) bf16_to_f32_kernel(const bf16* __restrict__ in, long long rows, int cols,
+                                                          int ld_in, float* __restrict__ out, int ld_out) {
+    const long long total = rows * cols;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = (int)(i % cols);
+        const long long r = i / cols;
+        out[r * ld_out + c] = __bfloat162float(in[r * ld_in + c]);
+    }
+}
+
+// forward B operand from the fp32 master: wb[o][map(kk)] = W[kk][o], map(kk) = (kk / ch) * ch_ld + kk % ch
+__global__ void __launch_bounds__(256) pack_fwd_kernel(const float* __restrict__ wf, int ldw, long long K, int ch, int ch_ld,
+                                                       int cout, bf16* __restrict__ wb, int w_ld) {
+    const long long total = K * cout;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int o = (int)(i % cout);
+        const long long kk = i / cout;
+        const long long col = (kk / ch) * ch_ld + kk % ch;
+        wb[(long long)o * w_ld + col] = __float2bfloat16_rn(wf[kk * ldw + o]);
+    }
+}
+
+// dgrad B operand: wt[c][tap'*cout_ld + o] = W[(taps-1-tap')*C + c][o]   (taps = 1: plain W^T rows)
+__global__ void __launch_bounds__(256) pack_dgrad_kernel(const float* __restrict__ wf, int ldw, int taps, int C, int cout,
+                                                         int cout_ld, bf16* __restrict__ wt, int wt_ld) {
+    const long long total = (long long)taps * C * cout;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int o = (int)(i % cout);
+        const long long r = i / cout;
+        const int c = (int)(r % C);
+        const int tp = (int)(r / C);
+        wt[(long long)c * wt_ld + (long long)tp * cout_ld + o] =
+            __float2bfloat16_rn(wf[((long long)(taps - 1 - tp) * C + c) * ldw + o]);
+    }
+}
+
+// pooled[s][tp][c] = max_q full[s][tp*pool+q][c]  (bf16 in / out), optional dropout (mask fp32, per element)
+__global__ void __launch_bounds__(256) pool_fwd_bf16_kernel(const bf16* __restrict__ full, int t_full, int pool, int t_pool,
+                                                            int ld, long long n_seq, bf16* __restrict__ out,
+                                                            const float* __restrict__ mask_in, float* __restrict__ mask_out,
+                                                            float p, unsigned long long seed) {
+    const long long total = n_seq * t_pool * ld;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = (int)(i % ld);
+        const long long rt = i / ld;
+        const int tp = (int)(rt % t_pool);
+        const long long s = rt / t_pool;
+        float m = -INFINITY;
+        for (int q = 0; q < pool; ++q)
+            m = fmaxf(m, __bfloat162float(full[(s * t_full + (long long)tp * pool + q) * ld + c]));
+        if (mask_in) m *= mask_in[i];
+        else if (p > 0.f) { const float k = hash_uniform(seed, (unsigned long long)i) >= p ? scale : 0.f; mask_out[i] = k; m *= k; }
+        out[i] = __float2bfloat16_rn(m);
+    }
+}
+
+// dfull[s][t][c] (t < t_in rows per sequence) from gout[s][t/pool][c]: first maximum of the window and > 0, times the
+// dropout mask; rows t >= t_pool*pool are zero.
+__global__ void __launch_bounds__(256) pool_relu_bwd_bf16_kernel(const bf16* __restrict__ full, int t_full, const bf16* __restrict__ gout,
+                                                                 const float* __restrict__ mask, int t_in, int pool, int t_pool,
+                                                                 int ld, long long n_seq, bf16* __restrict__ dfull) {
+    const long long total = n_seq * t_in * ld;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = (int)(i % ld);
+        const long long rt = i / ld;
+        const int t = (int)(rt % t_in);
+        const long long s = rt / t_in;
+        float g = 0.f;
+        const int tp = t / pool;
+        if (tp < t_pool) {
+            const float v = __bfloat162float(full[(s * t_full + t) * ld + c]);
+            if (v > 0.f) {
+                bool first_max = true;
+                for (int q = 0; q < pool; ++q) {
+                    const int tq = tp * pool + q;
+                    const float u = __bfloat162float(full[(s * t_full + tq) * ld + c]);
+                    if (u > v || (u == v && tq < t)) first_max = false;
+                }
+                if (first_max) {
+                    const long long oi = (s * t_pool + tp) * ld + c;
+                    g = __bfloat162float(gout[oi]);
+                    if (mask) g *= mask[oi];
+                }
+            }
+        }
+        dfull[i] = __float2bfloat16_rn(g);
+    }
+}
+
+// FC: dy = gout * mask * (y > 0)  in place (bf16)
+__global__ void __launch_bounds__(256) fc_bwd_bf16_kernel(bf16* __restrict__ g, const bf16* __restrict__ y, const float* __restrict__ mask,
+                                                          int relu, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float v = __bfloat162float(g[i]);
+        if (mask) v *= mask[i];
+        if (relu && !(__bfloat162float(y[i]) > 0.f)) v = 0.f;
+        g[i] = __float2bfloat16_rn(v);
+    }
+}
+
+__global__ void __launch_bounds__(256) dropout_bf16_kernel(bf16* __restrict__ y, long long n, const float* __restrict__ mask_in,
+                                                           float* __restrict__ mask_out, float p, unsigned long long seed) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float scale = 1.f / (1.f - p);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float m;
+        if (mask_in) m = mask_in[i];
+        else { m = hash_uniform(seed, (unsigned long long)i) >= p ? scale : 0.f; mask_out[i] = m; }
+        y[i] = __float2bfloat16_rn(__bfloat162float(y[i]) * m);
+    }
+}
+
+// BCE on fp32 logits -> loss (fp32 atomic) and dz (bf16, padded columns zero)
+__global__ void __launch_bounds__(256) bce_bf16_kernel(const float* __restrict__ z, int ldz, const float* __restrict__ y,
+                                                       long long n, int F, bf16* __restrict__ dz, int lddz,
+                                                       float* __restrict__ loss) {
+    const long long total = n * lddz;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float inv = 1.f / (float)(n * F);
+    float local = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long r = i / lddz;
+        const int f = (int)(i - r * lddz);
+        float g = 0.f;
+        if (f < F) {
+            const float p = sigmoid_f32(z[r * ldz + f]);
+            const float t = y[r * F + f];
+            const float lp = fmaxf(logf(p), -100.f), lq = fmaxf(logf(1.f - p), -100.f);
+            local += -(t * lp + (1.f - t) * lq);
+            g = (p - t) * inv;
+        }
+        dz[i] = __float2bfloat16_rn(g);
+    }
+    local *= inv;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+    if ((threadIdx.x & 31) == 0) atomicAdd(loss, local);
+}
+
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ dy, long long rows, int ld, int n_cols,
+                                                          float* __restrict__ db) {
+    const int o = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int part = threadIdx.x >> 5;
+    __shared__ float red[8][33];
+    float s = 0.f;
+    if (o < n_cols)
+        for (long long r = part; r < rows; r += 8) s += __bfloat162float(dy[r * ld + o]);
+    red[part][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (part == 0 && o < n_cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x & 31];
+        db[o] = t;
+    }
+}
+
+// First-conv weight gradient: dW[(j*4 + c)][o] = sum_r x[r + j][c] * dY[r][o] with the 4*taps (<= 32)
+// accumulators of output channel o in registers; each CTA covers a row range and adds its partial table.
+constexpr int kW1MaxK = 32;
+__global__ void __launch_bounds__(128) conv1_wgrad_kernel(const float* __restrict__ x, long long x_rows, const float* __restrict__ dy,
+                                                          int ld_dy, long long rows, int taps, int cout, int rows_per_block,
+                                                          float* __restrict__ gw, int ldw) {
+    __shared__ float xs[64 + 8][4];
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const int o = blockIdx.y * 128 + threadIdx.x;
+    float acc[kW1MaxK];
+#pragma unroll
+    for (int k = 0; k < kW1MaxK; ++k) acc[k] = 0.f;
+    for (long long rb = r0; rb < r0 + rows_per_block && rb < rows; rb += 64) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < (64 + 8) * 4; i += 128) {
+            const long long rr = rb + i / 4;
+            xs[i / 4][i % 4] = rr < x_rows ? x[rr * 4 + (i % 4)] : 0.f;
+        }
+        __syncthreads();
+        if (o < cout) {
+            for (int q = 0; q < 64; ++q) {
+                const long long r = rb + q;
+                if (r >= rows || r >= r0 + rows_per_block) break;
+                const float g = dy[r * ld_dy + o];
+                if (g != 0.f) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (j < taps) acc[j * 4 + c] = fmaf(xs[q + j][c], g, acc[j * 4 + c]);
+                }
+            }
+        }
+    }
+    if (o < cout)
+        for (int k = 0; k < taps * 4; ++k)
+            if (acc[k] != 0.f) atomicAdd(gw + (long long)k * ldw + o, acc[k]);
+}
+
+struct TcTrainLayer {
+    bf16* wb;      // forward B operand (cout x w_ld)
+    bf16* wt;      // dgrad B operand (cin x wt_ld)
+    int wt_ld;
+    int cin_ld, cout_ld;
+    int dg_block_n, dg_n_tiles_n;   // tiling of the dgrad output columns (= layer inputs)
+};
+
+}  // namespace
+
+struct sb_train_tc_state {
+    std::vector<TcTrainLayer> L;
+};
+
+namespace {
+
+bool tc_trainable(const sb_net* net, const char** why) {
+    if (net->has_lstm) { *why = "BiLSTM layers"; return false; }
+    if (net->layers[0].k > 8) { *why = "first conv longer than 8 taps"; return false; }
+    for (size_t li = 1; li < net->layers.size(); ++li) {
+        const NetLayer& N = net->layers[li];
+        const int ch = N.type == SB_LAYER_CONV ? N.cin : (N.fc_prev_c > 0 ? N.fc_prev_c : N.cin);
+        if (N.type == SB_LAYER_CONV && ch % 8 != 0) { *why = "conv input channels not a multiple of 8"; return false; }
+        if (N.type == SB_LAYER_FC && N.fc_prev_c > 0 && ch % 8 != 0) { *why = "flattened channels not a multiple of 8"; return false; }
+    }
+    return true;
+}
+
+struct TcPlan {
+    std::vector<size_t> full, pooled, mask;   // per layer byte offsets (layer 0: fp32 full / fp32 pooled / mask, + bf16 pooled)
+    size_t x1b, g_a, g_b, g32, logits, total;
+};
+
+TcPlan plan_train_tc(const sb_net* net, long long n) {
+    TcPlan P;
+    size_t off = 0, max_g = 0;
+    for (size_t li = 0; li < net->layers.size(); ++li) {
+        const NetLayer& N = net->layers[li];
+        const bool conv = N.type == SB_LAYER_CONV;
+        const int ld = li == 0 ? N.cout : round_up(N.cout, 8);
+        const size_t es = li == 0 ? 4 : 2;
+        const size_t full_b = (size_t)n * (conv ? (li == 0 ? N.t_in : N.t_conv) : 1) * ld * es;
+        const size_t pooled_e = (size_t)n * N.t_pool * ld;
+        P.full.push_back(off); off += align256(full_b);
+        P.pooled.push_back(off); off += align256(conv ? pooled_e * es : 0);
+        P.mask.push_back(off); off += align256((conv ? pooled_e : (size_t)n * ld) * 4);
+        // gradient buffers: dfull with (taps-1) leading rows over t_in rows, or the layer input gradient
+        const size_t dfull_b = ((size_t)n * N.t_in + N.k) * round_up(N.cout, 8) * 2;
+        const size_t dx_b = (size_t)n * N.t_in * round_up(N.cin, 8) * 2;
+        max_g = std::max(max_g, std::max(dfull_b, dx_b));
+    }
+    P.x1b = off; off += align256((size_t)n * net->layers[0].t_pool * round_up(net->layers[0].cout, 8) * 2);
+    P.g_a = off; off += align256(max_g + 65536);
+    P.g_b = off; off += align256(max_g + 65536);
+    // fp32 scratch for the first conv's backward: dfull over all input rows with (taps-1) leading rows
+    P.g32 = off; off += align256(((size_t)n * net->layers[0].t_in + 8) * net->layers[0].cout * 4 * 2);
+    P.logits = off; off += align256((size_t)n * round_up(net->n_out, 4) * 4);
+    P.total = off + 1024;
+    return P;
+}
+
+int launch_tc_plain(const void* a, long long rows_a, int a_ld, int k_full, const void* w, int n_rows_w, int w_ld,
+                    const float* bias, int block_n, int n_tiles_n, int t_in, int t_conv, int relu, int out_f32, void* out,
+                    int out_ld, int out_pitch, int dev, cudaStream_t s) {
+    SbTcLayer T;
+    memset(&T, 0, sizeof(T));
+    T.a = a; T.rows_a = rows_a; T.a_ld = a_ld; T.k_full = k_full;
+    T.w = w; T.n_rows_w = n_rows_w; T.w_ld = w_ld;
+    T.bias = bias; T.block_n = block_n; T.n_tiles_n = n_tiles_n;
+    T.t_in = t_in; T.t_conv = t_conv; T.pool = 1; T.relu = relu; T.out_f32 = out_f32; T.out = out; T.out_ld = out_ld;
+    T.out_pitch = out_pitch;
+    return sb_tc_launch(T, dev, s);
+}
+
+}  // namespace
+
+extern "C" int sb_net_train_init_tc(sb_net* net) {
+    int rc = sb_net_train_init(net);
+    if (rc) return rc;
+    if (net->train_tc) return SB_OK;
+    const char* why = "";
+    SB_REQUIRE(tc_trainable(net, &why), "sb_net_train_init_tc: unsupported on the tcgen05 training path (%s); use fp32", why);
+    sb_train_tc_state* S = new sb_train_tc_state();
+    S->L.resize(net->layers.size());
+    size_t max_cols = 256;
+    for (size_t li = 1; li < net->layers.size(); ++li) {
+        const NetLayer& N = net->layers[li];
+        TcTrainLayer& T = S->L[li];
+        T.cout_ld = round_up(N.cout, 8);
+        const bool conv = N.type == SB_LAYER_CONV;
+        const long long cin_rows = conv ? N.cin : N.cin;          // rows of the dgrad B operand = layer inputs
+        T.wt_ld = round_up((conv ? N.k : 1) * T.cout_ld, 8);
+        T.wb = N.wb;                                              // repacked in place every step
+        SB_CHECK_CUDA(cudaMalloc(&T.wt, (size_t)cin_rows * T.wt_ld * 2));
+        SB_CHECK_CUDA(cudaMemset(T.wt, 0, (size_t)cin_rows * T.wt_ld * 2));
+        const int nt = (int)((cin_rows + 255) / 256);
+        T.dg_n_tiles_n = nt;
+        T.dg_block_n = round_up((int)((cin_rows + nt - 1) / nt), 16);
+        max_cols = std::max(max_cols, (size_t)nt * T.dg_block_n);
+    }
+    SB_CHECK_CUDA(cudaMalloc(&net->zero_bias_tc, (max_cols + 256) * 4));
+    SB_CHECK_CUDA(cudaMemset(net->zero_bias_tc, 0, (max_cols + 256) * 4));
+    net->train_tc = S;
+    return SB_OK;
+}
+
+extern "C" size_t sb_net_train_workspace_bytes_tc(const sb_net* net, int64_t batch) {
+    if (!net || batch <= 0) return 0;
+    return plan_train_tc(net, batch).total;
+}
+
+extern "C" int sb_net_forward_backward_tc(sb_net* net, const float* x, const float* targets, int64_t n,
+                                          const float* const* dropout_masks, unsigned long long dropout_seed,
+                                          void* workspace, size_t workspace_bytes, float* grads, float* loss, void* stream) {
+    SB_REQUIRE(net && net->train && net->train_tc, "sb_net_forward_backward_tc: call sb_net_train_init_tc first");
+    SB_REQUIRE(x && targets && grads && loss && n > 0, "sb_net_forward_backward_tc: bad arguments");
+    const TcPlan P = plan_train_tc(net, n);
+    SB_REQUIRE(workspace && workspace_bytes >= P.total, "sb_net_forward_backward_tc: workspace too small: need %zu, have %zu",
+               P.total, workspace_bytes);
+    SB_CHECK_CUDA(cudaSetDevice(net->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int dev = net->device;
+    sb_train_state* T = net->train;
+    sb_train_tc_state* S = net->train_tc;
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    const size_t L = net->layers.size();
+    const int F = net->n_out;
+    const int ldl = round_up(F, 4);
+    float* logits = reinterpret_cast<float*>(base + P.logits);
+    auto mask_of = [&](size_t li) { return reinterpret_cast<float*>(base + P.mask[li]); };
+    auto ext_mask = [&](size_t li) -> const float* { return dropout_masks ? dropout_masks[li] : nullptr; };
+    auto seed_of = [&](size_t li) { return dropout_seed * 1315423911ull + li; };
+
+    // ---- repack the bf16 operands from the fp32 master weights (they changed in the last SGD step)
+    for (size_t li = 1; li < L; ++li) {
+        const NetLayer& N = net->layers[li];
+        const bool conv = N.type == SB_LAYER_CONV;
+        const int ch = conv ? N.cin : (N.fc_prev_c > 0 ? N.fc_prev_c : N.cin);
+        const int ch_ld = round_up(ch, 8);
+        pack_fwd_kernel<<<grid_for((long long)N.k_f32 * N.cout, dev), 256, 0, s>>>(N.wf, N.ldw_f32, N.k_f32, ch, ch_ld, N.cout,
+                                                                                 N.wb, N.w_ld);
+        SB_COUNT_LAUNCH();
+        pack_dgrad_kernel<<<grid_for((long long)N.k_f32 * N.cout, dev), 256, 0, s>>>(
+            N.wf, N.ldw_f32, conv ? N.k : 1, conv ? N.cin : N.cin, N.cout, S->L[li].cout_ld, S->L[li].wt, S->L[li].wt_ld);
+        SB_COUNT_LAUNCH();
+        SB_CHECK_LAUNCH();
+    }
+
+    // ------------------------------------------------------------------ forward
+    // layer 0 on CUDA cores (fp32), output converted to bf16
+    const NetLayer& N0 = net->layers[0];
+    float* full0 = reinterpret_cast<float*>(base + P.full[0]);
+    float* pooled0 = reinterpret_cast<float*>(base + P.pooled[0]);
+    bf16* x1b = reinterpret_cast<bf16*>(base + P.x1b);
+    const int ld0b = round_up(N0.cout, 8);
+    {
+        const long long rows = (long long)n * N0.t_in;
+        int rc = launch_gemm_gen(x, rows * 4, 4, 1, N0.wf, N0.ldw_f32, 1, rows, N0.cout, N0.k_f32, N0.biasf, N0.relu, full0,
+                                 N0.cout, s);
+        if (rc) return rc;
+        const long long pe = (long long)n * N0.t_pool * N0.cout;
+        pool_compact_kernel<float><<<grid_for(pe, dev), 256, 0, s>>>(full0, N0.cout, N0.t_in, N0.pool, N0.t_pool, N0.t_pool,
+                                                                     N0.cout, N0.cout, n, pooled0);
+        SB_COUNT_LAUNCH();
+        if (T->dropout_p[0] > 0.f || ext_mask(0)) {
+            dropout_kernel<<<grid_for(pe, dev), 256, 0, s>>>(pooled0, pe, ext_mask(0), mask_of(0), T->dropout_p[0], seed_of(0));
+            SB_COUNT_LAUNCH();
+        }
+        f32_to_bf16_kernel<<<grid_for((long long)n * N0.t_pool * ld0b, dev), 256, 0, s>>>(pooled0, (long long)n * N0.t_pool,
+                                                                                         N0.cout, N0.cout, x1b, ld0b);
+        SB_COUNT_LAUNCH();
+        SB_CHECK_LAUNCH();
+    }
+    std::vector<const bf16*> xin(L, nullptr);   // input activation of each layer (bf16)
+    xin[1] = x1b;
+    for (size_t li = 1; li < L; ++li) {
+        const NetLayer& N = net->layers[li];
+        const bool conv = N.type == SB_LAYER_CONV;
+        const bool last = li + 1 == L;
+        const int ldo = S->L[li].cout_ld;
+        bf16* full = reinterpret_cast<bf16*>(base + P.full[li]);
+        int rc;
+        if (conv) {
+            rc = launch_tc_plain(xin[li], (long long)n * N.t_in, N.a_ld, N.k_full, N.wb, N.cout, N.w_ld, N.biasb, N.block_n,
+                                 N.n_tiles_n, N.t_in, N.t_conv, N.relu, 0, full, ldo, N.t_conv, dev, s);
+            if (rc) return rc;
+            bf16* pooled = reinterpret_cast<bf16*>(base + P.pooled[li]);
+            const long long pe = (long long)n * N.t_pool * ldo;
+            pool_fwd_bf16_kernel<<<grid_for(pe, dev), 256, 0, s>>>(full, N.t_conv, N.pool, N.t_pool, ldo, n, pooled, ext_mask(li),
+                                                                   mask_of(li), T->dropout_p[li], seed_of(li));
+            SB_COUNT_LAUNCH();
+            SB_CHECK_LAUNCH();
+            if (!last) xin[li + 1] = pooled;
+        } else {
+            rc = launch_tc_plain(xin[li], n, N.a_ld, N.k_full, N.wb, N.cout, N.w_ld, N.biasb, N.block_n, N.n_tiles_n, 1, 1,
+                                 N.relu, last ? 1 : 0, last ? (void*)logits : (void*)full, last ? ldl : ldo, 1, dev, s);
+            if (rc) return rc;
+            if (!last && (T->dropout_p[li] > 0.f || ext_mask(li))) {
+                dropout_bf16_kernel<<<grid_for((long long)n * ldo, dev), 256, 0, s>>>(full, (long long)n * ldo, ext_mask(li),
+                                                                                      mask_of(li), T->dropout_p[li], seed_of(li));
+                SB_COUNT_LAUNCH();
+            }
+            if (!last) xin[li + 1] = full;
+        }
+    }
+
+    // ------------------------------------------------------------------ loss + dL/dz
+    bf16* g_cur = reinterpret_cast<bf16*>(base + P.g_a);
+    bf16* g_oth = reinterpret_cast<bf16*>(base + P.g_b);
+    SB_CHECK_CUDA(cudaMemsetAsync(loss, 0, 4, s));
+    SB_CHECK_CUDA(cudaMemsetAsync(grads, 0, T->n_params * 4, s));
+    {
+        const int ldz = S->L[L - 1].cout_ld;
+        bce_bf16_kernel<<<grid_for((long long)n * ldz, dev), 256, 0, s>>>(logits, ldl, targets, n, F, g_cur, ldz, loss);
+        SB_COUNT_LAUNCH();
+        SB_CHECK_LAUNCH();
+    }
+
+    // ------------------------------------------------------------------ backward, layers L-1 .. 1 on tcgen05
+    for (size_t li = L - 1; li >= 1; --li) {
+        const NetLayer& N = net->layers[li];
+        const bool conv = N.type == SB_LAYER_CONV;
+        const bool last = li + 1 == L;
+        const int ldo = S->L[li].cout_ld;
+        const int ch_in = conv ? N.cin : N.cin;
+        const int ld_in = round_up(ch_in, 8);
+        float* gw = grads + T->goff_w[li];
+        float* gb = grads + T->goff_b[li];
+        const bool dropped = !last && (T->dropout_p[li] > 0.f || ext_mask(li));
+        const float* mk = dropped ? (ext_mask(li) ? ext_mask(li) : mask_of(li)) : nullptr;
+        const bf16* full = reinterpret_cast<const bf16*>(base + P.full[li]);
+        const long long rows = (long long)n * N.t_in;
+        const bf16* dy;
+        int rc;
+        if (conv) {
+            SB_CHECK_CUDA(cudaMemsetAsync(g_oth, 0, (size_t)(N.k - 1) * ldo * 2, s));
+            bf16* dfull = g_oth + (size_t)(N.k - 1) * ldo;
+            pool_relu_bwd_bf16_kernel<<<grid_for(rows * ldo, dev), 256, 0, s>>>(full, N.t_conv, g_cur, mk, N.t_in, N.pool,
+                                                                               N.t_pool, ldo, n, dfull);
+            SB_COUNT_LAUNCH();
+            SB_CHECK_LAUNCH();
+            dy = dfull;
+        } else {
+            if (dropped || (N.relu && !last)) {
+                fc_bwd_bf16_kernel<<<grid_for(rows * ldo, dev), 256, 0, s>>>(g_cur, full, mk, (N.relu && !last) ? 1 : 0, rows * ldo);
+                SB_COUNT_LAUNCH();
+            }
+            dy = g_cur;
+        }
+        // wgrad on tcgen05: G[kk][o] += sum_r Xin[r*ld_in + kk] dY[r][o]
+        rc = sb_tc_wgrad_launch(dy, ldo, xin[li], conv ? ld_in : N.a_ld, rows, rows, N.cout, N.k_f32, gw, N.ldw_f32, dev, s);
+        if (rc) return rc;
+        colsum_bf16_kernel<<<(N.cout + 31) / 32, 256, 0, s>>>(dy, rows, ldo, N.cout, gb);
+        SB_COUNT_LAUNCH();
+        SB_CHECK_LAUNCH();
+        // dgrad on tcgen05 -> gradient w.r.t. this layer's input (previous layer's final output)
+        if (conv) {
+            rc = launch_tc_plain(g_oth, rows + (N.k - 1), ldo, N.k * ldo, S->L[li].wt, N.cin, S->L[li].wt_ld, net->zero_bias_tc,
+                                 S->L[li].dg_block_n, S->L[li].dg_n_tiles_n, 1, 1, 0, 0, g_cur, ld_in, 1, dev, s);
+            if (rc) return rc;
+        } else {
+            rc = launch_tc_plain(dy, rows, ldo, ldo, S->L[li].wt, N.cin, S->L[li].wt_ld, net->zero_bias_tc,
+                                 S->L[li].dg_block_n, S->L[li].dg_n_tiles_n, 1, 1, 0, 0, g_oth, N.a_ld, 1, dev, s);
+            if (rc) return rc;
+            bf16* t = g_cur; g_cur = g_oth; g_oth = t;
+        }
+        if (li == 1) break;
+    }
+
+    // ------------------------------------------------------------------ layer 0 backward on CUDA cores
+    {
+        const long long pe = (long long)n * N0.t_pool * N0.cout;
+        float* g32 = reinterpret_cast<float*>(base + P.g32);
+        float* dpool32 = g32;                                     // (n, t_pool, cout) fp32
+        float* dfull32 = g32 + (((size_t)pe + 63) / 64) * 64;     // (n, t_in, cout) fp32
+        bf16_to_f32_kernel<<<grid_for(pe, dev), 256, 0, s>>>(g_cur, (long long)n * N0.t_pool, N0.cout, ld0b, dpool32, N0.cout);
+        SB_COUNT_LAUNCH();
+        if (T->dropout_p[0] > 0.f || ext_mask(0)) {
+            mul_kernel<<<grid_for(pe, dev), 256, 0, s>>>(dpool32, ext_mask(0) ? ext_mask(0) : mask_of(0), pe);
+            SB_COUNT_LAUNCH();
+        }
+        const long long rows = (long long)n * N0.t_in;
+        pool_relu_bwd_kernel<<<grid_for(rows * N0.cout, dev), 256, 0, s>>>(full0, dpool32, N0.t_in, N0.pool, N0.t_pool, N0.cout, n,
+                                                                           dfull32);
+        SB_COUNT_LAUNCH();
+        const int rpb = 2048;
+        dim3 grid((unsigned)((rows + rpb - 1) / rpb), (unsigned)((N0.cout + 127) / 128));
+        conv1_wgrad_kernel<<<grid, 128, 0, s>>>(x, rows, dfull32, N0.cout, rows, N0.k, N0.cout, rpb, grads + T->goff_w[0],
+                                                N0.ldw_f32);
+        SB_COUNT_LAUNCH();
+        colsum_kernel<<<(N0.cout + 31) / 32, 256, 0, s>>>(dfull32, rows, N0.cout, N0.cout, grads + T->goff_b[0]);
+        SB_COUNT_LAUNCH();
+        SB_CHECK_LAUNCH();
+    }
+    return SB_OK;
+}

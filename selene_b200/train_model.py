@@ -22,13 +22,17 @@ logger = logging.getLogger("selene")
 
 class B200Trainer(object):
     def __init__(self, model_or_layers, sequence_length, lr=0.01, momentum=0.9, weight_decay=1e-6,
-                 dropout=None, perm=(0, 1, 2, 3), device=None, seed=0):
+                 dropout=None, perm=(0, 1, 2, 3), device=None, seed=0, precision="fp32"):
         import torch
         layers = model_or_layers if isinstance(model_or_layers, list) else layers_from_module(model_or_layers)
         self.net = B200Net(layers, sequence_length, perm=perm, device=device)
         self._lib = self.net._lib
         self._h = self.net._h
-        _lib.check(self._lib.sb_net_train_init(self._h), "sb_net_train_init")
+        self.precision = precision
+        if precision == "bf16":
+            _lib.check(self._lib.sb_net_train_init_tc(self._h), "sb_net_train_init_tc")
+        else:
+            _lib.check(self._lib.sb_net_train_init(self._h), "sb_net_train_init")
         self.n_layers = int(self._lib.sb_net_n_layers(self._h))
         self.n_params = int(self._lib.sb_net_n_params(self._h))
         self.lr, self.momentum, self.weight_decay = float(lr), float(momentum), float(weight_decay)
@@ -58,7 +62,9 @@ class B200Trainer(object):
 
     def _workspace(self, n):
         import torch
-        need = int(self._lib.sb_net_train_workspace_bytes(self._h, int(n)))
+        fn = (self._lib.sb_net_train_workspace_bytes_tc if self.precision == "bf16"
+              else self._lib.sb_net_train_workspace_bytes)
+        need = int(fn(self._h, int(n)))
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
             self._ws = torch.empty((need,), dtype=torch.uint8, device=self.device)
@@ -75,7 +81,8 @@ class B200Trainer(object):
             mask_arr = (C.c_void_p * self.n_layers)()
             for k, t in masks.items():
                 mask_arr[int(k)] = t.data_ptr()
-        _lib.check(self._lib.sb_net_forward_backward(
+        fb = self._lib.sb_net_forward_backward_tc if self.precision == "bf16" else self._lib.sb_net_forward_backward
+        _lib.check(fb(
             self._h, _lib.ptr(inputs), _lib.ptr(targets), n, mask_arr, self.seed * 1000003 + self.step_count,
             _lib.ptr(ws), ws.numel(), _lib.ptr(self.grads), _lib.ptr(self.loss), _lib.stream_ptr()),
             "sb_net_forward_backward")
@@ -121,7 +128,7 @@ class TrainModel(object):
 
     def __init__(self, model, data_sampler, loss_criterion=None, optimizer_class=None, optimizer_kwargs=None,
                  batch_size=64, max_steps=1000, report_stats_every_n_steps=100, sequence_length=1000,
-                 use_cuda=True, device=None, **_ignored):
+                 use_cuda=True, device=None, precision="fp32", **_ignored):
         if not use_cuda:
             raise ValueError("selene_b200 has no CPU path: use_cuda must be True")
         kw = dict(optimizer_kwargs or {})
@@ -131,7 +138,7 @@ class TrainModel(object):
         self.nth_step_report_stats = report_stats_every_n_steps
         self.trainer = B200Trainer(model, sequence_length, lr=kw.get("lr", 0.01), momentum=kw.get("momentum", 0.0),
                                    weight_decay=kw.get("weight_decay", 0.0),
-                                   dropout=B200Trainer.dropout_of_module(model), device=device)
+                                   dropout=B200Trainer.dropout_of_module(model), device=device, precision=precision)
         self.step = 0
         self._time_per_step, self._train_loss = [], []
 

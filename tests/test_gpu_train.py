@@ -101,3 +101,48 @@ def test_device_dropout_statistics():
     l1 = tr.step(x, y)
     l2 = tr.step(x, y)
     assert np.isfinite(l1) and np.isfinite(l2) and l2 < l1 + 1e-3
+
+
+@pytest.mark.parametrize("with_masks", [False, True])
+def test_train_step_tcgen05_close_to_torch(with_masks):
+    """bf16 tensor-core training step (fp32 master weights / gradients): gradients within bf16 rounding of
+    torch fp32 autograd, loss trajectory within 1e-3."""
+    import torch
+    import sb_models as M
+    from selene_b200.train_model import B200Trainer
+    torch.manual_seed(3)
+    model = M.DeepSEA(1000, 919)
+    rng = np.random.default_rng(5)
+    n = 6
+    codes = rng.integers(0, 4, (n, 1000))
+    x = np.zeros((n, 1000, 4), np.float32)
+    for b in range(4):
+        x[codes == b, b] = 1
+    y = (rng.random((n, 919)) < 0.1).astype(np.float32)
+    masks = None
+    if with_masks:
+        shapes = {0: (n, 248, 320, 0.2), 1: (n, 60, 480, 0.2), 2: (n, 53, 960, 0.5)}
+        masks = {k: ((rng.random(s[:3]) >= s[3]) / (1 - s[3])).astype(np.float32) for k, s in shapes.items()}
+    lr, mom, wd, steps = 0.05, 0.9, 1e-6, 3
+    tr = B200Trainer(model, 1000, lr=lr, momentum=mom, weight_decay=wd, precision="bf16")
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    md = {k: torch.from_numpy(v).cuda() for k, v in masks.items()} if masks else None
+    ref_losses, ref_grads = _torch_reference(model, x, y, masks, lr, mom, wd, steps)
+    got_losses = []
+    for s in range(steps):
+        tr.forward_backward(xd, yd, md)
+        if s == 0:
+            for li in range(5):
+                gw, gb = tr.layer_params(li, grads=True)
+                rw, rb = ref_grads[li], ref_grads[5 + li]
+                # relative Frobenius error: bf16 operands, fp32 accumulation
+                rel = np.linalg.norm(gw - rw) / max(np.linalg.norm(rw), 1e-20)
+                relb = np.linalg.norm(gb - rb) / max(np.linalg.norm(rb), 1e-20)
+                assert rel <= 3e-2, ("weight grad", li, rel)
+                assert relb <= 3e-2, ("bias grad", li, relb)
+                cos = (gw * rw).sum() / (np.linalg.norm(gw) * np.linalg.norm(rw) + 1e-30)
+                assert cos >= 0.999, ("weight grad direction", li, cos)
+        tr.sgd_step()
+        got_losses.append(float(tr.loss.item()))
+    assert np.allclose(got_losses, ref_losses, rtol=0, atol=1e-3), (got_losses, ref_losses)
+    assert got_losses[-1] < got_losses[0]
