@@ -185,30 +185,39 @@ def main():
     if want('train'):
         # ------------------------------------------------------------ config 3: training step, batch 64
         from selene_b200.train_model import B200Trainer
-        torch.manual_seed(0)
-        mdl = M.DeepSEA(1000, 919)
-        tr = B200Trainer(mdl, 1000, lr=0.01, momentum=0.9, weight_decay=1e-6, dropout=B200Trainer.dropout_of_module(mdl))
-        xb, yb = smp.sample_device(64, seq_dtype="float32", label_dtype="float32")
-        for _ in range(2):
-            tr.step(xb, yb)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        ns = 5
-        for _ in range(ns):
-            tr.forward_backward(xb, yb)
-            tr.sgd_step()
-        torch.cuda.synchronize()
-        dt_ = (time.perf_counter() - t0) / ns
-        emit(config="3: DeepSEA training step (fwd train-mode + BCE + bwd + SGD), batch 64, fp32 CUDA-core path",
-             seconds_per_step=dt_, samples_per_s=64 / dt_, tflops=64 * 3 * 1.0986e9 / dt_ / 1e12)
-        t0 = time.perf_counter()
-        for _ in range(ns):
-            xb, yb = smp.sample_device(64, seq_dtype="float32", label_dtype="float32")
-            tr.step(xb, yb)
-        torch.cuda.synchronize()
-        dt_ = (time.perf_counter() - t0) / ns
-        emit(config="3: sample + training step end to end (RandomPositionsSampler -> step), batch 64",
-             seconds_per_step=dt_, samples_per_s=64 / dt_)
+        for prec in ("bf16", "fp32"):
+            torch.manual_seed(0)
+            mdl = M.DeepSEA(1000, 919)
+            tr = B200Trainer(mdl, 1000, lr=0.01, momentum=0.9, weight_decay=1e-6,
+                             dropout=B200Trainer.dropout_of_module(mdl), precision=prec)
+            for batch in ((64, 256) if prec == "bf16" else (64,)):
+                xb, yb = smp.sample_device(batch, seq_dtype="float32", label_dtype="float32")
+                for _ in range(3):
+                    tr.step(xb, yb)
+                torch.cuda.synchronize()
+                ns = 10 if prec == "bf16" else 4
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(ns):
+                    tr.forward_backward(xb, yb)
+                    tr.sgd_step()
+                e1.record()
+                torch.cuda.synchronize()
+                dt_ = e0.elapsed_time(e1) / ns * 1e-3
+                emit(config="3: DeepSEA training step (fwd train-mode + BCE + bwd + SGD), per GPU", precision=prec,
+                     batch=batch, seconds_per_step=dt_, samples_per_s=batch / dt_,
+                     tflops=batch * 3 * 1.0986e9 / dt_ / 1e12)
+            if prec == "bf16":
+                t0 = time.perf_counter()
+                ns = 10
+                for _ in range(ns):
+                    xb, yb = smp.sample_device(64, seq_dtype="float32", label_dtype="float32")
+                    tr.step(xb, yb)
+                torch.cuda.synchronize()
+                dt_ = (time.perf_counter() - t0) / ns
+                emit(config="3: sample + training step end to end (RandomPositionsSampler -> step -> loss to host)",
+                     precision=prec, batch=64, seconds_per_step=dt_, samples_per_s=64 / dt_)
+            del tr
     if not want('sampler'):
         return 0
     smp.sample_device(64)
