@@ -202,22 +202,25 @@ __global__ void __launch_bounds__(256) flip_weights_kernel(const float* __restri
     }
 }
 
-// db[o] = sum_r dY[r][o]
+// db[o] += sum_r dY[r][o]  (db zeroed by the caller; grid.y splits the rows, partials are added atomically)
+constexpr int kColsumRows = 1024;
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dy, long long rows, int ld, int n_cols,
                                                      float* __restrict__ db) {
     const int o = blockIdx.x * 32 + (threadIdx.x & 31);
     const int part = threadIdx.x >> 5;  // 8 row partitions
     __shared__ float red[8][33];
+    const long long r0 = (long long)blockIdx.y * kColsumRows;
+    const long long r1 = r0 + kColsumRows < rows ? r0 + kColsumRows : rows;
     float s = 0.f;
     if (o < n_cols)
-        for (long long r = part; r < rows; r += 8) s += dy[r * ld + o];
+        for (long long r = r0 + part; r < r1; r += 8) s += dy[r * ld + o];
     red[part][threadIdx.x & 31] = s;
     __syncthreads();
     if (part == 0 && o < n_cols) {
         float t = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x & 31];
-        db[o] = t;
+        if (t != 0.f) atomicAdd(db + o, t);
     }
 }
 
@@ -431,7 +434,8 @@ extern "C" int sb_net_forward_backward(sb_net* net, const float* x, const float*
         int rc = launch_gemm_gen(B[li].x, rows * N.cin, 1, N.cin, dy, N.cout, 1, N.k_f32, N.cout, rows, nullptr, 0, gw,
                                  N.ldw_f32, s);
         if (rc) return rc;
-        colsum_kernel<<<(N.cout + 31) / 32, 256, 0, s>>>(dy, rows, N.cout, N.cout, gb);
+        colsum_kernel<<<dim3((N.cout + 31) / 32, (unsigned)((rows + kColsumRows - 1) / kColsumRows)), 256, 0, s>>>(
+            dy, rows, N.cout, N.cout, gb);
         SB_COUNT_LAUNCH();
         SB_CHECK_LAUNCH();
         if (li == 0) break;

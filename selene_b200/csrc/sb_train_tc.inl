@@ -174,16 +174,18 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict
     const int o = blockIdx.x * 32 + (threadIdx.x & 31);
     const int part = threadIdx.x >> 5;
     __shared__ float red[8][33];
+    const long long r0 = (long long)blockIdx.y * kColsumRows;
+    const long long r1 = r0 + kColsumRows < rows ? r0 + kColsumRows : rows;
     float s = 0.f;
     if (o < n_cols)
-        for (long long r = part; r < rows; r += 8) s += __bfloat162float(dy[r * ld + o]);
+        for (long long r = r0 + part; r < r1; r += 8) s += __bfloat162float(dy[r * ld + o]);
     red[part][threadIdx.x & 31] = s;
     __syncthreads();
     if (part == 0 && o < n_cols) {
         float t = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x & 31];
-        db[o] = t;
+        if (t != 0.f) atomicAdd(db + o, t);
     }
 }
 
@@ -192,11 +194,12 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict
 constexpr int kW1MaxK = 32;
 __global__ void __launch_bounds__(128) conv1_wgrad_kernel(const float* __restrict__ x, long long x_rows, const float* __restrict__ dy,
                                                           int ld_dy, long long rows, int taps, int cout, int rows_per_block,
-                                                          float* __restrict__ gw, int ldw) {
+                                                          float* __restrict__ gw, int ldw, float* __restrict__ gb) {
     __shared__ float xs[64 + 8][4];
     const long long r0 = (long long)blockIdx.x * rows_per_block;
     const int o = blockIdx.y * 128 + threadIdx.x;
     float acc[kW1MaxK];
+    float gsum = 0.f;   // bias gradient of channel o over this CTA's rows
 #pragma unroll
     for (int k = 0; k < kW1MaxK; ++k) acc[k] = 0.f;
     for (long long rb = r0; rb < r0 + rows_per_block && rb < rows; rb += 64) {
@@ -211,6 +214,7 @@ __global__ void __launch_bounds__(128) conv1_wgrad_kernel(const float* __restric
                 const long long r = rb + q;
                 if (r >= rows || r >= r0 + rows_per_block) break;
                 const float g = dy[r * ld_dy + o];
+                gsum += g;
                 if (g != 0.f) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
@@ -221,9 +225,11 @@ __global__ void __launch_bounds__(128) conv1_wgrad_kernel(const float* __restric
             }
         }
     }
-    if (o < cout)
+    if (o < cout) {
         for (int k = 0; k < taps * 4; ++k)
             if (acc[k] != 0.f) atomicAdd(gw + (long long)k * ldw + o, acc[k]);
+        if (gsum != 0.f) atomicAdd(gb + o, gsum);
+    }
 }
 
 struct TcTrainLayer {
@@ -478,7 +484,8 @@ extern "C" int sb_net_forward_backward_tc(sb_net* net, const float* x, const flo
         // wgrad on tcgen05: G[kk][o] += sum_r Xin[r*ld_in + kk] dY[r][o]
         rc = sb_tc_wgrad_launch(dy, ldo, xin[li], conv ? ld_in : N.a_ld, rows, rows, N.cout, N.k_f32, gw, N.ldw_f32, dev, s);
         if (rc) return rc;
-        colsum_bf16_kernel<<<(N.cout + 31) / 32, 256, 0, s>>>(dy, rows, ldo, N.cout, gb);
+        colsum_bf16_kernel<<<dim3((N.cout + 31) / 32, (unsigned)((rows + kColsumRows - 1) / kColsumRows)), 256, 0, s>>>(
+            dy, rows, ldo, N.cout, gb);
         SB_COUNT_LAUNCH();
         SB_CHECK_LAUNCH();
         // dgrad on tcgen05 -> gradient w.r.t. this layer's input (previous layer's final output)
@@ -511,12 +518,10 @@ extern "C" int sb_net_forward_backward_tc(sb_net* net, const float* x, const flo
         pool_relu_bwd_kernel<<<grid_for(rows * N0.cout, dev), 256, 0, s>>>(full0, dpool32, N0.t_in, N0.pool, N0.t_pool, N0.cout, n,
                                                                            dfull32);
         SB_COUNT_LAUNCH();
-        const int rpb = 2048;
+        const int rpb = 256;
         dim3 grid((unsigned)((rows + rpb - 1) / rpb), (unsigned)((N0.cout + 127) / 128));
         conv1_wgrad_kernel<<<grid, 128, 0, s>>>(x, rows, dfull32, N0.cout, rows, N0.k, N0.cout, rpb, grads + T->goff_w[0],
-                                                N0.ldw_f32);
-        SB_COUNT_LAUNCH();
-        colsum_kernel<<<(N0.cout + 31) / 32, 256, 0, s>>>(dfull32, rows, N0.cout, N0.cout, grads + T->goff_b[0]);
+                                                N0.ldw_f32, grads + T->goff_b[0]);
         SB_COUNT_LAUNCH();
         SB_CHECK_LAUNCH();
     }
