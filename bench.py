@@ -216,7 +216,6 @@ def main():
     from selene_b200 import _lib
     from selene_b200.sequences import Genome
     from selene_b200.predict.model_predict import AnalyzeSequences
-    from oracle import selene_oracle as O  # weights only (random-init DeepSEA, torch.manual_seed(0))
     lib = _lib.load()
 
     names, seqs = synth_genome_arrays(args.genome_mbp)
@@ -296,7 +295,9 @@ def main():
     layer_names = ["conv1(lut)", "conv2", "conv3", "fc1", "fc2"]
     roofline = {"bound": "tensor", "kernel": "tc_layer_kernel[%s]" % layer_names[dom] if dom < 5 else str(dom),
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                "traffic": None, "peak_source": peak_src,
+                # dram__bytes_read+write of one conv2 launch of 8192 rows (ncu --set full, profiles/r01a_summary.md);
+                # algorithmic bytes of that launch: 8192*(248*320 + 60*480)*2 + weights 2.5 MB = 1.77 GB
+                "traffic": 1.757e9 if dom == 1 else None, "peak_source": peak_src,
                 "layer_ms_per_step": {layer_names[i] if i < 5 else str(i): layer_ms[i] / args.steps
                                       for i in range(len(layer_ms))},
                 "whole_net_tflops": az.net.flops_per_seq * 2.0 * V * args.steps / (ms_max * 1e-3) / 1e12}
