@@ -40,6 +40,11 @@ struct NetLayer {
     float* lut;  // dev (k x 5 x cout)
     uint16_t* w1_packed;  // dev, tcgen05 core-matrix layout (sb_conv1.cu); null if unsupported
     float* bias1_padded;  // dev, n_pass*64
+    // first layer too long / pooled too wide for sb_conv1.cu (DanQ: 26 taps, pool 13): generic layer kernel
+    // on a (n, L, 8) bf16 one-hot (4 zero channels), K index = tap*8 + canonical base
+    __nv_bfloat16* w0_b;
+    int w0_ld, w0_block_n, w0_n_tiles_n;
+    float* w0_bias;
     // SB_LAYER_BILSTM: the generic fields above hold the input projection (cin -> 8*hidden, both
     // directions, bias = b_ih + b_hh); these hold the recurrent matrices (hidden -> 4*hidden) per direction
     int hidden;
@@ -337,6 +342,48 @@ __global__ void __launch_bounds__(256) zero_u32_kernel(uint32_t* p, long long n)
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = 0u;
 }
 
+// (n, L, 8) bf16 one-hot rows of the model rows (code row + optional substitution); channels 4..7 zero
+__global__ void __launch_bounds__(256) codes_onehot8_kernel(const uint8_t* __restrict__ codes, const int32_t* __restrict__ src,
+                                                            const int32_t* __restrict__ sub_pos,
+                                                            const uint8_t* __restrict__ sub_code, long long row0,
+                                                            long long n_rows, int L, uint4* __restrict__ out) {
+    const long long total = n_rows * L;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long r = i / L;
+        const int t = (int)(i - r * L);
+        const long long row = row0 + r;
+        const long long srow = src ? (long long)src[row] : row;
+        int c = __ldg(codes + srow * L + t);
+        if (sub_pos && sub_pos[row] == t) c = sub_code ? sub_code[row] : 4;
+        uint32_t lo = 0, hi = 0;
+        if (c > 3) { lo = 0x3E803E80u; hi = 0x3E803E80u; }
+        else if (c == 0) lo = 0x00003F80u;
+        else if (c == 1) lo = 0x3F800000u;
+        else if (c == 2) hi = 0x00003F80u;
+        else hi = 0x3F800000u;
+        out[i] = make_uint4(lo, hi, 0u, 0u);
+    }
+}
+
+// bf16 max-pool + compaction: out[s][tp][c] = max_q full[s][tp*pool + q][c]
+__global__ void __launch_bounds__(256) pool_bf16_kernel(const __nv_bfloat16* __restrict__ full, int t_full, int pool,
+                                                        int t_pool, int out_pitch, int ld, long long n_seq,
+                                                        __nv_bfloat16* __restrict__ out) {
+    const long long total = n_seq * t_pool * ld;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = (int)(i % ld);
+        const long long rt = i / ld;
+        const int tp = (int)(rt % t_pool);
+        const long long s = rt / t_pool;
+        float m = -INFINITY;
+        for (int q = 0; q < pool; ++q)
+            m = fmaxf(m, __bfloat162float(full[(s * t_full + (long long)tp * pool + q) * ld + c]));
+        out[(s * out_pitch + tp) * ld + c] = __float2bfloat16_rn(m);
+    }
+}
+
 int grid_for(long long total, int device) {
     long long b = (total + 255) / 256;
     const long long cap = (long long)sb_sm_count(device) * 16;
@@ -503,6 +550,21 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
                 std::vector<float> bp((size_t)n_pass * 64, 0.f);
                 for (int o = 0; o < S.cout; ++o) bp[o] = S.bias[o];
                 rc = upload(&N.bias1_padded, bp); if (rc) return rc;
+            } else {
+                N.w0_ld = S.k * 8;
+                std::vector<uint16_t> w0((size_t)S.cout * N.w0_ld, 0);
+                for (int o = 0; o < S.cout; ++o)
+                    for (int j = 0; j < S.k; ++j)
+                        for (int b = 0; b < 4; ++b)
+                            w0[(size_t)o * N.w0_ld + (size_t)j * 8 + b] =
+                                f32_to_bf16_bits(S.weight[((size_t)o * 4 + perm[b]) * S.k + j]);
+                rc = upload(reinterpret_cast<uint16_t**>(&N.w0_b), w0); if (rc) return rc;
+                const int nt = (S.cout + 255) / 256;
+                N.w0_n_tiles_n = nt;
+                N.w0_block_n = round_up((S.cout + nt - 1) / nt, 16);
+                std::vector<float> bb((size_t)nt * N.w0_block_n, 0.f);
+                for (int o = 0; o < S.cout; ++o) bb[o] = S.bias[o];
+                rc = upload(&N.w0_bias, bb); if (rc) return rc;
             }
         }
 
@@ -587,7 +649,7 @@ extern "C" int sb_net_destroy(sb_net* net) {
     if (!net) return SB_OK;
     cudaSetDevice(net->device);
     for (auto& N : net->layers) {
-        cudaFree(N.wf); cudaFree(N.biasf); cudaFree(N.wb); cudaFree(N.wb_tap); cudaFree(N.biasb); cudaFree(N.lut); cudaFree(N.w1_packed); cudaFree(N.bias1_padded);
+        cudaFree(N.wf); cudaFree(N.biasf); cudaFree(N.wb); cudaFree(N.wb_tap); cudaFree(N.biasb); cudaFree(N.lut); cudaFree(N.w1_packed); cudaFree(N.bias1_padded); cudaFree(N.w0_b); cudaFree(N.w0_bias);
         cudaFree(N.whh_f[0]); cudaFree(N.whh_f[1]); cudaFree(N.whh_b[0]); cudaFree(N.whh_b[1]); cudaFree(N.zero_bias);
     }
     delete net;
@@ -671,6 +733,11 @@ WsPlan plan_ws(const sb_net* net, long long n, int precision, bool generic) {
             const size_t fb = (size_t)ch * N.t_in * N.cout * 4;
             if (fb > full) full = fb;
         }
+    }
+    if (precision == SB_PREC_BF16 && !generic && net->layers[0].w0_b) {
+        const NetLayer& N0 = net->layers[0];
+        const size_t fb = (size_t)ch * net->L * 8 * 2 + 1024 + (size_t)ch * N0.t_conv * N0.out_ld_b * 2;
+        if (fb > full) full = fb;
     }
     // generic-input first conv also runs through the fp32 "full" path
     if (generic) {
@@ -838,6 +905,29 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
                                             N.t_pool, N.pitch_out, N.cout, out_ld, N.relu, N.w1_packed,
                                             N.bias1_padded, act[cur], dev, stream);
                 if (rc) return rc;
+            } else if (bf && N.w0_b) {
+                // one-hot (n, L, 8) -> generic tcgen05 layer kernel (unpooled) -> bf16 pool
+                uint4* oh = reinterpret_cast<uint4*>(full);
+                codes_onehot8_kernel<<<grid_for(m * net->L, dev), 256, 0, stream>>>(in.codes, in.src, in.sub_pos, in.sub_code,
+                                                                                  r0, m, net->L, oh);
+                SB_COUNT_LAUNCH();
+                SB_CHECK_LAUNCH();
+                __nv_bfloat16* fullb = reinterpret_cast<__nv_bfloat16*>(
+                    reinterpret_cast<uint8_t*>(full) + (((size_t)m * net->L * 16 + 1023) / 1024) * 1024);
+                SbTcLayer T0;
+                memset(&T0, 0, sizeof(T0));
+                T0.a = oh; T0.rows_a = m * (long long)net->L; T0.a_ld = 8; T0.k_full = N.k * 8;
+                T0.w = N.w0_b; T0.n_rows_w = N.cout; T0.w_ld = N.w0_ld;
+                T0.bias = N.w0_bias; T0.block_n = N.w0_block_n; T0.n_tiles_n = N.w0_n_tiles_n;
+                T0.t_in = net->L; T0.t_conv = N.t_conv; T0.pool = 1; T0.relu = N.relu; T0.out_f32 = 0;
+                T0.out = fullb; T0.out_ld = out_ld; T0.out_pitch = N.t_conv;
+                int rc = sb_tc_launch(T0, dev, stream);
+                if (rc) return rc;
+                const long long total = m * N.t_pool * out_ld;
+                pool_bf16_kernel<<<grid_for(total, dev), 256, 0, stream>>>(fullb, N.t_conv, N.pool, N.t_pool, N.pitch_out,
+                                                                           out_ld, m, reinterpret_cast<__nv_bfloat16*>(act[cur]));
+                SB_COUNT_LAUNCH();
+                SB_CHECK_LAUNCH();
             } else if (bf) {
                 SB_CHECK_CUDA(cudaFuncSetAttribute(conv_codes_kernel<__nv_bfloat16>,
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -851,7 +941,7 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
                     in.codes, in.src, in.sub_pos, in.sub_code, r0, net->L, N.k, N.cout, out_ld, N.relu, N.pool,
                     N.t_pool, N.t_pool, N.lut, N.biasf, reinterpret_cast<float*>(act[cur]));
             }
-            if (!(bf && N.w1_packed)) {
+            if (!(bf && (N.w1_packed || N.w0_b))) {
                 SB_COUNT_LAUNCH();
                 SB_CHECK_LAUNCH();
             }

@@ -34,16 +34,30 @@ __global__ void __launch_bounds__(256) bf16_to_f32_kernel(const bf16* __restrict
     }
 }
 
-// forward B operand from the fp32 master: wb[o][map(kk)] = W[kk][o], map(kk) = (kk / ch) * ch_ld + kk % ch
+// forward B operand from the fp32 master: wb[o][map(kk)] = W[kk][o], map(kk) = (kk / ch) * ch_ld + kk % ch.
+// 32 x 32 tiles through shared memory so that both the fp32 reads (o contiguous) and the bf16 writes
+// (kk contiguous) are coalesced.
 __global__ void __launch_bounds__(256) pack_fwd_kernel(const float* __restrict__ wf, int ldw, long long K, int ch, int ch_ld,
                                                        int cout, bf16* __restrict__ wb, int w_ld) {
-    const long long total = K * cout;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int o = (int)(i % cout);
-        const long long kk = i / cout;
-        const long long col = (kk / ch) * ch_ld + kk % ch;
-        wb[(long long)o * w_ld + col] = __float2bfloat16_rn(wf[kk * ldw + o]);
+    __shared__ float tile[32][33];
+    const long long k0 = (long long)blockIdx.x * 32;
+    const int o0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const long long kk = k0 + r;
+        const int o = o0 + tx;
+        tile[r][tx] = (kk < K && o < cout) ? wf[kk * ldw + o] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int o = o0 + r;
+        const long long kk = k0 + tx;
+        if (o < cout && kk < K) {
+            const long long col = (kk / ch) * ch_ld + kk % ch;
+            wb[(long long)o * w_ld + col] = __float2bfloat16_rn(tile[tx][r]);
+        }
     }
 }
 
@@ -371,8 +385,8 @@ extern "C" int sb_net_forward_backward_tc(sb_net* net, const float* x, const flo
         const bool conv = N.type == SB_LAYER_CONV;
         const int ch = conv ? N.cin : (N.fc_prev_c > 0 ? N.fc_prev_c : N.cin);
         const int ch_ld = round_up(ch, 8);
-        pack_fwd_kernel<<<grid_for((long long)N.k_f32 * N.cout, dev), 256, 0, s>>>(N.wf, N.ldw_f32, N.k_f32, ch, ch_ld, N.cout,
-                                                                                 N.wb, N.w_ld);
+        pack_fwd_kernel<<<dim3((unsigned)((N.k_f32 + 31) / 32), (unsigned)((N.cout + 31) / 32)), 256, 0, s>>>(
+            N.wf, N.ldw_f32, N.k_f32, ch, ch_ld, N.cout, N.wb, N.w_ld);
         SB_COUNT_LAUNCH();
         pack_dgrad_kernel<<<grid_for((long long)N.k_f32 * N.cout, dev), 256, 0, s>>>(
             N.wf, N.ldw_f32, conv ? N.k : 1, conv ? N.cin : N.cin, N.cout, S->L[li].cout_ld, S->L[li].wt, S->L[li].wt_ld);
