@@ -176,7 +176,7 @@ class B200Net(object):
         """Row grouping of BiLSTM recurrences (DanQ): ``group`` = the caller's batch_size, ``interleave``
         = 2 when rows are interleaved ref/alt pairs.  No effect on networks without an LSTM."""
         _lib.check(self._lib.sb_net_set_recurrence(self._h, int(group), int(interleave)), "sb_net_set_recurrence")
-        self._ws = None  # workspace size depends on the grouping
+        # the workspace requirement depends on the grouping; _workspace() re-queries it and only ever grows
 
     def _workspace(self, n, precision):
         import torch
