@@ -60,6 +60,12 @@ struct NetLayer {
 struct sb_train_state;
 struct sb_train_tc_state;
 
+struct LstmGraphKey {
+    const void* act_in; void* act_out; float* xw; uint8_t* ws;
+    long long m; int group, interleave, precision; const void* layer;
+};
+struct LstmGraph { LstmGraphKey key; cudaGraphExec_t exec; unsigned long long n_launches; };
+
 struct sb_net {
     sb_train_state* train;          // sb_train.inl; null until sb_net_train_init
     sb_train_tc_state* train_tc;    // sb_train_tc.inl; null until sb_net_train_init_tc
@@ -75,6 +81,7 @@ struct sb_net {
     int rec_group, rec_interleave;   // row grouping of BiLSTM recurrences (sb_net_set_recurrence)
     bool has_lstm;
     std::vector<NetLayer> layers;
+    std::vector<LstmGraph> lstm_graphs;   // captured BiLSTM layers (run_lstm)
     // optional per-layer device timing (bench.py's roofline leg): one event pair per launch
     bool timing;
     std::vector<std::vector<cudaEvent_t>> ev;  // per layer: start0, stop0, start1, stop1, ...
@@ -648,6 +655,7 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
 extern "C" int sb_net_destroy(sb_net* net) {
     if (!net) return SB_OK;
     cudaSetDevice(net->device);
+    for (auto& g : net->lstm_graphs) cudaGraphExecDestroy(g.exec);
     for (auto& N : net->layers) {
         cudaFree(N.wf); cudaFree(N.biasf); cudaFree(N.wb); cudaFree(N.wb_tap); cudaFree(N.biasb); cudaFree(N.lut); cudaFree(N.w1_packed); cudaFree(N.bias1_padded); cudaFree(N.w0_b); cudaFree(N.w0_bias);
         cudaFree(N.whh_f[0]); cudaFree(N.whh_f[1]); cudaFree(N.whh_b[0]); cudaFree(N.whh_b[1]); cudaFree(N.zero_bias);
@@ -796,8 +804,8 @@ void time_end(sb_net* net, size_t li, cudaStream_t s) {
 
 // One BiLSTM layer over m rows (T positions each): input projection as one GEMM, then G sequential
 // steps of (recurrent GEMM per direction + cell update) batched over every (chain, position) unit.
-int run_lstm(sb_net* net, const NetLayer& N, const void* act_in, void* act_out, long long m, int precision,
-             float* xw, uint8_t* lstm_ws, cudaStream_t stream) {
+int run_lstm_body(sb_net* net, const NetLayer& N, const void* act_in, void* act_out, long long m, int precision,
+                  float* xw, uint8_t* lstm_ws, cudaStream_t stream) {
     const bool bf = precision == SB_PREC_BF16;
     const int dev = net->device;
     const int H = N.hidden, T = N.t_in, G = net->rec_group, I = net->rec_interleave;
@@ -875,6 +883,49 @@ int run_lstm(sb_net* net, const NetLayer& N, const void* act_in, void* act_out, 
         SB_COUNT_LAUNCH();
         SB_CHECK_LAUNCH();
     }
+    return SB_OK;
+}
+
+// The recurrence is ~190 small launches per chunk; issued one by one the host cannot keep the GPU fed, so
+// the whole layer is captured once per (buffers, rows, grouping) into a CUDA graph and replayed.
+int run_lstm(sb_net* net, const NetLayer& N, const void* act_in, void* act_out, long long m, int precision,
+             float* xw, uint8_t* lstm_ws, cudaStream_t stream) {
+    const char* no_graph = getenv("SB_NO_GRAPH");
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cs);
+    if ((no_graph && no_graph[0] == '1') || cs != cudaStreamCaptureStatusNone)
+        return run_lstm_body(net, N, act_in, act_out, m, precision, xw, lstm_ws, stream);
+    LstmGraphKey key = {act_in, act_out, xw, lstm_ws, m, net->rec_group, net->rec_interleave, precision, &N};
+    for (auto& e : net->lstm_graphs)
+        if (memcmp(&e.key, &key, sizeof(key)) == 0) {
+            SB_CHECK_CUDA(cudaGraphLaunch(e.exec, stream));
+            g_sb_launches += e.n_launches;
+            return SB_OK;
+        }
+    // warm the lazily initialised pieces (function attributes, driver entry point) outside the capture
+    if (net->lstm_graphs.empty()) {
+        int rc = run_lstm_body(net, N, act_in, act_out, m, precision, xw, lstm_ws, stream);
+        if (rc) return rc;
+    }
+    const unsigned long long before = g_sb_launches;
+    SB_CHECK_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    int rc = run_lstm_body(net, N, act_in, act_out, m, precision, xw, lstm_ws, stream);
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+    if (rc != SB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    SB_CHECK_CUDA(ce);
+    LstmGraph g;
+    memset(&g, 0, sizeof(g));
+    g.key = key;
+    g.n_launches = g_sb_launches - before;
+    SB_CHECK_CUDA(cudaGraphInstantiate(&g.exec, graph, 0));
+    cudaGraphDestroy(graph);
+    if (net->lstm_graphs.size() >= 16) {   // bounded cache
+        cudaGraphExecDestroy(net->lstm_graphs.front().exec);
+        net->lstm_graphs.erase(net->lstm_graphs.begin());
+    }
+    net->lstm_graphs.push_back(g);
+    SB_CHECK_CUDA(cudaGraphLaunch(g.exec, stream));
     return SB_OK;
 }
 
