@@ -82,6 +82,7 @@ struct sb_net {
     bool has_lstm;
     std::vector<NetLayer> layers;
     std::vector<LstmGraph> lstm_graphs;   // captured BiLSTM layers (run_lstm)
+    cudaStream_t capture_stream;
     // optional per-layer device timing (bench.py's roofline leg): one event pair per launch
     bool timing;
     std::vector<std::vector<cudaEvent_t>> ev;  // per layer: start0, stop0, start1, stop1, ...
@@ -435,6 +436,7 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
     SB_CHECK_CUDA(cudaSetDevice(device));
     sb_net* net = new sb_net();
     net->train = nullptr;
+    net->capture_stream = nullptr;
     net->train_tc = nullptr;
     net->zero_bias_tc = nullptr;
     net->inference_weights_stale = false;
@@ -656,6 +658,7 @@ extern "C" int sb_net_destroy(sb_net* net) {
     if (!net) return SB_OK;
     cudaSetDevice(net->device);
     for (auto& g : net->lstm_graphs) cudaGraphExecDestroy(g.exec);
+    if (net->capture_stream) cudaStreamDestroy(net->capture_stream);
     for (auto& N : net->layers) {
         cudaFree(N.wf); cudaFree(N.biasf); cudaFree(N.wb); cudaFree(N.wb_tap); cudaFree(N.biasb); cudaFree(N.lut); cudaFree(N.w1_packed); cudaFree(N.bias1_padded); cudaFree(N.w0_b); cudaFree(N.w0_bias);
         cudaFree(N.whh_f[0]); cudaFree(N.whh_f[1]); cudaFree(N.whh_b[0]); cudaFree(N.whh_b[1]); cudaFree(N.zero_bias);
@@ -908,10 +911,14 @@ int run_lstm(sb_net* net, const NetLayer& N, const void* act_in, void* act_out, 
         if (rc) return rc;
     }
     const unsigned long long before = g_sb_launches;
-    SB_CHECK_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-    int rc = run_lstm_body(net, N, act_in, act_out, m, precision, xw, lstm_ws, stream);
+    // the caller's stream may be the legacy default stream, which cannot be captured: record on a private
+    // stream, replay on the caller's
+    if (!net->capture_stream) SB_CHECK_CUDA(cudaStreamCreateWithFlags(&net->capture_stream, cudaStreamNonBlocking));
+    cudaStream_t cap = net->capture_stream;
+    SB_CHECK_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+    int rc = run_lstm_body(net, N, act_in, act_out, m, precision, xw, lstm_ws, cap);
     cudaGraph_t graph = nullptr;
-    cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+    cudaError_t ce = cudaStreamEndCapture(cap, &graph);
     if (rc != SB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     SB_CHECK_CUDA(ce);
     LstmGraph g;
