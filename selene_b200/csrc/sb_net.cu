@@ -89,6 +89,11 @@ struct sb_net {
     std::vector<size_t> ev_used;
 };
 
+// sb_lstm.cu
+int sb_lstm_persistent_supported(int H);
+int sb_lstm_persistent_launch(const void* whh0, const void* whh1, int h_ld, const float* xw, float* cstate, void* out,
+                              int out_ld, long long m_rows, int H, int T, int G, int I, int device, cudaStream_t stream);
+
 // sb_conv1.cu
 size_t sb_conv1_pack_weights(const float* w, int cout, int taps, const uint8_t perm[4], uint16_t* out,
                              uint16_t (*to_bf16)(float));
@@ -848,6 +853,12 @@ int run_lstm_body(sb_net* net, const NetLayer& N, const void* act_in, void* act_
                                                                                      (long long)(2 * h_bytes / 4));
     SB_COUNT_LAUNCH();
     SB_CHECK_LAUNCH();
+    {
+        const char* stepwise = getenv("SB_LSTM_STEPWISE");
+        if (bf && sb_lstm_persistent_supported(H) && !(stepwise && stepwise[0] == '1'))
+            return sb_lstm_persistent_launch(N.whh_b[0], N.whh_b[1], N.hidden_ld, xw, cst[0], act_out, N.out_ld_b, m, H, T,
+                                             G, I, dev, stream);
+    }
     long long steps = (m + I - 1) / I;
     if (steps > G) steps = G;
     const int ld4 = round_up(4 * H, 4);
