@@ -854,8 +854,11 @@ int run_lstm_body(sb_net* net, const NetLayer& N, const void* act_in, void* act_
     SB_COUNT_LAUNCH();
     SB_CHECK_LAUNCH();
     {
-        const char* stepwise = getenv("SB_LSTM_STEPWISE");
-        if (bf && sb_lstm_persistent_supported(H) && !(stepwise && stepwise[0] == '1'))
+        // One persistent kernel for all steps (sb_lstm.cu).  Opt-in: measured on B200 (r01) it is 2.4-2.9x SLOWER
+        // than the per-step launches below replayed from a CUDA graph — each CTA's 128 cell-update threads wait
+        // on the per-step input-projection reads and only 38-56 CTAs exist per chunk.
+        const char* persistent = getenv("SB_LSTM_PERSISTENT");
+        if (bf && sb_lstm_persistent_supported(H) && persistent && persistent[0] == '1')
             return sb_lstm_persistent_launch(N.whh_b[0], N.whh_b[1], N.hidden_ld, xw, cst[0], act_out, N.out_ld_b, m, H, T,
                                              G, I, dev, stream);
     }
