@@ -99,7 +99,7 @@ def main():
     e_i = np.ascontiguousarray(s_i + ln)
     _lib.check(lib.sb_intervals_create(_lib.ptr(c_i), _lib.ptr(s_i), _lib.ptr(e_i),
                                        _lib.ptr(f_i), nrows, F, len(names), 0, C.byref(h)), "sb_intervals_create")
-    nq = 65536
+    nq = 65536 if args.quick else 1 << 20   # int64 labels of 2^20 bins = 7.7 GB written per launch
     qc = torch.from_numpy(lr.integers(0, len(names), nq).astype(np.int32)).cuda()
     qs_np = lr.integers(0, per - 200, nq).astype(np.int32)
     qs = torch.from_numpy(qs_np).cuda()

@@ -8,14 +8,16 @@
 // Layout in HBM: all intervals sorted by (chromosome, start) as four int32 arrays — start, end,
 // feature, and a running maximum of `end` inside each chromosome — plus per-chromosome offsets
 // (16 B per interval).  One WARP owns one query bin:
-//   1. lanes binary-search the running max for the first interval that can still reach the bin
-//      (exact for any interval-length mix; ~log2(n) L2-resident probes, done once per QUERY, not per
-//      feature),
-//   2. the warp sweeps the overlapping intervals 32 at a time (coalesced loads), replaying them in
-//      start order so the per-feature union coverage (cov[f], covered_until[f] in shared memory) is
-//      exact,
-//   3. lanes compare coverage with the host-computed integer thresholds and write the F labels with
-//      coalesced stores.
+//   1. a bucket table over positions (one int32 per 1024 bases, L2-resident) brackets the first interval whose
+//      running max end exceeds the bin start; the warp finishes the search with 32 probes per round, normally
+//      one round (exact for any interval-length mix; once per QUERY, not per feature),
+//   2. the warp loads the next 32 intervals (coalesced); a feature that occurs once among the overlapping ones
+//      is labelled straight from registers, features with several intervals are replayed in start order into a
+//      per-feature union state (coverage and covered_until packed in one shared-memory word for bins shorter
+//      than 2^15 bases),
+//   3. the row is zero-filled with 16-byte stores and only the features of overlapping intervals are
+//      compared with the host-computed integer thresholds and set (labels are sparse; thresholds are >= 0,
+//      so an untouched feature is always 0).
 // Algorithmic traffic per query: F x sizeof(out) written + 12 B per overlapping interval read; for
 // large batches the kernel is bound by those output writes.
 #include "sb_common.cuh"
@@ -34,71 +36,226 @@ struct sb_intervals {
     int32_t* feat;       // dev
     int32_t* cmax;       // dev, running max of end inside each chromosome
     int64_t* chrom_off;  // dev, n_chrom + 1
+    // bucket table: for bucket b of chromosome c (positions [b << tab_shift, ...)), the first interval (relative to
+    // chrom_off[c]) whose running max end exceeds b << tab_shift; the answer for any bin start inside the bucket lies
+    // between two consecutive entries, so a query needs one table read and (almost always) one round of probes
+    int32_t* tab;        // dev, tab_off[n_chrom] entries
+    int64_t* tab_off;    // dev, n_chrom + 1
+    int tab_shift;
 };
 
 namespace {
 
 constexpr int kWarpsPerBlock = 4;
 
+// Per-feature state of one query, one 32-bit word per feature while the bin is shorter than 2^15 bases
+// (bits 0-14 covered_until, bits 15-29 union coverage, bit 30 "some row overlapped"); longer bins take the
+// features in two passes with two words each in the same shared memory.
+constexpr int kPackedMaxLen = 32767;
+constexpr int32_t kAnyRow = 0x40000000;
+
+// first index in [lo, hi) whose running max end exceeds qs, by a 32-ary search the warp does together:
+// ~log32(n) dependent rounds of L2-resident probes instead of log2(n)
+__device__ __forceinline__ long long first_reaching(const int32_t* __restrict__ cmax, long long lo, long long hi, int qs,
+                                                    int lane) {
+    while (hi - lo > 32) {
+        const long long stride = (hi - lo + 31) >> 5;
+        long long p = lo + (long long)(lane + 1) * stride - 1;
+        if (p > hi - 1) p = hi - 1;
+        const unsigned reach = __ballot_sync(0xffffffffu, __ldg(cmax + p) > qs);   // monotone: a suffix of lanes
+        if (reach == 0) return hi;
+        const int first = __ffs(reach) - 1;
+        const long long p_first = __shfl_sync(0xffffffffu, p, first);
+        if (first > 0) lo = __shfl_sync(0xffffffffu, p, first - 1) + 1;
+        hi = p_first;   // cmax[p_first] > qs is known: the answer is in [lo, p_first]
+        if (hi == lo) return lo;
+    }
+    const long long i = lo + lane;
+    const unsigned reach = __ballot_sync(0xffffffffu, i < hi && __ldg(cmax + i) > qs);
+    return reach ? lo + (__ffs(reach) - 1) : hi;
+}
+
+// zero one output row with 16-byte stores (rows are only sizeof(OutT)-aligned: element stores for the ragged ends)
+template <typename OutT>
+__device__ __forceinline__ void zero_row(OutT* __restrict__ o, int n, int lane) {
+    constexpr int kPer = 16 / (int)sizeof(OutT);
+    const int mis = (int)((reinterpret_cast<uintptr_t>(o) & 15) / sizeof(OutT));
+    int head = mis ? kPer - mis : 0;
+    if (head > n) head = n;
+    if (lane < head) o[lane] = (OutT)0;
+    const int body = (n - head) / kPer;
+    uint4* o4 = reinterpret_cast<uint4*>(o + head);
+    for (int i = lane; i < body; i += 32) o4[i] = make_uint4(0, 0, 0, 0);
+    const int done = head + body * kPer;
+    if (lane < n - done) o[done + lane] = (OutT)0;
+}
+
+struct LabelArgs {
+    const int32_t *iv_start, *iv_end, *iv_feat, *iv_cmax;
+    const int64_t* chrom_off;
+    const int32_t* tab;
+    const int64_t* tab_off;
+    int tab_shift, n_features, n_chrom;
+    int meta_in_smem;   // chrom_off / tab_off copied to shared memory (n_chrom small)
+};
+
+// clipped [is, ie) of an interval inside the bin, as the reference paints it
+__device__ __forceinline__ void clip_interval(int s, int e, int qs, int qlen, int& is, int& ie) {
+    is = s - qs; if (is < 0) is = 0;              // _genomic_features.pyx:32
+    ie = e - qs; if (ie > qlen) ie = qlen;        // :33
+    if (is == ie) ie += 1;                        // :35-36
+    if (ie > qlen) ie = qlen;                     // numpy slice assignment clamps
+}
+
+// lane 0 replays the intervals of `hit` (lane order = start order) into the per-feature union state
+__device__ __forceinline__ void replay(unsigned hit, int fs, int fe, int ff, int qs, int qlen, bool packed, int f_lo,
+                                       int half, int32_t* st, int lane) {
+    while (hit) {
+        const int l = __ffs(hit) - 1;
+        hit &= hit - 1;
+        const int s = __shfl_sync(0xffffffffu, fs, l);
+        const int e = __shfl_sync(0xffffffffu, fe, l);
+        const int f = __shfl_sync(0xffffffffu, ff, l);
+        if (lane == 0) {
+            int is, ie;
+            clip_interval(s, e, qs, qlen, is, ie);
+            if (packed) {
+                const int32_t w = st[f];
+                int u = w & 0x7fff, cv = (w >> 15) & 0x7fff;
+                if (ie > u) { cv += ie - (is > u ? is : u); u = ie; }
+                st[f] = u | (cv << 15) | kAnyRow;             // "any row" marker for no-threshold mode
+            } else {
+                int32_t* cov = st + (f - f_lo);
+                int32_t* until = cov + half;
+                const int u = *until;
+                if (ie > u) { *cov += ie - (is > u ? is : u); *until = ie; }
+                *cov |= kAnyRow;
+            }
+        }
+    }
+}
+
+// Labels are sparse (a bin overlaps a handful of the features), so a query costs one vectorised zero fill of its
+// row plus work proportional to the intervals it overlaps: no per-feature loop anywhere.  A feature that occurs
+// once among the overlapping intervals (the common case) is labelled straight from registers; features with
+// several intervals, and bins with more than 32 candidate intervals, go through the per-warp union state in
+// shared memory, which is all-zero between queries (only touched entries are written and then cleared).
 template <typename OutT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) label_bins_kernel(
-    const int32_t* __restrict__ iv_start, const int32_t* __restrict__ iv_end, const int32_t* __restrict__ iv_feat,
-    const int32_t* __restrict__ iv_cmax, const int64_t* __restrict__ chrom_off, int n_features, int n_chrom,
-    const int32_t* __restrict__ q_chrom, const int32_t* __restrict__ q_start, const int32_t* __restrict__ q_end,
-    int n_queries, const int32_t* __restrict__ thr_i, OutT* __restrict__ out) {
+    const LabelArgs a, const int32_t* __restrict__ q_chrom, const int32_t* __restrict__ q_start,
+    const int32_t* __restrict__ q_end, int n_queries, const int32_t* __restrict__ thr_i, OutT* __restrict__ out) {
     extern __shared__ int32_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int32_t* cov = smem + (size_t)warp * 2 * n_features;  // union coverage per feature
-    int32_t* until = cov + n_features;                     // bin coordinate covered so far per feature
+    const int n_features = a.n_features;
+    const int words = (n_features + 1) & ~1;             // per warp
+    int32_t* st = smem + (size_t)warp * words;
+    for (int i = lane; i < words; i += 32) st[i] = 0;
+    const int64_t* coff = a.chrom_off;
+    const int64_t* toff = a.tab_off;
+    if (a.meta_in_smem) {
+        int64_t* m = reinterpret_cast<int64_t*>(smem + (size_t)kWarpsPerBlock * words);
+        for (int i = threadIdx.x; i <= a.n_chrom; i += blockDim.x) {
+            m[i] = a.chrom_off[i];
+            m[a.n_chrom + 1 + i] = a.tab_off[i];
+        }
+        coff = m;
+        toff = m + a.n_chrom + 1;
+    }
+    __syncthreads();
     const int warps_total = gridDim.x * kWarpsPerBlock;
-    for (int q = blockIdx.x * kWarpsPerBlock + warp; q < n_queries; q += warps_total) {
-        for (int f = lane; f < n_features; f += 32) { cov[f] = 0; until[f] = 0; }
-        __syncwarp();
-        const int c = q_chrom[q];
-        const int qs = q_start[q];
-        const int qe = q_end[q];
+    int q = blockIdx.x * kWarpsPerBlock + warp;
+    int c_n = 0, qs_n = 0, qe_n = 0;
+    if (q < n_queries) { c_n = q_chrom[q]; qs_n = q_start[q]; qe_n = q_end[q]; }
+    for (; q < n_queries; q += warps_total) {
+        const int c = c_n, qs = qs_n, qe = qe_n;
+        if (q + warps_total < n_queries) {   // next query's coordinates: off the dependent chain
+            c_n = q_chrom[q + warps_total]; qs_n = q_start[q + warps_total]; qe_n = q_end[q + warps_total];
+        }
         const int qlen = qe - qs;
-        if (c >= 0 && c < n_chrom && qlen > 0) {
-            const long long lo0 = chrom_off[c], hi0 = chrom_off[c + 1];
-            // first interval whose running max end exceeds qs (the running max is non-decreasing)
-            long long lo = lo0, hi = hi0;
-            while (lo < hi) {
-                const long long mid = (lo + hi) >> 1;
-                if (__ldg(iv_cmax + mid) > qs) hi = mid; else lo = mid + 1;
-            }
-            for (long long base = lo; base < hi0; base += 32) {
-                const long long i = base + lane;
-                int fs = 0x7fffffff, fe = 0, ff = 0;
-                if (i < hi0) { fs = __ldg(iv_start + i); fe = __ldg(iv_end + i); ff = __ldg(iv_feat + i); }
-                const unsigned live = __ballot_sync(0xffffffffu, fs < qe);   // sorted by start: a prefix
-                const int cnt = __popc(live);
-                for (int l = 0; l < cnt; ++l) {
-                    const int s = __shfl_sync(0xffffffffu, fs, l);
-                    const int e = __shfl_sync(0xffffffffu, fe, l);
-                    const int f = __shfl_sync(0xffffffffu, ff, l);
-                    if (lane == 0 && e > qs) {                 // tabix: start < q_end and end > q_start
-                        int is = s - qs; if (is < 0) is = 0;              // _genomic_features.pyx:32
-                        int ie = e - qs; if (ie > qlen) ie = qlen;        // :33
-                        if (is == ie) ie += 1;                            // :35-36
-                        if (ie > qlen) ie = qlen;                         // numpy slice assignment clamps
-                        const int u = until[f];
-                        if (ie > u) { cov[f] += ie - (is > u ? is : u); until[f] = ie; }
-                        cov[f] |= 0x40000000;                             // "any row" marker for no-threshold mode
-                    }
-                }
-                if (cnt < 32) break;
-            }
-        }
-        __syncwarp();
         OutT* o = out + (long long)q * n_features;
-        for (int f = lane; f < n_features; f += 32) {
-            const int v = cov[f];
-            const int t = __ldg(thr_i + f);
-            // :39-40 with thresholds; genomic_features.py:406-415 (any overlapping row) when thr < 0
-            const int label = t < 0 ? (v != 0) : ((v & 0x3fffffff) > t);
-            o[f] = (OutT)label;
+        zero_row(o, n_features, lane);
+        __syncwarp();   // orders the zero fill before the label stores of other lanes
+        if (!(c >= 0 && c < a.n_chrom && qlen > 0)) continue;
+        const long long lo0 = coff[c], hi0 = coff[c + 1];
+        long long lo, hi;
+        {
+            const long long t0 = toff[c];
+            const long long nb = toff[c + 1] - t0;
+            if (qs < 0) { lo = lo0; hi = lo0 + __ldg(a.tab + t0); }
+            else {
+                const long long b = (long long)(qs >> a.tab_shift);
+                if (b >= nb - 1) { lo = hi = hi0; }     // past the last interval end of the chromosome
+                else { lo = lo0 + __ldg(a.tab + t0 + b); hi = lo0 + __ldg(a.tab + t0 + b + 1); }
+            }
         }
-        __syncwarp();
+        lo = first_reaching(a.iv_cmax, lo, hi, qs, lane);
+        const bool packed = qlen <= kPackedMaxLen;
+        // ---- first 32 candidates
+        int fs = 0x7fffffff, fe = 0, ff = 0;
+        if (lo + lane < hi0) {
+            fs = __ldg(a.iv_start + lo + lane); fe = __ldg(a.iv_end + lo + lane); ff = __ldg(a.iv_feat + lo + lane);
+        }
+        const bool more = __ballot_sync(0xffffffffu, fs < qe) == 0xffffffffu;   // sorted by start: a prefix
+        const bool is_hit = fs < qe && fe > qs;                                 // tabix: start < q_end and end > q_start
+        const unsigned hitmask = __ballot_sync(0xffffffffu, is_hit);
+        if (!more && packed) {
+            if (hitmask == 0) continue;
+            bool unique = false;
+            if (is_hit) unique = __match_any_sync(hitmask, ff) == (1u << lane);
+            const unsigned dup = __ballot_sync(0xffffffffu, is_hit && !unique);
+            if (is_hit && unique) {
+                int is, ie;
+                clip_interval(fs, fe, qs, qlen, is, ie);
+                const int t = __ldg(thr_i + ff);
+                // :39-40 with thresholds; genomic_features.py:406-415 (any overlapping row) when thr < 0
+                if (t < 0 || ie - is > t) o[ff] = (OutT)1;
+            }
+            if (dup) {
+                replay(dup, fs, fe, ff, qs, qlen, true, 0, 0, st, lane);
+                __syncwarp();
+                const bool mine = (dup >> lane) & 1;
+                if (mine) {
+                    const int32_t w = st[ff];
+                    const int t = __ldg(thr_i + ff);
+                    if (t < 0 || ((w >> 15) & 0x7fff) > t) o[ff] = (OutT)1;
+                }
+                __syncwarp();
+                if (mine) st[ff] = 0;
+                __syncwarp();
+            }
+            continue;
+        }
+        // ---- general path: more than 32 candidates and/or a bin of 2^15 bases or more (features in two passes)
+        const int half = words >> 1;
+        const int n_pass = packed ? 1 : 2;
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const int f_lo = packed ? 0 : pass * half;
+            const int f_hi = packed ? n_features : min(n_features, f_lo + half);
+            for (int sweep = 0; sweep < 3; ++sweep) {
+                for (long long base = lo; base < hi0; base += 32) {
+                    const long long i = base + lane;
+                    int gs = 0x7fffffff, ge = 0, gf = 0;
+                    if (i < hi0) { gs = __ldg(a.iv_start + i); ge = __ldg(a.iv_end + i); gf = __ldg(a.iv_feat + i); }
+                    const unsigned live = __ballot_sync(0xffffffffu, gs < qe);
+                    const bool h = gs < qe && ge > qs && gf >= f_lo && gf < f_hi;
+                    if (sweep == 0) {          // union state, in start order
+                        replay(__ballot_sync(0xffffffffu, h), gs, ge, gf, qs, qlen, packed, f_lo, half, st, lane);
+                    } else if (sweep == 1) {   // every lane labels its interval's feature (duplicates agree)
+                        if (h) {
+                            const int32_t w = st[gf - f_lo];
+                            const int cv = packed ? ((w >> 15) & 0x7fff) : (w & 0x3fffffff);
+                            const int t = __ldg(thr_i + gf);
+                            if (t < 0 || cv > t) o[gf] = (OutT)1;
+                        }
+                    } else if (h) {            // clear the touched state
+                        st[gf - f_lo] = 0;
+                        if (!packed) st[half + gf - f_lo] = 0;
+                    }
+                    if (live != 0xffffffffu) break;
+                }
+                __syncwarp();
+            }
+        }
     }
 }
 
@@ -140,9 +297,31 @@ extern "C" int sb_intervals_create(const int32_t* chrom, const int32_t* start, c
             m[(size_t)i] = run;
         }
     }
+    // bucket table over positions (see sb_intervals): shift grows until the table is at most 16 M entries
+    int64_t span = 1;
+    for (int c = 0; c < n_chrom; ++c)
+        if (off[(size_t)c + 1] > off[(size_t)c]) span += std::max<int64_t>(m[(size_t)off[(size_t)c + 1] - 1], 0);
+    int shift = 10;
+    while ((span >> shift) + 2 * n_chrom > (int64_t)(16 << 20)) ++shift;
+    std::vector<int64_t> toff((size_t)n_chrom + 1, 0);
+    std::vector<int32_t> tab;
+    for (int c = 0; c < n_chrom; ++c) {
+        const int64_t b0 = off[(size_t)c], b1 = off[(size_t)c + 1];
+        SB_REQUIRE(b1 - b0 < INT32_MAX, "sb_intervals_create: chromosome %d has too many intervals", c);
+        const int64_t max_end = b1 > b0 ? std::max<int64_t>(m[(size_t)b1 - 1], 0) : 0;
+        const int64_t nb = (max_end >> shift) + 2;
+        int64_t i = b0;
+        for (int64_t b = 0; b < nb; ++b) {
+            const int64_t p = b << shift;
+            while (i < b1 && (int64_t)m[(size_t)i] <= p) ++i;   // running max is non-decreasing
+            tab.push_back((int32_t)(i - b0));
+        }
+        toff[(size_t)c + 1] = (int64_t)tab.size();
+    }
     SB_CHECK_CUDA(cudaSetDevice(device));
     sb_intervals* iv = new sb_intervals();
     memset(iv, 0, sizeof(*iv));
+    iv->tab_shift = shift;
     iv->device = device;
     iv->n_features = n_features;
     iv->n_chrom = n_chrom;
@@ -161,6 +340,10 @@ extern "C" int sb_intervals_create(const int32_t* chrom, const int32_t* start, c
     }
     SB_CHECK_CUDA(cudaMemcpy(iv->chrom_off, off.data(), sizeof(int64_t) * (size_t)(n_chrom + 1),
                              cudaMemcpyHostToDevice));
+    SB_CHECK_CUDA(cudaMalloc(&iv->tab, sizeof(int32_t) * tab.size()));
+    SB_CHECK_CUDA(cudaMalloc(&iv->tab_off, sizeof(int64_t) * (size_t)(n_chrom + 1)));
+    SB_CHECK_CUDA(cudaMemcpy(iv->tab, tab.data(), sizeof(int32_t) * tab.size(), cudaMemcpyHostToDevice));
+    SB_CHECK_CUDA(cudaMemcpy(iv->tab_off, toff.data(), sizeof(int64_t) * (size_t)(n_chrom + 1), cudaMemcpyHostToDevice));
     *out = iv;
     return SB_OK;
 }
@@ -173,6 +356,8 @@ extern "C" int sb_intervals_destroy(sb_intervals* iv) {
     cudaFree(iv->feat);
     cudaFree(iv->cmax);
     cudaFree(iv->chrom_off);
+    cudaFree(iv->tab);
+    cudaFree(iv->tab_off);
     delete iv;
     return SB_OK;
 }
@@ -184,20 +369,29 @@ extern "C" int sb_label_bins(const sb_intervals* iv, const int32_t* chrom, const
     SB_REQUIRE(n >= 0, "sb_label_bins: bad n");
     if (n == 0) return SB_OK;
     SB_REQUIRE(chrom && bin_start && bin_end && thr_i && out, "sb_label_bins: null argument");
-    const size_t smem = (size_t)kWarpsPerBlock * 2 * iv->n_features * sizeof(int32_t);
+    const int meta_in_smem = iv->n_chrom <= 512;
+    const size_t smem = (size_t)kWarpsPerBlock * ((iv->n_features + 1) & ~1) * sizeof(int32_t) +
+                        (meta_in_smem ? 2 * (size_t)(iv->n_chrom + 1) * sizeof(int64_t) : 0);
     SB_REQUIRE(smem <= 200 * 1024, "sb_label_bins: %d features need %zu bytes of shared memory", iv->n_features, smem);
     int64_t blocks = ((int64_t)n + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const int64_t cap = (int64_t)sb_sm_count(iv->device) * 6;
+    // persistent grid: as many blocks as are resident at once (shared memory is the limiter)
+    int64_t per_sm = (int64_t)(200 * 1024 / (smem + 1024));
+    if (per_sm > 16) per_sm = 16;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t cap = (int64_t)sb_sm_count(iv->device) * per_sm;
     if (blocks > cap) blocks = cap;
+    LabelArgs a;
+    a.iv_start = iv->start; a.iv_end = iv->end; a.iv_feat = iv->feat; a.iv_cmax = iv->cmax;
+    a.chrom_off = iv->chrom_off; a.tab = iv->tab; a.tab_off = iv->tab_off; a.tab_shift = iv->tab_shift;
+    a.n_features = iv->n_features; a.n_chrom = iv->n_chrom; a.meta_in_smem = meta_in_smem;
     cudaStream_t s = (cudaStream_t)stream;
 #define SB_LAUNCH_LABEL(T)                                                                                  \
     do {                                                                                                    \
         if (smem > 48 * 1024)                                                                               \
             SB_CHECK_CUDA(cudaFuncSetAttribute(label_bins_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                (int)smem));                                                 \
-        label_bins_kernel<T><<<(int)blocks, kWarpsPerBlock * 32, smem, s>>>(                               \
-            iv->start, iv->end, iv->feat, iv->cmax, iv->chrom_off, iv->n_features, iv->n_chrom, chrom, bin_start,  \
-            bin_end, n, thr_i, (T*)out);                                                                    \
+        label_bins_kernel<T><<<(int)blocks, kWarpsPerBlock * 32, smem, s>>>(a, chrom, bin_start, bin_end, n, thr_i, \
+                                                                            (T*)out);                       \
     } while (0)
     switch (out_dtype) {
         case SB_U8: SB_LAUNCH_LABEL(uint8_t); break;

@@ -236,6 +236,58 @@ def test_labels_vs_oracle(torch, tmp_path, thr):
     assert z.dtype == np.float64 and not z.any()
 
 
+@pytest.mark.parametrize("thr", [0.5, None])
+def test_labels_many_intervals_and_long_bins(torch, tmp_path, thr):
+    """Thousands of intervals per chromosome (several rounds of the 32-way search), a few very long intervals
+    (the running-max search must still find them), an odd feature count, and bins longer than 2^15 bases
+    (two-pass wide state) mixed with short ones in one call."""
+    from selene_b200.targets import GenomicFeatures
+    rng = np.random.default_rng(17)
+    chrom_len = {"chrA": 400000, "chrB": 250000, "chrC": 90000}
+    n_feat = 13
+    feats = ["f%d" % i for i in range(n_feat)]
+    rows = []
+    for c, L in chrom_len.items():
+        for _ in range(L // 40):
+            ln = int(np.clip(rng.lognormal(np.log(150), 1.0), 1, 4000))
+            s = int(rng.integers(0, L - ln))
+            rows.append((c, s, s + ln, feats[rng.integers(0, n_feat)]))
+        for _ in range(6):      # long intervals that reach far past their neighbours
+            s = int(rng.integers(0, L // 2))
+            rows.append((c, s, s + int(rng.integers(L // 8, L // 2)), feats[rng.integers(0, n_feat)]))
+    rows.sort(key=lambda r: (r[0], r[1], r[2]))
+    path = str(tmp_path / "many.bed.gz")
+    H.write_bed(rows, path)
+    GF = GenomicFeatures(path, feats, feature_thresholds=thr)
+    by = H.rows_by_chrom(rows)
+    fid = {f: i for i, f in enumerate(feats)}
+    qc, qs, qe = [], [], []
+    names = list(chrom_len)
+    for i in range(260):
+        c = names[rng.integers(0, 3)]
+        ln = 200 if i % 10 else int(rng.integers(32768, 70000))
+        s = int(rng.integers(0, chrom_len[c] - ln))
+        qc.append(c); qs.append(s); qe.append(s + ln)
+    if thr is None:
+        got = GF.label_bins(qc, qs, qe, out_dtype="int64").cpu().numpy()     # short and long bins in one launch
+    else:
+        # thresholds need one bin length per call (the integer threshold depends on it)
+        got = np.zeros((260, n_feat), dtype=np.int64)
+        short = [i for i in range(260) if qe[i] - qs[i] == 200]
+        got[short] = GF.label_bins([qc[i] for i in short], [qs[i] for i in short], [qe[i] for i in short],
+                                   out_dtype="int64").cpu().numpy()
+        for i in range(260):
+            if i not in short:
+                got[i] = GF.label_bins([qc[i]], [qs[i]], [qe[i]], out_dtype="int64").cpu().numpy()[0]
+    for i in range(260):
+        r = O.query_rows(by, qc[i], qs[i], qe[i])
+        if thr is None:
+            exp = O.feature_data_no_threshold(n_feat, fid, r)
+        else:
+            exp = O.fast_get_feature_data(qs[i], qe[i], GF._feature_thresholds_vec, fid, r)
+        assert np.array_equal(got[i], exp), (qc[i], qs[i], qe[i])
+
+
 def test_labels_reference_goldens(torch, tmp_path):
     """Rows and expected vectors of selene_sdk/targets/tests/test_genomic_features.py:24-42,151-187."""
     from selene_b200.targets import GenomicFeatures
