@@ -187,6 +187,33 @@ __device__ __forceinline__ void sb_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) 
         : "memory");
 }
 
+__device__ __forceinline__ void sb_tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void sb_tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :
+                 : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void sb_tmem_wait_st() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// 1-D bulk copy global -> shared (size multiple of 16 bytes, both addresses 16-byte aligned), completion
+// counted in bytes on `bar`
+__device__ __forceinline__ void sb_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :
+                 : "r"(sb_smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(sb_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void sb_prefetch_l2(const void* g) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<uint64_t>(g)));
+}
+
 // Shared-memory matrix descriptor for a K-major bf16 tile stored as rows of 128 bytes (64 bf16)
 // in the 128-byte-swizzle pattern TMA writes (8-row / 1024-byte atoms): SBO = 1024 B, LBO unused,
 // descriptor version 1 (sm_100), layout type 2 (SWIZZLE_128B). The tile base must be 1024-byte

@@ -4,18 +4,22 @@
 // batch_first quirk, recurs over the rows of a batch independently for every position.
 // A (chain, position) pair is therefore an independent "unit" with `steps` sequential LSTM cell updates.
 //
-// One CTA owns 128 units of one direction for ALL steps; nothing but the streamed recurrent weights and
-// the per-step inputs/outputs touches global memory between steps:
+// One CTA owns 128 units of one direction for ALL steps; between steps only the streamed recurrent weights,
+// the per-step input projection and the layer output touch global memory:
 //   * h_{s-1} of the 128 units lives in shared memory in the K-major 128-byte-swizzled layout tcgen05.mma
 //     reads as its A operand (double buffered: step s reads one copy while its epilogue writes h_s into
 //     the other);
-//   * warp 0 (one lane) streams W_hh through a 3-stage TMA ring in tiles of 128 gate rows (4 gates x 32
-//     hidden units) x 64 k, identical every step (L2-resident, 800 KB per step per CTA);
-//   * warp 1 (one lane) issues the MMAs: per step 10 N-tiles x 5 k-blocks x 4 x (128 x 128 x 16), fp32
-//     accumulators in TMEM (2 x 128 columns so the cell math of tile i overlaps the MMAs of tile i+1);
-//   * warps 2-5 (thread = unit) do the cell update straight from TMEM: gates = acc + xW (precomputed input
-//     projection, fp32), c' = f*c + i*g, h' = o*tanh(c'); c stays in global fp32 (L2), h' goes to the other
-//     smem copy (swizzled by hand) and to the layer output.
+//   * c of the 128 units lives in TENSOR MEMORY next to the accumulators (lane = unit, column = hidden
+//     unit, fp32), read with tcgen05.ld and written back with tcgen05.st by the thread that owns the unit;
+//   * warp 0 (one lane) streams W_hh through a TMA ring in tiles of 64 gate rows x 64 k.  The rows are
+//     permuted on the host so that a tile holds 2 halves x 4 gates x 8 hidden units (sb_lstm_perm_row):
+//     one contiguous TMA box per tile, identical every step (L2-resident);
+//   * warp 1 (one lane) issues the MMAs: per step H/16 N-tiles x H/64 k-blocks x 4 x (128 x 64 x 16), fp32
+//     accumulators in TMEM (2 x 64 columns, so the cell math of tile i overlaps the MMAs of tile i+1);
+//   * warps 2-9 (thread = unit x half tile) do the cell update: gates = acc + xW, where xW is the input
+//     projection (+ bias) written by the projection GEMM as bf16 in the same permuted column order, so the 64
+//     bytes one thread needs per tile are contiguous; every thread fetches its own with a bulk async copy two
+//     tiles ahead (and prefetches the next step's line into L2), so no thread ever waits on a global load.
 #include "sb_common.cuh"
 
 #include <cuda.h>
@@ -23,30 +27,36 @@
 namespace {
 
 constexpr int kUnits = 128;
-constexpr int kNTile = 128;          // 4 gates x 32 hidden units
-constexpr int kUnitsPerTile = 32;
+constexpr int kNTile = 64;           // 2 halves x 4 gates x 8 hidden units
+constexpr int kHidPerTile = 16;
 constexpr int kBStages = 3;
-constexpr int kBStageBytes = kNTile * 64 * 2;   // 16384
-constexpr int kLThreads = 192;
+constexpr int kBStageBytes = kNTile * 64 * 2;   // 8192
+constexpr int kEpiThreads = 256;
+constexpr int kLThreads = 64 + kEpiThreads;
+constexpr int kXwPitch = 80;         // 64 B payload + 16: conflict-free 16-byte reads, thread = row
+constexpr int kXwSlotBytes = kEpiThreads * kXwPitch;
+constexpr int kAccCols = 2 * kNTile; // c state starts at this TMEM column
 
 struct LstmParams {
     long long m_rows;        // rows of the chunk
     long long n_units;       // chains * T
     int H, T, G, I, steps;
     int kblocks;             // H / 64
-    int n_tiles;             // H / 32
-    const float* xw;         // (m_rows*T, 8H) fp32
-    float* cstate;           // (2, n_units, H) fp32
+    int n_tiles;             // H / 16
+    const __nv_bfloat16* xw; // (m_rows*T, 8H) bf16, permuted columns, bias included
     __nv_bfloat16* out;      // (m_rows*T, out_ld)
     int out_ld;
 };
 
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) {
     float r;
     asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// one MUFU instead of ex2 + rcp
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
 __global__ void __launch_bounds__(kLThreads, 1)
 lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid_constant__ CUtensorMap tmap_w1,
@@ -55,14 +65,16 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
     uint8_t* smem = smem_raw + ((1024u - (sb_smem_u32(smem_raw) & 1023u)) & 1023u);
     const int a_bytes = p.kblocks * kUnits * 128;          // one copy of h: kblocks x (128 rows x 128 B)
     uint8_t* hA = smem;                                     // [2][a_bytes]
-    uint8_t* bring = smem + 2 * a_bytes;                    // [kBStages][16 KB]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bring + kBStages * kBStageBytes);
+    uint8_t* bring = smem + 2 * a_bytes;                    // [kBStages][8 KB]
+    uint8_t* xring = bring + kBStages * kBStageBytes;       // [2][256 x 80 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xring + 2 * kXwSlotBytes);
     uint64_t* b_full = bars;                 // [3]
     uint64_t* b_empty = bars + 3;            // [3]
     uint64_t* tfull = bars + 6;              // [2]
     uint64_t* tempty = bars + 8;             // [2]
     uint64_t* h_ready = bars + 10;           // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* xw_full = bars + 12;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
@@ -71,10 +83,15 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
     if (warp == 0 && lane == 0) sb_prefetch_tmap(tmap_w);
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kBStages; ++i) { sb_mbar_init(&b_full[i], 1); sb_mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { sb_mbar_init(&tfull[i], 1); sb_mbar_init(&tempty[i], 128); sb_mbar_init(&h_ready[i], 128); }
+        for (int i = 0; i < 2; ++i) {
+            sb_mbar_init(&tfull[i], 1);
+            sb_mbar_init(&tempty[i], kEpiThreads);
+            sb_mbar_init(&h_ready[i], kEpiThreads);
+            sb_mbar_init(&xw_full[i], kEpiThreads);
+        }
         sb_fence_mbar_init();
     }
-    if (warp == 2) sb_tmem_alloc(tmem_slot, 256);
+    if (warp == 2) sb_tmem_alloc(tmem_slot, 512);
     // h_{-1} = 0
     for (int i = threadIdx.x; i < a_bytes / 16; i += blockDim.x) reinterpret_cast<uint4*>(hA)[i] = make_uint4(0, 0, 0, 0);
     sb_fence_proxy_async();
@@ -91,11 +108,8 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
                 for (int nt = 0; nt < p.n_tiles; ++nt)
                     for (int kb = 0; kb < p.kblocks; ++kb) {
                         sb_mbar_wait(&b_empty[stage], phase ^ 1);
-                        uint8_t* dst = bring + stage * kBStageBytes;
                         sb_mbar_expect_tx(&b_full[stage], kBStageBytes);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)   // gate g, hidden units [32 nt, 32 nt + 32)
-                            sb_tma_load_2d(dst + g * 4096, tmap_w, &b_full[stage], kb * 64, g * p.H + nt * kUnitsPerTile);
+                        sb_tma_load_2d(bring + stage * kBStageBytes, tmap_w, &b_full[stage], kb * 64, nt * kNTile);
                         if (++stage == kBStages) { stage = 0; phase ^= 1; }
                     }
         }
@@ -133,9 +147,11 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
         }
         __syncwarp();
     } else {
-        // ===================== cell update (warps 2..5, thread = unit) =====================
-        const int quad = warp & 3;
+        // ===================== cell update (warps 2..9; thread = (unit, half of the tile)) =====================
+        const int quad = warp & 3;                            // TMEM lane quadrant this warp may touch
+        const int half = (warp - 2) >> 2;
         const int r = quad * 32 + lane;                       // row of the tile = unit
+        const int e = half * kUnits + r;                      // row of the xw ring
         const long long unit = (long long)blockIdx.x * kUnits + r;
         // unit -> (chain, position) -> rows of the chunk
         long long first = 0;
@@ -151,68 +167,92 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
                 len = (int)(l > p.G ? p.G : l);
             }
         }
-        float* cst = p.cstate + ((long long)dir * p.n_units + (unit < p.n_units ? unit : 0)) * p.H;
+        const uint32_t lane_bits = (uint32_t)(quad * 32) << 16;
+        const long long xw_ld = 8LL * p.H;
+        // element offset of this thread's 32 projection values of tile nt at step s: row(s) * xw_ld + col0 + 64 nt
+        const long long col0 = (long long)dir * 4 * p.H + half * 32;
+        auto row_of = [&](int s) { return (first + (long long)p.I * (dir == 0 ? s : len - 1 - s)) * p.T + pos; };
+        auto fetch = [&](int s, int nt, int slot) {
+            // own row of the ring only: the async-proxy write below is ordered after this thread's earlier reads
+            if (s < len) {
+                sb_fence_proxy_async();
+                sb_mbar_expect_tx(&xw_full[slot], 64);
+                sb_bulk_load(xring + slot * kXwSlotBytes + e * kXwPitch, p.xw + row_of(s) * xw_ld + col0 + nt * kNTile, 64,
+                             &xw_full[slot]);
+            } else {
+                sb_mbar_arrive(&xw_full[slot]);
+            }
+        };
+        // prologue: tiles 0 and 1
+        int fs = 0, fnt = 0;   // next tile to fetch
+        for (int i = 0; i < 2; ++i) {
+            if (fs < p.steps) fetch(fs, fnt, i);
+            if (++fnt == p.n_tiles) { fnt = 0; ++fs; }
+        }
         uint32_t gt = 0;
         for (int s = 0; s < p.steps; ++s) {
             const bool live = s < len;
-            const long long row = first + (long long)p.I * (dir == 0 ? s : len - 1 - s);
-            const float* xw = p.xw + ((live ? row : 0) * p.T + pos) * (long long)(8 * p.H) + (long long)dir * 4 * p.H;
-            __nv_bfloat16* orow = p.out + ((live ? row : 0) * p.T + pos) * (long long)p.out_ld + (long long)dir * p.H;
+            const long long grow = live ? row_of(s) : 0;
+            __nv_bfloat16* orow = p.out + grow * (long long)p.out_ld + (long long)dir * p.H + half * 8;
+            // the next step's projection row: pull it towards L2 while this step computes
+            const __nv_bfloat16* nxt = (s + 1 < len) ? p.xw + row_of(s + 1) * xw_ld + col0 : nullptr;
             uint8_t* hnext = hA + ((s + 1) & 1) * a_bytes;
             for (int nt = 0; nt < p.n_tiles; ++nt, ++gt) {
                 const uint32_t as = gt & 1;
-                sb_mbar_wait(&tfull[as], (gt >> 1) & 1);
-                sb_tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * kNTile;
+                const uint32_t par = (gt >> 1) & 1;
+                if (nxt) sb_prefetch_l2(nxt + nt * kNTile);
+                sb_mbar_wait(&xw_full[as], par);
+                uint4 xv[4];   // gates i, f, g, o: 8 bf16 each
+                {
+                    const uint4* xs = reinterpret_cast<const uint4*>(xring + as * kXwSlotBytes + e * kXwPitch);
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t ri[16], rf[16], rg[16], ro[16];
-                    sb_tmem_ld16(taddr + 0 * 32 + half * 16, ri);
-                    sb_tmem_ld16(taddr + 1 * 32 + half * 16, rf);
-                    sb_tmem_ld16(taddr + 2 * 32 + half * 16, rg);
-                    sb_tmem_ld16(taddr + 3 * 32 + half * 16, ro);
-                    sb_tmem_wait_ld();
-                    const int k0 = nt * kUnitsPerTile + half * 16;   // first hidden unit of this group
-                    uint32_t hp[8];
-                    if (live) {
-#pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            const float4 xi = *reinterpret_cast<const float4*>(xw + 0 * p.H + k0 + 4 * j4);
-                            const float4 xf = *reinterpret_cast<const float4*>(xw + 1 * p.H + k0 + 4 * j4);
-                            const float4 xg = *reinterpret_cast<const float4*>(xw + 2 * p.H + k0 + 4 * j4);
-                            const float4 xo = *reinterpret_cast<const float4*>(xw + 3 * p.H + k0 + 4 * j4);
-                            float4 cc = s > 0 ? *reinterpret_cast<const float4*>(cst + k0 + 4 * j4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            const float xiv[4] = {xi.x, xi.y, xi.z, xi.w}, xfv[4] = {xf.x, xf.y, xf.z, xf.w};
-                            const float xgv[4] = {xg.x, xg.y, xg.z, xg.w}, xov[4] = {xo.x, xo.y, xo.z, xo.w};
-                            float cv[4] = {cc.x, cc.y, cc.z, cc.w};
-                            float hv[4];
-#pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) {
-                                const int j = 4 * j4 + jj;
-                                const float ig = sigmoid_fast(__uint_as_float(ri[j]) + xiv[jj]);
-                                const float fg = sigmoid_fast(__uint_as_float(rf[j]) + xfv[jj]);
-                                const float gg = tanh_fast(__uint_as_float(rg[j]) + xgv[jj]);
-                                const float og = sigmoid_fast(__uint_as_float(ro[j]) + xov[jj]);
-                                cv[jj] = fg * cv[jj] + ig * gg;
-                                hv[jj] = og * tanh_fast(cv[jj]);
-                            }
-                            *reinterpret_cast<float4*>(cst + k0 + 4 * j4) = make_float4(cv[0], cv[1], cv[2], cv[3]);
-                            __nv_bfloat162 a = __floats2bfloat162_rn(hv[0], hv[1]), b = __floats2bfloat162_rn(hv[2], hv[3]);
-                            hp[2 * j4] = *reinterpret_cast<uint32_t*>(&a);
-                            hp[2 * j4 + 1] = *reinterpret_cast<uint32_t*>(&b);
-                        }
-                        // layer output (bf16, 32 contiguous bytes)
-                        *reinterpret_cast<uint4*>(orow + k0) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-                        *reinterpret_cast<uint4*>(orow + k0 + 8) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
-                        // h_s into the other A copy: k-block k0/64, 128-byte rows, 16-byte chunks XOR-swizzled by row&7
-                        uint8_t* rowp = hnext + (k0 >> 6) * (kUnits * 128) + r * 128;
-                        const int ch0 = ((k0 & 63) * 2) >> 4;
-                        *reinterpret_cast<uint4*>(rowp + (((ch0) ^ (r & 7)) << 4)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-                        *reinterpret_cast<uint4*>(rowp + (((ch0 + 1) ^ (r & 7)) << 4)) = make_uint4(hp[4], hp[5], hp[6], hp[7]);
-                    }
+                    for (int g = 0; g < 4; ++g) xv[g] = xs[g];
                 }
+                if (fs < p.steps) fetch(fs, fnt, as);   // tile gt + 2 into the slot just read
+                if (++fnt == p.n_tiles) { fnt = 0; ++fs; }
+                sb_mbar_wait(&tfull[as], par);
+                sb_tc_fence_after();
+                const uint32_t taddr = tmem_base + lane_bits + as * kNTile + half * 32;
+                const uint32_t caddr = tmem_base + lane_bits + kAccCols + nt * kHidPerTile + half * 8;
+                uint32_t ri[8], rf[8], rg[8], ro[8], rc[8];
+                sb_tmem_ld8(taddr + 0, ri);
+                sb_tmem_ld8(taddr + 8, rf);
+                sb_tmem_ld8(taddr + 16, rg);
+                sb_tmem_ld8(taddr + 24, ro);
+                if (s > 0) sb_tmem_ld8(caddr, rc);
+                sb_tmem_wait_ld();
                 sb_tc_fence_before();
-                sb_mbar_arrive(&tempty[as]);
+                sb_mbar_arrive(&tempty[as]);    // accumulators are in registers: the MMAs of tile gt + 2 may start
+                const uint32_t xi[4] = {xv[0].x, xv[0].y, xv[0].z, xv[0].w};
+                const uint32_t xf[4] = {xv[1].x, xv[1].y, xv[1].z, xv[1].w};
+                const uint32_t xg[4] = {xv[2].x, xv[2].y, xv[2].z, xv[2].w};
+                const uint32_t xo[4] = {xv[3].x, xv[3].y, xv[3].z, xv[3].w};
+                uint32_t hp[4];
+#pragma unroll
+                for (int j2 = 0; j2 < 4; ++j2) {
+                    float hv[2];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int j = 2 * j2 + q;
+                        const float ai = __uint_as_float(ri[j]) + (q ? bf16_hi(xi[j2]) : bf16_lo(xi[j2]));
+                        const float af = __uint_as_float(rf[j]) + (q ? bf16_hi(xf[j2]) : bf16_lo(xf[j2]));
+                        const float ag = __uint_as_float(rg[j]) + (q ? bf16_hi(xg[j2]) : bf16_lo(xg[j2]));
+                        const float ao = __uint_as_float(ro[j]) + (q ? bf16_hi(xo[j2]) : bf16_lo(xo[j2]));
+                        const float c_old = s > 0 ? __uint_as_float(rc[j]) : 0.f;
+                        const float c_new = fmaf(sigmoid_fast(af), c_old, sigmoid_fast(ai) * tanh_fast(ag));
+                        rc[j] = __float_as_uint(c_new);
+                        hv[q] = sigmoid_fast(ao) * tanh_fast(c_new);
+                    }
+                    __nv_bfloat162 a = __floats2bfloat162_rn(hv[0], hv[1]);
+                    hp[j2] = *reinterpret_cast<uint32_t*>(&a);
+                }
+                sb_tmem_st8(caddr, rc);
+                const uint4 hq = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                const int k0 = nt * kHidPerTile + half * 8;          // first hidden unit of this thread's group
+                if (live) *reinterpret_cast<uint4*>(orow + nt * kHidPerTile) = hq;   // layer output (bf16, 16 bytes)
+                // h_s into the other A copy: k-block k0/64, 128-byte rows, 16-byte chunks XOR-swizzled by row&7
+                *reinterpret_cast<uint4*>(hnext + (k0 >> 6) * (kUnits * 128) + r * 128 + ((((k0 & 63) >> 3) ^ (r & 7)) << 4)) = hq;
+                sb_tmem_wait_st();
             }
             sb_fence_proxy_async();           // this step's h is visible to the tensor core
             sb_mbar_arrive(&h_ready[(s + 1) & 1]);
@@ -220,20 +260,35 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
     }
     sb_tc_fence_before();
     __syncthreads();
-    if (warp == 2) { sb_tc_fence_after(); sb_tmem_dealloc(tmem_base, 256); }
+    if (warp == 2) { sb_tc_fence_after(); sb_tmem_dealloc(tmem_base, 512); }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+size_t lstm_smem_bytes(int H) {
+    return 1024 + 2 * (size_t)(H / 64) * kUnits * 128 + kBStages * kBStageBytes + 2 * kXwSlotBytes + 256;
+}
+
 }  // namespace
 
-int sb_lstm_persistent_supported(int H) { return H % 64 == 0 && H >= 64 && H <= 512; }
+int sb_lstm_persistent_supported(int H) {
+    return H % 64 == 0 && H >= 64 && lstm_smem_bytes(H) <= 227 * 1024 && kAccCols + H <= 512;
+}
 
-// whh[d]: (4H x h_ld) bf16 K-major; xw: (m*T, 8H) fp32; cstate: (2, n_units, H) fp32 scratch; out: (m*T, out_ld) bf16
-int sb_lstm_persistent_launch(const void* whh0, const void* whh1, int h_ld, const float* xw, float* cstate, void* out,
-                              int out_ld, long long m_rows, int H, int T, int G, int I, int device, cudaStream_t stream) {
+// Row order of the permuted recurrent / projection matrices of one direction: tile nt holds, for each half,
+// the four gates of 8 consecutive hidden units.  Returns the torch row (gate*H + hidden) stored at row n.
+int sb_lstm_perm_row(int n, int H) {
+    const int nt = n / kNTile, rem = n % kNTile;
+    const int half = rem / 32, g = (rem % 32) / 8, j = rem % 8;
+    return g * H + nt * kHidPerTile + half * 8 + j;
+}
+
+// whh[d]: (4H x h_ld) bf16 K-major, rows permuted by sb_lstm_perm_row; xw: (m*T, 8H) bf16 projection + bias with
+// columns in the same permuted order per direction; out: (m*T, out_ld) bf16
+int sb_lstm_persistent_launch(const void* whh0, const void* whh1, int h_ld, const void* xw, void* out, int out_ld,
+                              long long m_rows, int H, int T, int G, int I, int device, cudaStream_t stream) {
     SB_REQUIRE(sb_lstm_persistent_supported(H), "sb_lstm_persistent_launch: hidden size %d unsupported", H);
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
@@ -248,7 +303,7 @@ int sb_lstm_persistent_launch(const void* whh0, const void* whh1, int h_ld, cons
     for (int d = 0; d < 2; ++d) {
         cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)(4 * H)};
         cuuint64_t strides[1] = {(cuuint64_t)h_ld * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)kUnitsPerTile};
+        cuuint32_t box[2] = {64, (cuuint32_t)kNTile};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = fn(&tm[d], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w[d]), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -262,10 +317,9 @@ int sb_lstm_persistent_launch(const void* whh0, const void* whh1, int h_ld, cons
     p.H = H; p.T = T; p.G = G; p.I = I;
     long long steps = (m_rows + I - 1) / I;
     p.steps = (int)(steps > G ? G : steps);
-    p.kblocks = H / 64; p.n_tiles = H / kUnitsPerTile;
-    p.xw = xw; p.cstate = cstate; p.out = reinterpret_cast<__nv_bfloat16*>(out); p.out_ld = out_ld;
-    const size_t smem = 1024 + 2 * (size_t)p.kblocks * kUnits * 128 + kBStages * kBStageBytes + 256;
-    SB_REQUIRE(smem <= 227 * 1024, "sb_lstm_persistent_launch: %zu bytes of shared memory needed", smem);
+    p.kblocks = H / 64; p.n_tiles = H / kHidPerTile;
+    p.xw = reinterpret_cast<const __nv_bfloat16*>(xw); p.out = reinterpret_cast<__nv_bfloat16*>(out); p.out_ld = out_ld;
+    const size_t smem = lstm_smem_bytes(H);
     static size_t attr = 0;
     if (smem > attr) {
         SB_CHECK_CUDA(cudaFuncSetAttribute(lstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -51,6 +51,11 @@ struct NetLayer {
     float* whh_f[2];            // dev (hidden x 4*hidden): row = K index
     __nv_bfloat16* whh_b[2];    // dev (4*hidden x hidden_ld) K-major
     float* zero_bias;           // dev, zeros (padded for the tcgen05 tiles)
+    // one-launch recurrence (sb_lstm.cu): projection weights / bias and recurrent matrices with their gate rows
+    // in the tile order of sb_lstm_perm_row; null when the hidden size is unsupported
+    __nv_bfloat16* wb_perm;     // dev (8*hidden x w_ld)
+    float* biasb_perm;          // dev, padded like biasb
+    __nv_bfloat16* whh_perm[2]; // dev (4*hidden x hidden_ld)
     int hh_block_n, hh_n_tiles_n, hidden_ld;
     int fc_prev_c, fc_prev_t;   // first FC after the conv stack: channels / positions it flattens (else 0)
 };
@@ -91,8 +96,9 @@ struct sb_net {
 
 // sb_lstm.cu
 int sb_lstm_persistent_supported(int H);
-int sb_lstm_persistent_launch(const void* whh0, const void* whh1, int h_ld, const float* xw, float* cstate, void* out,
-                              int out_ld, long long m_rows, int H, int T, int G, int I, int device, cudaStream_t stream);
+int sb_lstm_persistent_launch(const void* whh0, const void* whh1, int h_ld, const void* xw, void* out, int out_ld,
+                              long long m_rows, int H, int T, int G, int I, int device, cudaStream_t stream);
+int sb_lstm_perm_row(int n, int H);
 
 // sb_conv1.cu
 size_t sb_conv1_pack_weights(const float* w, int cout, int taps, const uint8_t perm[4], uint16_t* out,
@@ -636,6 +642,31 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
                     }
                 rc = upload(&N.whh_f[d], wf); if (rc) return rc;
                 rc = upload(reinterpret_cast<uint16_t**>(&N.whh_b[d]), wb); if (rc) return rc;
+                if (sb_lstm_persistent_supported(H)) {
+                    std::vector<uint16_t> wp((size_t)4 * H * N.hidden_ld, 0);
+                    for (int n = 0; n < 4 * H; ++n) {
+                        const int o = sb_lstm_perm_row(n, H);
+                        for (int k2 = 0; k2 < H; ++k2)
+                            wp[(size_t)n * N.hidden_ld + k2] = f32_to_bf16_bits(whh[(size_t)o * H + k2]);
+                    }
+                    rc = upload(reinterpret_cast<uint16_t**>(&N.whh_perm[d]), wp); if (rc) return rc;
+                }
+            }
+            if (sb_lstm_persistent_supported(H) && li > 0) {
+                // input projection with the same row order per direction (lstm_w / lstm_b: 8H rows, bias = b_ih + b_hh)
+                const int a_ld_ch = round_up(S.cin, 8);
+                std::vector<uint16_t> wp((size_t)8 * H * N.w_ld, 0);
+                std::vector<float> bp((size_t)N.n_tiles_n * N.block_n, 0.f);
+                for (int d = 0; d < 2; ++d)
+                    for (int n = 0; n < 4 * H; ++n) {
+                        const int o = d * 4 * H + sb_lstm_perm_row(n, H);
+                        bp[(size_t)d * 4 * H + n] = Bsrc[o];
+                        for (int cc = 0; cc < S.cin; ++cc)
+                            wp[((size_t)d * 4 * H + n) * N.w_ld + cc] = f32_to_bf16_bits(w_at(o, 0, cc));
+                    }
+                (void)a_ld_ch;
+                rc = upload(reinterpret_cast<uint16_t**>(&N.wb_perm), wp); if (rc) return rc;
+                rc = upload(&N.biasb_perm, bp); if (rc) return rc;
             }
         }
         net->layers.push_back(N);
@@ -667,6 +698,7 @@ extern "C" int sb_net_destroy(sb_net* net) {
     for (auto& N : net->layers) {
         cudaFree(N.wf); cudaFree(N.biasf); cudaFree(N.wb); cudaFree(N.wb_tap); cudaFree(N.biasb); cudaFree(N.lut); cudaFree(N.w1_packed); cudaFree(N.bias1_padded); cudaFree(N.w0_b); cudaFree(N.w0_bias);
         cudaFree(N.whh_f[0]); cudaFree(N.whh_f[1]); cudaFree(N.whh_b[0]); cudaFree(N.whh_b[1]); cudaFree(N.zero_bias);
+        cudaFree(N.wb_perm); cudaFree(N.biasb_perm); cudaFree(N.whh_perm[0]); cudaFree(N.whh_perm[1]);
     }
     delete net;
     return SB_OK;
@@ -821,6 +853,23 @@ int run_lstm_body(sb_net* net, const NetLayer& N, const void* act_in, void* act_
     const long long blk = (long long)G * I;
     const long long chains = ((m + blk - 1) / blk) * I;
     const long long U = chains * T;
+    {
+        // One persistent kernel for all steps (sb_lstm.cu); SB_LSTM_STEPWISE=1 selects the per-step launches below.
+        const char* stepwise = getenv("SB_LSTM_STEPWISE");
+        if (bf && N.wb_perm && !(stepwise && stepwise[0] == '1')) {
+            // projection (+ bias) as bf16, gate columns in the recurrent kernel's tile order
+            SbTcLayer P;
+            memset(&P, 0, sizeof(P));
+            P.a = act_in; P.rows_a = rows; P.a_ld = N.a_ld; P.k_full = N.k_full;
+            P.w = N.wb_perm; P.n_rows_w = 8 * H; P.w_ld = N.w_ld;
+            P.bias = N.biasb_perm; P.block_n = N.block_n; P.n_tiles_n = N.n_tiles_n;
+            P.t_in = 1; P.t_conv = 1; P.pool = 1; P.relu = 0; P.out_f32 = 0; P.out = xw; P.out_ld = 8 * H;
+            int rc = sb_tc_launch(P, dev, stream);
+            if (rc) return rc;
+            return sb_lstm_persistent_launch(N.whh_perm[0], N.whh_perm[1], N.hidden_ld, xw, act_out, N.out_ld_b, m, H, T, G,
+                                             I, dev, stream);
+        }
+    }
     // ---- input projection for both directions: xw[row*T + p][dir*4H + gate*H + j]
     if (bf) {
         SbTcLayer P;
@@ -853,15 +902,6 @@ int run_lstm_body(sb_net* net, const NetLayer& N, const void* act_in, void* act_
                                                                                      (long long)(2 * h_bytes / 4));
     SB_COUNT_LAUNCH();
     SB_CHECK_LAUNCH();
-    {
-        // One persistent kernel for all steps (sb_lstm.cu).  Opt-in: measured on B200 (r01) it is 2.4-2.9x SLOWER
-        // than the per-step launches below replayed from a CUDA graph — each CTA's 128 cell-update threads wait
-        // on the per-step input-projection reads and only 38-56 CTAs exist per chunk.
-        const char* persistent = getenv("SB_LSTM_PERSISTENT");
-        if (bf && sb_lstm_persistent_supported(H) && persistent && persistent[0] == '1')
-            return sb_lstm_persistent_launch(N.whh_b[0], N.whh_b[1], N.hidden_ld, xw, cst[0], act_out, N.out_ld_b, m, H, T,
-                                             G, I, dev, stream);
-    }
     long long steps = (m + I - 1) / I;
     if (steps > G) steps = G;
     const int ld4 = round_up(4 * H, 4);

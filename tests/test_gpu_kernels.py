@@ -488,21 +488,27 @@ def test_danq_batch_axis_recurrence_vs_torch(torch, precision, tol):
         assert np.abs(got[0::2] - exp_even).max() <= tol and np.abs(got[1::2] - exp_odd).max() <= tol
 
 
-def test_danq_persistent_recurrent_kernel(torch, monkeypatch):
-    """The opt-in one-launch recurrence (sb_lstm.cu, SB_LSTM_PERSISTENT=1) against torch, ragged groups included."""
+@pytest.mark.parametrize("stepwise", ["0", "1"])
+def test_danq_recurrence_paths(torch, monkeypatch, stepwise):
+    """bf16 recurrence both ways — the one-launch persistent kernel (sb_lstm.cu, default) and the per-step
+    launches (SB_LSTM_STEPWISE=1) — against torch, ragged groups and interleaved ref/alt chains included."""
     import sb_models as M
     from selene_b200.nets import B200Net, layers_from_module
-    monkeypatch.setenv("SB_LSTM_PERSISTENT", "1")
+    monkeypatch.setenv("SB_LSTM_STEPWISE", stepwise)
     torch.manual_seed(10)
     model = M.DanQ(1000, 919).eval()
-    codes = _rand_codes(7, 1000, 32)
+    codes = _rand_codes(11, 1000, 32)
     x = torch.tensor(_onehot(codes)).transpose(1, 2)
     net = B200Net(layers_from_module(model), 1000)
     with torch.no_grad():
-        split = np.concatenate([model(x[:3]).numpy(), model(x[3:6]).numpy(), model(x[6:]).numpy()])
-    net.set_recurrence(3, 1)
+        split = np.concatenate([model(x[:4]).numpy(), model(x[4:8]).numpy(), model(x[8:]).numpy()])
+        exp_even, exp_odd = model(x[0:10:2]).numpy(), model(x[1:10:2]).numpy()
+    net.set_recurrence(4, 1)
     got = net.forward_codes(torch.from_numpy(codes).cuda(), precision="bf16").cpu().numpy()
     assert np.abs(got - split).max() <= 2e-2, np.abs(got - split).max()
+    net.set_recurrence(5, 2)
+    got = net.forward_codes(torch.from_numpy(codes[:10]).cuda(), precision="bf16").cpu().numpy()
+    assert np.abs(got[0::2] - exp_even).max() <= 2e-2 and np.abs(got[1::2] - exp_odd).max() <= 2e-2
 
 
 # ------------------------------------------------------------------------------------------------
