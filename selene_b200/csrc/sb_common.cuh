@@ -210,6 +210,15 @@ __device__ __forceinline__ void sb_bulk_load(void* smem_dst, const void* gsrc, u
                  : "r"(sb_smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(sb_smem_u32(bar))
                  : "memory");
 }
+// per-thread 16-byte asynchronous copy global -> shared (Ampere-style cp.async; completion by commit/wait groups)
+__device__ __forceinline__ void sb_cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb_smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(gsrc))
+                 : "memory");
+}
+__device__ __forceinline__ void sb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void sb_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void sb_prefetch_l2(const void* g) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<uint64_t>(g)));
 }

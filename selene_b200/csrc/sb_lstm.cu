@@ -15,11 +15,11 @@
 //     permuted on the host so that a tile holds 2 halves x 4 gates x 8 hidden units (sb_lstm_perm_row):
 //     one contiguous TMA box per tile, identical every step (L2-resident);
 //   * warp 1 (one lane) issues the MMAs: per step H/16 N-tiles x H/64 k-blocks x 4 x (128 x 64 x 16), fp32
-//     accumulators in TMEM (2 x 64 columns, so the cell math of tile i overlaps the MMAs of tile i+1);
+//     accumulators in TMEM (3 x 64 columns, so the cell math of a tile overlaps the MMAs of the next two);
 //   * warps 2-9 (thread = unit x half tile) do the cell update: gates = acc + xW, where xW is the input
 //     projection (+ bias) written by the projection GEMM as bf16 in the same permuted column order, so the 64
-//     bytes one thread needs per tile are contiguous; every thread fetches its own with a bulk async copy two
-//     tiles ahead (and prefetches the next step's line into L2), so no thread ever waits on a global load.
+//     bytes one thread needs per tile are contiguous; every thread loads its own one tile ahead into
+//     registers (and prefetches the next step's line into L2 a whole step ahead).
 #include "sb_common.cuh"
 
 #include <cuda.h>
@@ -29,13 +29,12 @@ namespace {
 constexpr int kUnits = 128;
 constexpr int kNTile = 64;           // 2 halves x 4 gates x 8 hidden units
 constexpr int kHidPerTile = 16;
-constexpr int kBStages = 3;
+constexpr int kBStages = 8;          // 64 KB of W_hh in flight: the ring must cover the L2 latency x bandwidth product
 constexpr int kBStageBytes = kNTile * 64 * 2;   // 8192
 constexpr int kEpiThreads = 256;
 constexpr int kLThreads = 64 + kEpiThreads;
-constexpr int kXwPitch = 80;         // 64 B payload + 16: conflict-free 16-byte reads, thread = row
-constexpr int kXwSlotBytes = kEpiThreads * kXwPitch;
-constexpr int kAccCols = 2 * kNTile; // c state starts at this TMEM column
+constexpr int kAccStages = 3;        // accumulator stages: tiles are short, the handshake latency needs depth
+constexpr int kAccCols = kAccStages * kNTile; // c state starts at this TMEM column
 
 struct LstmParams {
     long long m_rows;        // rows of the chunk
@@ -66,15 +65,13 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
     const int a_bytes = p.kblocks * kUnits * 128;          // one copy of h: kblocks x (128 rows x 128 B)
     uint8_t* hA = smem;                                     // [2][a_bytes]
     uint8_t* bring = smem + 2 * a_bytes;                    // [kBStages][8 KB]
-    uint8_t* xring = bring + kBStages * kBStageBytes;       // [2][256 x 80 B]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xring + 2 * kXwSlotBytes);
-    uint64_t* b_full = bars;                 // [3]
-    uint64_t* b_empty = bars + 3;            // [3]
-    uint64_t* tfull = bars + 6;              // [2]
-    uint64_t* tempty = bars + 8;             // [2]
-    uint64_t* h_ready = bars + 10;           // [2]
-    uint64_t* xw_full = bars + 12;           // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bring + kBStages * kBStageBytes);
+    uint64_t* b_full = bars;                    // [kBStages]
+    uint64_t* b_empty = bars + kBStages;        // [kBStages]
+    uint64_t* tfull = bars + 2 * kBStages;      // [kAccStages]
+    uint64_t* tempty = tfull + kAccStages;      // [kAccStages]
+    uint64_t* h_ready = tempty + kAccStages;    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_ready + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
@@ -83,12 +80,8 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
     if (warp == 0 && lane == 0) sb_prefetch_tmap(tmap_w);
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kBStages; ++i) { sb_mbar_init(&b_full[i], 1); sb_mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) {
-            sb_mbar_init(&tfull[i], 1);
-            sb_mbar_init(&tempty[i], kEpiThreads);
-            sb_mbar_init(&h_ready[i], kEpiThreads);
-            sb_mbar_init(&xw_full[i], kEpiThreads);
-        }
+        for (int i = 0; i < kAccStages; ++i) { sb_mbar_init(&tfull[i], 1); sb_mbar_init(&tempty[i], kEpiThreads); }
+        for (int i = 0; i < 2; ++i) sb_mbar_init(&h_ready[i], kEpiThreads);
         sb_fence_mbar_init();
     }
     if (warp == 2) sb_tmem_alloc(tmem_slot, 512);
@@ -118,16 +111,15 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = sb_umma_idesc_bf16(kUnits, kNTile);
-            uint32_t stage = 0, phase = 0, gt = 0;
+            uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
             for (int s = 0; s < p.steps; ++s) {
                 if (s > 0) {   // h_{s-1} has been written by the epilogue of step s-1
                     sb_mbar_wait(&h_ready[s & 1], ((s - 1) >> 1) & 1);
                     sb_tc_fence_after();
                 }
                 const uint32_t a_addr = sb_smem_u32(hA + (s & 1) * a_bytes);
-                for (int nt = 0; nt < p.n_tiles; ++nt, ++gt) {
-                    const uint32_t as = gt & 1;
-                    sb_mbar_wait(&tempty[as], ((gt >> 1) & 1) ^ 1);
+                for (int nt = 0; nt < p.n_tiles; ++nt) {
+                    sb_mbar_wait(&tempty[as], aphase ^ 1);
                     sb_tc_fence_after();
                     const uint32_t tmem_d = tmem_base + as * kNTile;
                     for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -142,6 +134,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
                         if (++stage == kBStages) { stage = 0; phase ^= 1; }
                     }
                     sb_umma_commit(&tfull[as]);
+                    if (++as == kAccStages) { as = 0; aphase ^= 1; }
                 }
             }
         }
@@ -151,7 +144,6 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
         const int quad = warp & 3;                            // TMEM lane quadrant this warp may touch
         const int half = (warp - 2) >> 2;
         const int r = quad * 32 + lane;                       // row of the tile = unit
-        const int e = half * kUnits + r;                      // row of the xw ring
         const long long unit = (long long)blockIdx.x * kUnits + r;
         // unit -> (chain, position) -> rows of the chunk
         long long first = 0;
@@ -172,24 +164,20 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
         // element offset of this thread's 32 projection values of tile nt at step s: row(s) * xw_ld + col0 + 64 nt
         const long long col0 = (long long)dir * 4 * p.H + half * 32;
         auto row_of = [&](int s) { return (first + (long long)p.I * (dir == 0 ? s : len - 1 - s)) * p.T + pos; };
-        auto fetch = [&](int s, int nt, int slot) {
-            // own row of the ring only: the async-proxy write below is ordered after this thread's earlier reads
+        // every thread loads its OWN 64 bytes of the projection one tile ahead, straight into registers (the line
+        // was pulled into L2 during the previous step)
+        auto fetch = [&](int s, int nt, uint4 (&x)[4]) {
             if (s < len) {
-                sb_fence_proxy_async();
-                sb_mbar_expect_tx(&xw_full[slot], 64);
-                sb_bulk_load(xring + slot * kXwSlotBytes + e * kXwPitch, p.xw + row_of(s) * xw_ld + col0 + nt * kNTile, 64,
-                             &xw_full[slot]);
-            } else {
-                sb_mbar_arrive(&xw_full[slot]);
+                const uint4* src = reinterpret_cast<const uint4*>(p.xw + row_of(s) * xw_ld + col0 + nt * kNTile);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) x[g] = __ldg(src + g);
             }
         };
-        // prologue: tiles 0 and 1
+        uint4 xn[4] = {};
         int fs = 0, fnt = 0;   // next tile to fetch
-        for (int i = 0; i < 2; ++i) {
-            if (fs < p.steps) fetch(fs, fnt, i);
-            if (++fnt == p.n_tiles) { fnt = 0; ++fs; }
-        }
-        uint32_t gt = 0;
+        fetch(0, 0, xn);
+        if (++fnt == p.n_tiles) { fnt = 0; ++fs; }
+        uint32_t as = 0, aphase = 0;
         for (int s = 0; s < p.steps; ++s) {
             const bool live = s < len;
             const long long grow = live ? row_of(s) : 0;
@@ -197,20 +185,14 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
             // the next step's projection row: pull it towards L2 while this step computes
             const __nv_bfloat16* nxt = (s + 1 < len) ? p.xw + row_of(s + 1) * xw_ld + col0 : nullptr;
             uint8_t* hnext = hA + ((s + 1) & 1) * a_bytes;
-            for (int nt = 0; nt < p.n_tiles; ++nt, ++gt) {
-                const uint32_t as = gt & 1;
-                const uint32_t par = (gt >> 1) & 1;
+            for (int nt = 0; nt < p.n_tiles; ++nt) {
                 if (nxt) sb_prefetch_l2(nxt + nt * kNTile);
-                sb_mbar_wait(&xw_full[as], par);
                 uint4 xv[4];   // gates i, f, g, o: 8 bf16 each
-                {
-                    const uint4* xs = reinterpret_cast<const uint4*>(xring + as * kXwSlotBytes + e * kXwPitch);
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) xv[g] = xs[g];
-                }
-                if (fs < p.steps) fetch(fs, fnt, as);   // tile gt + 2 into the slot just read
+                for (int g = 0; g < 4; ++g) xv[g] = xn[g];
+                if (fs < p.steps) fetch(fs, fnt, xn);   // tile gt + 1
                 if (++fnt == p.n_tiles) { fnt = 0; ++fs; }
-                sb_mbar_wait(&tfull[as], par);
+                sb_mbar_wait(&tfull[as], aphase);
                 sb_tc_fence_after();
                 const uint32_t taddr = tmem_base + lane_bits + as * kNTile + half * 32;
                 const uint32_t caddr = tmem_base + lane_bits + kAccCols + nt * kHidPerTile + half * 8;
@@ -222,7 +204,8 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
                 if (s > 0) sb_tmem_ld8(caddr, rc);
                 sb_tmem_wait_ld();
                 sb_tc_fence_before();
-                sb_mbar_arrive(&tempty[as]);    // accumulators are in registers: the MMAs of tile gt + 2 may start
+                sb_mbar_arrive(&tempty[as]);    // accumulators are in registers: this stage may be overwritten
+                if (++as == kAccStages) { as = 0; aphase ^= 1; }
                 const uint32_t xi[4] = {xv[0].x, xv[0].y, xv[0].z, xv[0].w};
                 const uint32_t xf[4] = {xv[1].x, xv[1].y, xv[1].z, xv[1].w};
                 const uint32_t xg[4] = {xv[2].x, xv[2].y, xv[2].z, xv[2].w};
@@ -268,7 +251,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 size_t lstm_smem_bytes(int H) {
-    return 1024 + 2 * (size_t)(H / 64) * kUnits * 128 + kBStages * kBStageBytes + 2 * kXwSlotBytes + 256;
+    return 1024 + 2 * (size_t)(H / 64) * kUnits * 128 + kBStages * kBStageBytes + 256;
 }
 
 }  // namespace
