@@ -756,11 +756,26 @@ int chunk_rows(int precision) { return precision == SB_PREC_BF16 ? 8192 : 256; }
 // bytes of the two ping-pong activation buffers, the fp32 "full" buffer and the logits buffer
 struct WsPlan { size_t act, full, logits, lstm, total; long long n_units; };
 
+// the one-launch recurrence (sb_lstm.cu) runs this layer at this precision
+bool lstm_persistent(const NetLayer& N, int precision) {
+    const char* stepwise = getenv("SB_LSTM_STEPWISE");
+    return precision == SB_PREC_BF16 && N.wb_perm && !(stepwise && stepwise[0] == '1');
+}
+
 long long chunk_for(const sb_net* net, int precision, bool generic) {
     long long c = generic ? 256 : chunk_rows(precision);
     if (net->has_lstm) {  // chunks must hold whole recurrence blocks
         const long long blk = (long long)net->rec_group * net->rec_interleave;
-        if (c > 2048) c = 2048;
+        long long cap = 2048;
+        for (const NetLayer& N : net->layers)
+            if (N.type == SB_LAYER_BILSTM && lstm_persistent(N, precision) && !generic) {
+                // the persistent kernel's time does not depend on its grid size while every CTA (128 units of one
+                // direction) has its own SM: take as many rows per launch as one wave holds
+                const long long units = 128ll * (sb_sm_count(net->device) / 2);
+                const long long chains = units / N.t_in;
+                cap = std::max<long long>(cap, chains * net->rec_group);
+            }
+        if (c > cap) c = cap;
         c = c / blk * blk;
         if (c < blk) c = blk;
     }
@@ -801,7 +816,7 @@ WsPlan plan_ws(const sb_net* net, long long n, int precision, bool generic) {
         const long long blk = (long long)net->rec_group * net->rec_interleave;
         const long long chains = ((ch + blk - 1) / blk) * net->rec_interleave;
         n_units = chains * N.t_in;
-        const size_t xw = (size_t)ch * N.t_in * 8 * N.hidden * 4;
+        const size_t xw = (size_t)ch * N.t_in * 8 * N.hidden * (lstm_persistent(N, precision) ? 2 : 4);
         if (xw > full) full = xw;
         // gates (2 x units x 4H fp32) + h (2 x units x H_ld, 4 B each) + c (2 x units x H fp32)
         lstm = (size_t)n_units * (2 * 4 * N.hidden * 4 + 2 * N.hidden_ld * 4 + 2 * N.hidden * 4) + 4096;
@@ -855,8 +870,7 @@ int run_lstm_body(sb_net* net, const NetLayer& N, const void* act_in, void* act_
     const long long U = chains * T;
     {
         // One persistent kernel for all steps (sb_lstm.cu); SB_LSTM_STEPWISE=1 selects the per-step launches below.
-        const char* stepwise = getenv("SB_LSTM_STEPWISE");
-        if (bf && N.wb_perm && !(stepwise && stepwise[0] == '1')) {
+        if (lstm_persistent(N, precision)) {
             // projection (+ bias) as bf16, gate columns in the recurrent kernel's tile order
             SbTcLayer P;
             memset(&P, 0, sizeof(P));
