@@ -156,11 +156,16 @@ def main():
          tflops=3000 / dt_ * azd.net.flops_per_seq / 1e12)
 
     # ---------------------------------------------------------------- config 5: Seqweaver / HeartENN sweep
-    for name, model in ((("Seqweaver(217)", M.Seqweaver(217)), ("HeartENN(1000, 90)", M.HeartENN(1000, 90)))
+    for name, model in ((("Seqweaver(217)", M.Seqweaver(217)), ("HeartENN(1000, 90)", M.HeartENN(1000, 90)),
+                         ("DeeperDeepSEA(1000, 919) [SURVEY 8 f4]", M.DeeperDeepSEA(1000, 919)),
+                         ("NonStrandSpecific(DeepSEA(1000, 919), mean) [SURVEY 8 f3]",
+                          M.NonStrandSpecific(M.DeepSEA(1000, 919), "mean")))
                         if want('sweep') else ()):
         torch.manual_seed(0)
         model.eval()
-        net = B200Net(layers_from_module(model), 1000)
+        from selene_b200.nets import unwrap_non_strand_specific
+        strand = unwrap_non_strand_specific(model)[1]
+        net = B200Net(layers_from_module(model), 1000, strand_mode=strand)
         for batch in (64, 256, 1024, 4096):
             codes_b = torch.from_numpy(rng.integers(0, 4, (batch, 1000)).astype(np.uint8)).cuda()
             src = torch.arange(batch, dtype=torch.int32, device="cuda").repeat_interleave(2)
@@ -169,7 +174,7 @@ def main():
             fn = lambda: net.forward_score(codes_b, src, p_, sc, 2 * batch, _lib.SB_PAIR_INTERLEAVED, precision="bf16",
                                            want=("abs_diffs", "logits"))
             t = timed(fn, warmup=2, iters=5)
-            tf = 2 * batch * net.flops_per_seq / t / 1e12
+            tf = 2 * batch * net.flops_per_seq * (2 if strand else 1) / t / 1e12   # both strands are computed
             emit(config="5: %s VEP-style scoring" % name, variants_per_batch=batch, ms=t * 1e3,
                  predictions_per_s=2 * batch / t, tflops=tf, tensor_frac_of_sustained=tf / float(peaks["bf16_tflops_sustained"]))
 

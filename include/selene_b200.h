@@ -200,6 +200,13 @@ double sb_net_flops_per_seq(const sb_net* net);
  * reference predicts the ref batch and the alt batch separately), else 1.  Default: group 64, interleave 1. */
 int sb_net_set_recurrence(sb_net* net, int group, int interleave);
 
+/* NonStrandSpecific wrapper (utils/non_strand_specific_module.py:62-85; every manuscript config uses
+ * `non_strand_specific: mean`): mode 1 (mean) / 2 (max) makes every forward entry point also run the rows with the
+ * position axis and the channel axis reversed (channel c -> 3-c, which is the reverse complement for the ACGT
+ * order) and combine the two sigmoid outputs before any score is computed; 0 (default) turns it off.  Set it
+ * before asking for sb_net_workspace_bytes.  Doubles the FLOPs per prediction. */
+int sb_net_set_strand_mode(sb_net* net, int mode);
+
 /* Per-layer device timing for roofline reports: when enabled, every layer launch is bracketed by
  * CUDA events on the launching stream; sb_net_layer_time sums them (synchronising on the events)
  * since the last sb_net_set_timing call. */

@@ -53,6 +53,7 @@ SIGNATURES = {
     "sb_net_n_outputs": (_I, [_P]),
     "sb_net_flops_per_seq": (C.c_double, [_P]),
     "sb_net_set_recurrence": (_I, [_P, _I, _I]),
+    "sb_net_set_strand_mode": (_I, [_P, _I]),
     "sb_net_set_timing": (_I, [_P, _I]),
     "sb_net_n_layers": (_I, [_P]),
     "sb_net_layer_flops_per_seq": (C.c_double, [_P, _I]),

@@ -84,6 +84,7 @@ struct sb_net {
     double flops_per_seq;
     bool force_per_tap;
     int rec_group, rec_interleave;   // row grouping of BiLSTM recurrences (sb_net_set_recurrence)
+    int strand_mode;                 // 0: plain; 1 / 2: NonStrandSpecific mean / max (sb_net_set_strand_mode)
     bool has_lstm;
     std::vector<NetLayer> layers;
     std::vector<LstmGraph> lstm_graphs;   // captured BiLSTM layers (run_lstm)
@@ -308,6 +309,48 @@ __global__ void __launch_bounds__(256) score_kernel(const float* __restrict__ x,
 }
 
 // ---------------------------------------------------------------------------------------------
+// NonStrandSpecific (utils/non_strand_specific_module.py:62-85): the wrapped model also sees the input with
+// its channel axis and its position axis reversed; the two outputs are averaged or maxed.
+// ---------------------------------------------------------------------------------------------
+// rows [r0, r0+m) of a codes source, substitution applied, positions reversed, channel c -> 3-c.  `map[b]` is the
+// canonical code whose channel is 3 - channel(b); the unknown code (0.25 in every channel) maps to itself.
+struct RcMap { uint8_t m[5]; };
+__global__ void __launch_bounds__(256) rc_codes_kernel(const uint8_t* __restrict__ codes, const int32_t* __restrict__ src,
+                                                       const int32_t* __restrict__ sub_pos,
+                                                       const uint8_t* __restrict__ sub_code, long long r0, long long m,
+                                                       int L, RcMap map, uint8_t* __restrict__ out) {
+    const long long total = m * L;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long r = i / L;
+        const int p = (int)(i - r * L);
+        const long long row = r0 + r;
+        const int q = L - 1 - p;
+        uint8_t c = codes[(src ? (long long)src[row] : row) * L + q];
+        if (sub_pos && sub_pos[row] == q) c = sub_code ? sub_code[row] : 4;
+        out[i] = map.m[c > 4 ? 4 : c];
+    }
+}
+__global__ void __launch_bounds__(256) rc_onehot_kernel(const float* __restrict__ x, long long r0, long long m, int L,
+                                                        float* __restrict__ out) {
+    const long long total = m * L * 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int ch = (int)(i & 3);
+        const long long rp = i >> 2;
+        const long long r = rp / L;
+        const int p = (int)(rp - r * L);
+        out[i] = x[((r0 + r) * L + (L - 1 - p)) * 4 + (3 - ch)];
+    }
+}
+__global__ void __launch_bounds__(256) strand_combine_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                             long long n, int mode, float* __restrict__ out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = mode == 1 ? (a[i] + b[i]) / 2.f : fmaxf(a[i], b[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
 // BiLSTM cell update for one step of every chain (torch gate order i, f, g, o)
 //   unit = (chain, position); chain = (block, c); row(chain, s) = block*G*I + c + I*s
 // ---------------------------------------------------------------------------------------------
@@ -460,6 +503,7 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
     net->force_per_tap = env && env[0] == '1';
     net->timing = false;
     net->rec_group = 64;
+    net->strand_mode = 0;
     net->rec_interleave = 1;
     net->has_lstm = false;
 
@@ -713,6 +757,13 @@ extern "C" int sb_net_set_recurrence(sb_net* net, int group, int interleave) {
     return SB_OK;
 }
 
+extern "C" int sb_net_set_strand_mode(sb_net* net, int mode) {
+    SB_REQUIRE(net, "sb_net_set_strand_mode: null handle");
+    SB_REQUIRE(mode >= 0 && mode <= 2, "sb_net_set_strand_mode: mode %d is not 0 (off), 1 (mean) or 2 (max)", mode);
+    net->strand_mode = mode;
+    return SB_OK;
+}
+
 extern "C" int sb_net_set_timing(sb_net* net, int enable) {
     SB_REQUIRE(net, "sb_net_set_timing: null handle");
     net->timing = enable != 0;
@@ -754,7 +805,7 @@ namespace {
 int chunk_rows(int precision) { return precision == SB_PREC_BF16 ? 8192 : 256; }
 
 // bytes of the two ping-pong activation buffers, the fp32 "full" buffer and the logits buffer
-struct WsPlan { size_t act, full, logits, lstm, total; long long n_units; };
+struct WsPlan { size_t act, full, logits, lstm, strand, total; long long n_units; };
 
 // the one-launch recurrence (sb_lstm.cu) runs this layer at this precision
 bool lstm_persistent(const NetLayer& N, int precision) {
@@ -828,7 +879,9 @@ WsPlan plan_ws(const sb_net* net, long long n, int precision, bool generic) {
     p.act = al(act);
     p.full = al(full);
     p.logits = al((size_t)ch * round_up(net->n_out, 4) * 4);
-    p.total = 2 * p.act + p.full + p.logits + p.lstm + 4096;
+    // NonStrandSpecific: probabilities of both strands + the reverse-complemented rows of the chunk
+    p.strand = net->strand_mode ? al(2 * (size_t)ch * net->n_out * 4) + al((size_t)ch * net->L * (generic ? 16 : 1)) : 0;
+    p.total = 2 * p.act + p.full + p.logits + p.lstm + p.strand + 4096;
     return p;
 }
 
@@ -1208,6 +1261,71 @@ static int forward_impl(sb_net* net, const RowSource& in, int64_t n, int precisi
         const long long m = (n - r0) < chunk ? (n - r0) : chunk;
         float* lg = nullptr;
         int ldl = 0;
+        if (net->strand_mode) {
+            // both strands through the network, combined probabilities, then the handlers' math on those
+            uint8_t* sbase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023) +
+                             2 * plan.act + plan.full + plan.logits + plan.lstm;
+            const long long cr = n < chunk ? n : chunk;
+            float* p_fwd = reinterpret_cast<float*>(sbase);
+            float* p_rev = p_fwd + cr * F;
+            uint8_t* rc_rows = sbase + ((2 * (size_t)cr * F * 4 + 1023) / 1024 * 1024 + 1024);
+            RowSource rin = {nullptr, nullptr, nullptr, nullptr, nullptr};
+            if (generic) {
+                rc_onehot_kernel<<<grid_for(m * net->L * 4, net->device), 256, 0, s>>>(in.onehot, r0, m, net->L,
+                                                                                      reinterpret_cast<float*>(rc_rows));
+                rin.onehot = reinterpret_cast<const float*>(rc_rows);
+            } else {
+                RcMap map;
+                uint8_t inv[4];
+                for (int b = 0; b < 4; ++b) inv[net->perm[b]] = (uint8_t)b;
+                for (int b = 0; b < 4; ++b) map.m[b] = inv[3 - net->perm[b]];
+                map.m[4] = 4;
+                rc_codes_kernel<<<grid_for(m * net->L, net->device), 256, 0, s>>>(in.codes, in.src, in.sub_pos, in.sub_code,
+                                                                                r0, m, net->L, map, rc_rows);
+                rin.codes = rc_rows;
+            }
+            SB_COUNT_LAUNCH();
+            SB_CHECK_LAUNCH();
+            for (int pass = 0; pass < 2; ++pass) {
+                const RowSource& src_rows = pass == 0 ? in : rin;
+                const long long row0 = pass == 0 ? r0 : 0;
+                float* dst = pass == 0 ? p_fwd : p_rev;
+                if (precision == SB_PREC_BF16) {
+                    SbScoreEpilogue E;
+                    memset(&E, 0, sizeof(E));
+                    E.F = F; E.row0 = 0; E.mode = 0; E.pred = dst;
+                    rc = run_chunk(net, src_rows, row0, m, precision, reinterpret_cast<uint8_t*>(ws), plan, &lg, &ldl, s, &E);
+                    if (rc) return rc;
+                } else {
+                    rc = run_chunk(net, src_rows, row0, m, precision, reinterpret_cast<uint8_t*>(ws), plan, &lg, &ldl, s);
+                    if (rc) return rc;
+                    sigmoid_kernel<<<grid_for(m * F, net->device), 256, 0, s>>>(lg, ldl, m, F, dst);
+                    SB_COUNT_LAUNCH();
+                    SB_CHECK_LAUNCH();
+                }
+            }
+            float* comb = scoring ? p_fwd : pred + r0 * F;
+            strand_combine_kernel<<<grid_for(m * F, net->device), 256, 0, s>>>(p_fwd, p_rev, m * F, net->strand_mode, comb);
+            SB_COUNT_LAUNCH();
+            SB_CHECK_LAUNCH();
+            if (scoring) {
+                if (pair_mode == SB_PAIR_INTERLEAVED) {
+                    const long long v0 = r0 / 2, nv = m / 2;
+                    score_kernel<<<grid_for(nv * F, net->device), 256, 0, s>>>(
+                        comb, F, 0, SB_PAIR_INTERLEAVED, nullptr, nullptr, 0, nv, F, abs_diff ? abs_diff + v0 * F : nullptr,
+                        diff ? diff + v0 * F : nullptr, logit ? logit + v0 * F : nullptr,
+                        pred_ref ? pred_ref + v0 * F : nullptr, pred_alt ? pred_alt + v0 * F : nullptr);
+                } else {
+                    score_kernel<<<grid_for(m * F, net->device), 256, 0, s>>>(
+                        comb, F, 0, SB_PAIR_BASELINE, base_pred, base_index ? base_index + r0 : nullptr, /*n_base*/ 1, m, F,
+                        abs_diff ? abs_diff + r0 * F : nullptr, diff ? diff + r0 * F : nullptr,
+                        logit ? logit + r0 * F : nullptr, nullptr, pred_alt ? pred_alt + r0 * F : nullptr);
+                }
+                SB_COUNT_LAUNCH();
+                SB_CHECK_LAUNCH();
+            }
+            continue;
+        }
         if (precision == SB_PREC_BF16) {
             // kernel (d): sigmoid + scores are the epilogue of the last layer's tcgen05 kernel
             SbScoreEpilogue E;

@@ -31,10 +31,22 @@ def deepsea_layers_from_state(state, pools=(4, 4, 1)):
     return out
 
 
+def unwrap_non_strand_specific(model):
+    """(inner model, strand mode) of a ``NonStrandSpecific`` wrapper (utils/non_strand_specific_module.py:26-85,
+    recognised by its ``model`` / ``mode`` attributes), else (model, 0).  Mode 1 = mean, 2 = max."""
+    if type(model).__name__ == "NonStrandSpecific" and hasattr(model, "model") and hasattr(model, "mode"):
+        if model.mode not in ("mean", "max"):
+            raise ValueError("Mode should be one of 'mean' or 'max' but was{0}.".format(model.mode))
+        return model.model, 1 if model.mode == "mean" else 2
+    return model, 0
+
+
 def layers_from_module(model):
     """Generic walk over Sequential conv stacks (Conv1d / Conv2d with (1,k) kernels / Linear / ReLU /
-    MaxPool / Dropout / BatchNorm1d / Sigmoid).  The final Sigmoid is implied by sb_net."""
+    MaxPool / Dropout / BatchNorm1d / Sigmoid).  The final Sigmoid is implied by sb_net.  A NonStrandSpecific
+    wrapper is looked through (pass ``strand_mode`` from ``unwrap_non_strand_specific`` to ``B200Net``)."""
     import torch.nn as nn
+    model, _ = unwrap_non_strand_specific(model)
     mods = []
 
     def walk(m):
@@ -126,7 +138,7 @@ def layers_from_module(model):
 class B200Net(object):
     """An ``sb_net`` handle plus its reusable device workspace."""
 
-    def __init__(self, layers, sequence_length, perm=(0, 1, 2, 3), device=None):
+    def __init__(self, layers, sequence_length, perm=(0, 1, 2, 3), device=None, strand_mode=0):
         import torch
         self._lib = _lib.load()
         self.device = torch.cuda.current_device() if device is None else int(device)
@@ -162,6 +174,9 @@ class B200Net(object):
         self.n_outputs = int(self._lib.sb_net_n_outputs(h))
         self.flops_per_seq = float(self._lib.sb_net_flops_per_seq(h))
         self._ws = None
+        self.strand_mode = 0
+        if strand_mode:
+            self.set_strand_mode(strand_mode)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -177,6 +192,12 @@ class B200Net(object):
         = 2 when rows are interleaved ref/alt pairs.  No effect on networks without an LSTM."""
         _lib.check(self._lib.sb_net_set_recurrence(self._h, int(group), int(interleave)), "sb_net_set_recurrence")
         # the workspace requirement depends on the grouping; _workspace() re-queries it and only ever grows
+
+    def set_strand_mode(self, mode):
+        """0: plain; 1 / "mean", 2 / "max": the reference's NonStrandSpecific wrapper around the network."""
+        mode = {"mean": 1, "max": 2}.get(mode, mode)
+        _lib.check(self._lib.sb_net_set_strand_mode(self._h, int(mode)), "sb_net_set_strand_mode")
+        self.strand_mode = int(mode)
 
     def _workspace(self, n, precision):
         import torch

@@ -159,7 +159,9 @@ class AnalyzeSequences(object):
                 for m in model.modules():
                     if isinstance(m, (torch.nn.Conv1d, torch.nn.Linear)):
                         m.weight.data.renorm_(2, 0, 0.9)
-        self.net = B200Net(layers_from_module(model), sequence_length, perm=Genome.perm(), device=device)
+        from ..nets import unwrap_non_strand_specific
+        self.net = B200Net(layers_from_module(model), sequence_length, perm=Genome.perm(), device=device,
+                           strand_mode=unwrap_non_strand_specific(model)[1])
         if self.net.n_outputs != len(self.features):
             raise ValueError("model predicts %d features, %d feature names given" %
                              (self.net.n_outputs, len(self.features)))

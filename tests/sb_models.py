@@ -56,6 +56,26 @@ class HeartENN(nn.Module):
         return self.classifier(o.view(o.size(0), 240 * self._n_channels))
 
 
+class DeeperDeepSEA(nn.Module):
+    """utils/example_model.py:19-93 — the model of the paper's VEP case study: DeepSEA with every
+    conv doubled and BatchNorm after each pool / before the classifier."""
+
+    def __init__(self, sequence_length=1000, n_targets=919):
+        super().__init__()
+        self.conv_net = nn.Sequential(
+            *_conv_block(4, 320, 8), *_conv_block(320, 320, 8, 4), nn.BatchNorm1d(320),
+            *_conv_block(320, 480, 8), *_conv_block(480, 480, 8, 4), nn.BatchNorm1d(480), nn.Dropout(p=0.2),
+            *_conv_block(480, 960, 8), *_conv_block(960, 960, 8), nn.BatchNorm1d(960), nn.Dropout(p=0.2))
+        self._n_channels = int(np.floor((np.floor((sequence_length - 14) / 4.) - 14) / 4.) - 14)
+        self.classifier = nn.Sequential(
+            nn.Linear(960 * self._n_channels, n_targets), nn.ReLU(inplace=True),
+            nn.BatchNorm1d(n_targets), nn.Linear(n_targets, n_targets), nn.Sigmoid())
+
+    def forward(self, x):
+        o = self.conv_net(x)
+        return self.classifier(o.view(o.size(0), 960 * self._n_channels))
+
+
 class Seqweaver(nn.Module):
     """models/seqweaver.py:25-61: Conv2d (1,8) stack; forward unsqueezes the height axis itself."""
 
@@ -91,6 +111,23 @@ class DanQ(nn.Module):
         out, _ = self.bdlstm(reshape_out)
         out = out.transpose(0, 1)
         return self.classifier(out.contiguous().view(out.size(0), 640 * self._n_channels))
+
+
+class NonStrandSpecific(nn.Module):
+    """utils/non_strand_specific_module.py:26-85 for models that take (B, 4, L): the wrapped model also sees the
+    input with its channel axis and its position axis flipped; outputs are averaged or maxed."""
+
+    def __init__(self, model, mode="mean"):
+        super().__init__()
+        if mode != "mean" and mode != "max":
+            raise ValueError("Mode should be one of 'mean' or 'max' but was{0}.".format(mode))
+        self.model = model
+        self.mode = mode
+
+    def forward(self, x):
+        out = self.model.forward(x)
+        out_rev = self.model.forward(torch.flip(x, dims=(1, 2)))
+        return (out + out_rev) / 2 if self.mode == "mean" else torch.max(out, out_rev)
 
 
 def randomize_batchnorm(model, seed=0):

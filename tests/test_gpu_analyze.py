@@ -104,3 +104,30 @@ def test_vep_files_match_oracle(tmp_path):
     assert os.path.exists(os.path.join(out_dir, "in.ref_predictions.tsv"))
     assert os.path.exists(os.path.join(out_dir, "in.alt_predictions.tsv"))
     assert open(os.path.join(out_dir, "in.NA")).read().count("\n") == 1
+
+
+def test_ism_with_non_strand_specific_model():
+    """AnalyzeSequences on a model wrapped in NonStrandSpecific (every manuscript config): ISM scores
+    equal those of the torch wrapper evaluated on the mutated one-hot sequences."""
+    import torch
+    import sb_models as M
+    from selene_b200.predict.model_predict import AnalyzeSequences
+    from selene_b200.sequences import Genome
+    Genome.update_bases_order(['A', 'C', 'G', 'T'])
+    torch.manual_seed(4)
+    wrapped = M.NonStrandSpecific(M.DeepSEA(1000, 919), mode="mean").eval()
+    az = AnalyzeSequences(wrapped, sequence_length=1000, features=FEATS, reference_sequence=Genome, precision="fp32")
+    r = np.random.default_rng(2)
+    seq = "".join(np.array(list("ACGT"))[r.integers(0, 4, 1000)].tolist())
+    (pos, alt), out, base = az.ism_scores(seq, ("abs_diffs",), start_position=480, end_position=500)
+    assert len(pos) == 60
+    enc = O.sequence_to_encoding(seq)
+    rows = np.repeat(enc[None], 60, axis=0)
+    for i in range(60):
+        rows[i, pos[i]] = 0
+        rows[i, pos[i], alt[i]] = 1
+    with torch.no_grad():
+        exp_base = wrapped(torch.tensor(enc[None]).transpose(1, 2)).numpy()
+        exp = wrapped(torch.tensor(rows).transpose(1, 2)).numpy()
+    assert np.abs(base - exp_base).max() <= 1e-5
+    assert np.abs(out["abs_diffs"] - np.abs(exp_base - exp)).max() <= 2e-5

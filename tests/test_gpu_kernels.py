@@ -427,7 +427,7 @@ def test_score_pairs_clamp_semantics(torch):
 # the other conv stacks of the reference: HeartENN (BatchNorm folding, renorm, odd row pitches,
 # 60/80/240 channels) and Seqweaver (Conv2d (1,8) kernels, 160/320/480 channels)
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("arch", ["heartenn", "seqweaver"])
+@pytest.mark.parametrize("arch", ["heartenn", "seqweaver", "deeperdeepsea"])
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
 def test_other_conv_stacks_vs_torch(torch, arch, precision, tol):
     import sb_models as M
@@ -441,6 +441,9 @@ def test_other_conv_stacks_vs_torch(torch, arch, precision, tol):
             for m in model.modules():
                 if isinstance(m, (torch.nn.Conv1d, torch.nn.Linear)):
                     m.weight.data.renorm_(2, 0, 0.9)
+    elif arch == "deeperdeepsea":   # utils/example_model.py: the paper's VEP model
+        model = M.DeeperDeepSEA(1000, 919)
+        M.randomize_batchnorm(model, 2)
     else:
         model = M.Seqweaver(217)
     model.eval()
@@ -454,6 +457,65 @@ def test_other_conv_stacks_vs_torch(torch, arch, precision, tol):
     assert np.abs(got - exp).max() <= tol, np.abs(got - exp).max()
     if precision == "bf16":
         assert np.corrcoef(got.ravel(), exp.ravel())[0, 1] > 0.99
+
+
+# ------------------------------------------------------------------------------------------------
+# NonStrandSpecific wrapper: both strands through the network, mean / max of the outputs
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["mean", "max"])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 2e-2)])
+def test_non_strand_specific_vs_torch(torch, mode, precision, tol):
+    import sb_models as M
+    from selene_b200 import _lib
+    from selene_b200.nets import B200Net, layers_from_module, unwrap_non_strand_specific
+    torch.manual_seed(13)
+    wrapped = M.NonStrandSpecific(M.DeepSEA(1000, 919), mode=mode).eval()
+    inner, sm = unwrap_non_strand_specific(wrapped)
+    assert inner is wrapped.model and sm == (1 if mode == "mean" else 2)
+    net = B200Net(layers_from_module(wrapped), 1000, strand_mode=sm)
+    codes = _rand_codes(6, 1000, 41)
+    x = torch.tensor(_onehot(codes)).transpose(1, 2)
+    with torch.no_grad():
+        exp = wrapped(x).numpy()
+        plain = wrapped.model(x).numpy()
+    assert np.abs(exp - plain).max() > 1e-4                     # the wrapper changes the answer
+    dev_codes = torch.from_numpy(codes).cuda()
+    got = net.forward_codes(dev_codes, precision=precision).cpu().numpy()
+    assert np.abs(got - exp).max() <= tol, np.abs(got - exp).max()
+    # rows built by substitution (ISM / VEP rows): row i = sequence i % 3 with one base replaced
+    src = torch.tensor([0, 1, 2, 0, 1, 2], dtype=torch.int32).cuda()
+    pos = torch.tensor([0, 499, 999, 3, 500, 7], dtype=torch.int32).cuda()
+    sub = torch.tensor([1, 2, 3, 0, 4, 2], dtype=torch.uint8).cuda()
+    rows = codes[[0, 1, 2, 0, 1, 2]].copy()
+    rows[np.arange(6), pos.cpu().numpy()] = sub.cpu().numpy()
+    with torch.no_grad():
+        exp_rows = wrapped(torch.tensor(_onehot(rows)).transpose(1, 2)).numpy()
+    got = net.forward_codes(dev_codes, src, pos, sub, n=6, precision=precision).cpu().numpy()
+    assert np.abs(got - exp_rows).max() <= tol
+    # interleaved ref/alt scoring on the combined predictions
+    res = net.forward_score(dev_codes, src, pos, sub, 6, _lib.SB_PAIR_INTERLEAVED, precision=precision,
+                            want=("abs_diffs", "diffs", "logits"))
+    ref_p, alt_p = exp_rows[0::2], exp_rows[1::2]
+    assert np.abs(res["abs_diffs"].cpu().numpy() - np.abs(ref_p - alt_p)).max() <= 2 * tol
+    assert np.abs(res["diffs"].cpu().numpy() - (alt_p - ref_p)).max() <= 2 * tol
+    if precision == "fp32":
+        # arbitrary float input (not one-hot): the generic path flips both axes
+        xg = torch.rand((3, 1000, 4), generator=torch.Generator().manual_seed(3))
+        with torch.no_grad():
+            exp_g = wrapped(xg.transpose(1, 2)).numpy()
+        got_g = net.forward_onehot(xg.cuda(), precision="fp32").cpu().numpy()
+        assert np.abs(got_g - exp_g).max() <= tol
+        # another channel order (A, G, C, T): the wrapper flips CHANNELS, whatever bases they hold
+        perm = (0, 2, 1, 3)
+        net2 = B200Net(layers_from_module(wrapped), 1000, perm=perm, strand_mode=mode)
+        oh = np.zeros(codes.shape + (4,), np.float32)
+        for b in range(4):
+            oh[codes == b, perm[b]] = 1
+        oh[codes == 4] = 0.25
+        with torch.no_grad():
+            exp2 = wrapped(torch.tensor(oh).transpose(1, 2)).numpy()
+        got2 = net2.forward_codes(dev_codes, precision="fp32").cpu().numpy()
+        assert np.abs(got2 - exp2).max() <= tol
 
 
 # ------------------------------------------------------------------------------------------------
