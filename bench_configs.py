@@ -135,6 +135,28 @@ def main():
         emit(config="1: DeepSEA ISM, one 1000-bp sequence, 3000 mutants, abs_diffs+logits to host", precision=prec,
              seconds=dt_, mutants_per_s=3000 / dt_)
 
+    # ISM with the reference's output files: the "{:.2e}" text is produced on the device
+    if want('ism'):
+        import io, shutil, tempfile
+        az.precision = "bf16"
+        tmpd = tempfile.mkdtemp(prefix="sb_ism_")
+        az.in_silico_mutagenesis(seq, ["abs_diffs", "logits"], output_path_prefix=os.path.join(tmpd, "w"))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(3):
+            az.in_silico_mutagenesis(seq, ["abs_diffs", "logits"], output_path_prefix=os.path.join(tmpd, "r%d" % i))
+        dt_files = (time.perf_counter() - t0) / 3
+        size = os.path.getsize(os.path.join(tmpd, "r0_abs_diffs.tsv"))
+        shutil.rmtree(tmpd, ignore_errors=True)
+        m_ = np.random.default_rng(0).random((3000, 919)).astype(np.float32) * 1e-3
+        t0 = time.perf_counter()
+        b_ = io.StringIO()
+        np.savetxt(b_, m_.astype(np.float64), fmt="%.2e", delimiter="\t")
+        host_fmt = time.perf_counter() - t0
+        emit(config="1: DeepSEA ISM incl. writing abs_diffs + logits TSV files (2 x 3000 x 919 values)", precision="bf16",
+             seconds=dt_files, mutants_per_s=3000 / dt_files, tsv_bytes_per_file=size,
+             host_savetxt_seconds_per_matrix=host_fmt)
+
     # ---------------------------------------------------------------- config 4: DanQ ISM
     torch.manual_seed(0)
     azd = AnalyzeSequences(M.DanQ(1000, 919), sequence_length=1000, features=feats, reference_sequence=Genome)

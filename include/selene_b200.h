@@ -284,6 +284,17 @@ int sb_net_forward_backward_tc(sb_net* net, const float* x, const float* targets
                                const float* const* dropout_masks, unsigned long long dropout_seed,
                                void* workspace, size_t workspace_bytes, float* grads, float* loss, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* score writers (predict_handlers/handler.py:15-42): "{:.2e}" text of a score matrix           */
+/* ------------------------------------------------------------------------------------------ */
+/* Row r of x (dev, n_rows x F float32) as text: "{:.2e}".format(value) per value (correctly rounded, ties to
+ * even, "nan" / "inf" / "-inf" as Python prints them), joined by tabs and ended by a newline — what
+ * write_to_tsv_file puts after the id columns.  Two calls: sb_format_e2_row_bytes gives the bytes of every row;
+ * the caller turns them into offsets (exclusive prefix sum, dev int64) and sb_format_e2_rows writes the text
+ * at out + row_off[r]. */
+int sb_format_e2_row_bytes(const float* x, int64_t n_rows, int F, int64_t* row_bytes, void* stream);
+int sb_format_e2_rows(const float* x, int64_t n_rows, int F, const int64_t* row_off, uint8_t* out, void* stream);
+
 /* Score two prediction matrices that already exist (handlers called on their own). */
 int sb_score_pairs(const float* ref /* dev (n_ref,F) */, const float* alt /* dev (n,F) */,
                    const int32_t* base_index /* dev (n) or NULL: ref row i (n_ref==n) or 0 */,

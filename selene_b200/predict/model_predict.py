@@ -59,16 +59,38 @@ def _scores_filepath(output_path_prefix, handler_filename):
     return output_path, filename_prefix, os.path.join(output_path, handler_filename)
 
 
+def format_e2_rows(data):
+    """``"{:.2e}"`` text of a float32 score matrix, formatted on the device (handler.py:36-42).
+    ``data``: (n, F) numpy array or CUDA tensor.  Returns (bytes of all rows as one uint8 numpy array, offsets
+    (n+1,) int64): row r is ``buf[off[r]:off[r+1]]`` = the values joined by tabs + a newline."""
+    import torch
+    lib = _lib.load()
+    t = data if isinstance(data, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32))
+    t = t.to(device="cuda", dtype=torch.float32).contiguous()
+    n, F = int(t.shape[0]), int(t.shape[1])
+    if n == 0:
+        return np.zeros(0, np.uint8), np.zeros(1, np.int64)
+    sizes = torch.empty(n, dtype=torch.int64, device=t.device)
+    _lib.check(lib.sb_format_e2_row_bytes(_lib.ptr(t), n, F, _lib.ptr(sizes), _lib.stream_ptr()), "sb_format_e2_row_bytes")
+    off = torch.zeros(n + 1, dtype=torch.int64, device=t.device)
+    torch.cumsum(sizes, 0, out=off[1:])
+    total = int(off[-1].item())
+    buf = torch.empty(total, dtype=torch.uint8, device=t.device)
+    _lib.check(lib.sb_format_e2_rows(_lib.ptr(t), n, F, _lib.ptr(off), _lib.ptr(buf), _lib.stream_ptr()), "sb_format_e2_rows")
+    return buf.cpu().numpy(), off.cpu().numpy()
+
+
 def write_tsv(path, columns_for_ids, features, ids, data, append=False):
-    """Rows ``id columns + "{:.2e}" per value`` (handler.py:36-42,99-114)."""
-    buf = io.StringIO()
-    np.savetxt(buf, np.asarray(data, dtype=np.float64), fmt="%.2e", delimiter="\t")
-    lines = buf.getvalue().split("\n")
-    with open(path, "a" if append else "w") as fh:
+    """Rows ``id columns + "{:.2e}" per value`` (handler.py:36-42,99-114); the numbers are formatted by
+    ``sb_format_e2_rows`` on the device, the host only splices the id columns in."""
+    buf, off = format_e2_rows(data)
+    view = memoryview(buf)
+    with open(path, "ab" if append else "wb") as fh:
         if not append:
-            fh.write("{0}\n".format("\t".join(list(columns_for_ids) + list(features))))
-        for info, line in zip(ids, lines):
-            fh.write("{0}\t{1}\n".format("\t".join(str(i) for i in info), line))
+            fh.write("{0}\n".format("\t".join(list(columns_for_ids) + list(features))).encode())
+        for r, info in enumerate(ids):
+            fh.write(("\t".join(str(i) for i in info) + "\t").encode())
+            fh.write(view[off[r]:off[r + 1]])
 
 
 def write_hdf5(path, data):

@@ -597,3 +597,49 @@ def test_tc_wgrad_selftest(torch, rows, M, x_ld, N):
     ref = view.t() @ dy.float()
     err = (g - ref).abs().max().item()
     assert err <= 3e-3 * max(1.0, ref.abs().max().item()), "max abs err %g" % err
+
+
+# ------------------------------------------------------------------------------------------------
+# the writers' "{:.2e}" formatting on the device
+# ------------------------------------------------------------------------------------------------
+def _py_rows(a):
+    return ["\t".join("{:.2e}".format(v) for v in row) + "\n" for row in a]
+
+
+def test_format_e2_matches_python(torch):
+    from selene_b200.predict.model_predict import format_e2_rows
+    special = np.array([0.0, -0.0, 1.0, -1.0, 0.125, 1.125, 1.375, 1.135, 2.5, 9.995, 9.9951, 99.95, 999.5, 0.5, 0.999999,
+                        1e-24, 123.456, 1.005, 1.015, 1.025, 3.4028235e38, -3.4028235e38, 1.4e-45, 1.1754944e-38,
+                        np.nan, np.inf, -np.inf, 6.5e-5, 1.0000001, 0.99999994, 9.99e10, 1.245e-3, 4.4999999e-7,
+                        1e10, 1.5e-10, 2.675, 1e-3, 1.0625, 1.1875, 8.5e8, 1.00097656], dtype=np.float32)
+    r = np.random.default_rng(0)
+    rand_bits = r.integers(0, 2 ** 32, (2048, 257), dtype=np.uint64).astype(np.uint32).view(np.float32)
+    # exact ties on purpose: k + 0.5 at three significant digits, scaled by powers of ten / two that stay exact
+    ties = np.array([(2 * k + 1) / 2.0 * s for k in range(100, 1000, 7) for s in (1e-2, 1e-1, 1.0, 10.0, 1e3, 1e5)],
+                    dtype=np.float32)
+    small = (r.random((512, 919)) * np.float32(10.0) ** r.integers(-8, 1, (512, 919))).astype(np.float32)
+    for a in (special[None, :], rand_bits, ties[None, :], small, np.zeros((3, 1), np.float32)):
+        buf, off = format_e2_rows(a)
+        got = [bytes(buf[off[i]:off[i + 1]]).decode() for i in range(a.shape[0])]
+        exp = _py_rows(a)
+        bad = [i for i in range(len(exp)) if got[i] != exp[i]]
+        if bad:
+            g, e = got[bad[0]].split("\t"), exp[bad[0]].split("\t")
+            diff = [(a[bad[0], j], g[j], e[j]) for j in range(len(e)) if j >= len(g) or g[j] != e[j]][:5]
+            raise AssertionError("row %d differs: %r" % (bad[0], diff))
+    buf, off = format_e2_rows(np.zeros((0, 5), np.float32))
+    assert buf.size == 0 and off.tolist() == [0]
+
+
+def test_tsv_writer_uses_device_formatter(torch, tmp_path):
+    """handler.py:15-42,99-114: header, id columns, then "{:.2e}" per value."""
+    from selene_b200.predict.model_predict import write_tsv
+    data = np.array([[1.234e-5, 0.5, 0.999999], [1e-24, 123.456, 0.0]], dtype=np.float32)
+    path = str(tmp_path / "x.tsv")
+    ids = [("1", "A", "C"), ("2", "G", "T")]
+    write_tsv(path, ["pos", "ref", "alt"], ["f0", "f1", "f2"], ids, data)
+    write_tsv(path, ["pos", "ref", "alt"], ["f0", "f1", "f2"], ids[:1], torch.from_numpy(data[:1]).cuda(), append=True)
+    lines = open(path).read().split("\n")
+    assert lines[0] == "pos\tref\talt\tf0\tf1\tf2" and lines[-1] == "" and len(lines) == 5
+    for line, row, ident in zip(lines[1:4], [data[0], data[1], data[0]], ids + ids[:1]):
+        assert line == "\t".join(ident) + "\t" + "\t".join("{:.2e}".format(p) for p in list(row))

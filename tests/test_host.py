@@ -154,19 +154,6 @@ def test_ref_alt_strings_match_oracle_for_snvs():
         assert len(rs) == L and len(als) == L
 
 
-def test_tsv_number_format(tmp_path):
-    """handler.py:99-114: "{:.2e}".format per value."""
-    from selene_b200.predict.model_predict import write_tsv
-    data = np.array([[1.234e-5, 0.5, 0.999999], [1e-24, 123.456, 0.0]], dtype=np.float32)
-    path = str(tmp_path / "x.tsv")
-    write_tsv(path, ["pos", "ref", "alt"], ["f0", "f1", "f2"], [("1", "A", "C"), ("2", "G", "T")], data)
-    lines = open(path).read().strip().split("\n")
-    assert lines[0] == "pos\tref\talt\tf0\tf1\tf2"
-    for line, row, ident in zip(lines[1:], data, [("1", "A", "C"), ("2", "G", "T")]):
-        exp = "\t".join(ident) + "\t" + "\t".join("{:.2e}".format(p) for p in list(row))
-        assert line == exp
-
-
 def test_batchnorm_folding_matches_torch_eval():
     """nets.layers_from_module: eval-mode BatchNorm folded into the following layer."""
     import torch
