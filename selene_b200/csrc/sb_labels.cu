@@ -85,7 +85,7 @@ __device__ __forceinline__ void zero_row(OutT* __restrict__ o, int n, int lane) 
     if (lane < head) o[lane] = (OutT)0;
     const int body = (n - head) / kPer;
     uint4* o4 = reinterpret_cast<uint4*>(o + head);
-    for (int i = lane; i < body; i += 32) o4[i] = make_uint4(0, 0, 0, 0);
+    for (int i = lane; i < body; i += 32) __stcs(o4 + i, make_uint4(0, 0, 0, 0));   // streaming: written once, never re-read here
     const int done = head + body * kPer;
     if (lane < n - done) o[done + lane] = (OutT)0;
 }
