@@ -177,6 +177,27 @@ def main():
          seconds_per_sequence=dt_, mutants_per_s=3000 / dt_, flops_per_seq=azd.net.flops_per_seq,
          tflops=3000 / dt_ * azd.net.flops_per_seq / 1e12)
 
+    # the same workload with two sequences in flight on two CUDA streams: a 3000-mutant ISM keeps only 56 of the 148
+    # SMs busy inside the persistent recurrence kernel, whose time does not depend on its grid size
+    if want('danq'):
+        torch.manual_seed(0)
+        azd2 = AnalyzeSequences(M.DanQ(1000, 919), sequence_length=1000, features=feats, reference_sequence=Genome)
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        azs = [azd, azd2]
+        for k in range(4):
+            with torch.cuda.stream(streams[k & 1]):
+                azs[k & 1].ism_scores(seq, ("abs_diffs", "logits"), to_host=False)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(2 * n_seq):
+            with torch.cuda.stream(streams[k & 1]):
+                azs[k & 1].ism_scores(seq, ("abs_diffs", "logits"), to_host=False)
+        torch.cuda.synchronize()
+        dt2 = (time.perf_counter() - t0) / (2 * n_seq)
+        emit(config="4: DanQ ISM, two sequences in flight on two streams, per 1000-bp sequence of 3000 mutants",
+             precision="bf16", seconds_per_sequence=dt2, mutants_per_s=3000 / dt2,
+             tflops=3000 / dt2 * azd.net.flops_per_seq / 1e12)
+
     # ---------------------------------------------------------------- config 5: Seqweaver / HeartENN sweep
     for name, model in ((("Seqweaver(217)", M.Seqweaver(217)), ("HeartENN(1000, 90)", M.HeartENN(1000, 90)),
                          ("DeeperDeepSEA(1000, 919) [SURVEY 8 f4]", M.DeeperDeepSEA(1000, 919)),

@@ -32,6 +32,8 @@ constexpr int kMaxN = 256;
 constexpr int kABytes = kBlockM * kBlockK * 2;       // 16384
 constexpr int kBBytesMax = kMaxN * kBlockK * 2;      // 32768
 constexpr int kStageBytes = kABytes + kBBytesMax;    // 49152
+constexpr int kRingBytes = kStages * kStageBytes;    // 196608: tc_layer_kernel cuts it into stages of 16 KB + its B tile
+constexpr int kMaxStages = 8;                        // small-N layers: more, smaller stages (the ring must cover the TMA latency)
 constexpr int kAuxBytes = 4096;                      // barriers + tmem slot + 2 bias tiles
 constexpr int kSmemBytes = kStages * kStageBytes + kAuxBytes + 1024;  // + alignment slack
 constexpr int kThreads = 192;
@@ -43,6 +45,7 @@ struct TcParams {
     int out_ld, relu, out_f32;
     int block_n, n_tiles_n, n_tiles_m, num_k_blocks;
     int chunks_per_tap;  // 0: overlapping-stride A view; >0: per-tap boxes
+    int stages, stage_bytes;   // smem ring: stage = A tile (16 KB) + B tile (block_n x 128 B)
     const float* bias;
     void* out;
     SbScoreEpilogue sc;
@@ -77,10 +80,10 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (sb_smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared pointer
-    uint8_t* aux = smem + kStages * kStageBytes;
+    uint8_t* aux = smem + kRingBytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
-    uint64_t* empty_bar = full_bar + kStages;
-    uint64_t* tfull_bar = empty_bar + kStages;
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tfull_bar = empty_bar + kMaxStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     float* bias_s = reinterpret_cast<float*>(aux + 1024);  // [2][256]
@@ -94,7 +97,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         sb_prefetch_tmap(&tmap_b);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < kStages; ++i) {
+        for (int i = 0; i < p.stages; ++i) {
             sb_mbar_init(&full_bar[i], 1);
             sb_mbar_init(&empty_bar[i], 1);
         }
@@ -120,7 +123,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 const int n0 = (tile % p.n_tiles_n) * p.block_n;
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     sb_mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * kStageBytes;
+                    uint8_t* sa = smem + stage * p.stage_bytes;
                     uint8_t* sb = sa + kABytes;
                     sb_mbar_expect_tx(&full_bar[stage], tx_bytes);
                     if (p.chunks_per_tap > 0) {
@@ -131,7 +134,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         sb_tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0);
                     }
                     sb_tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBlockK, n0);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -150,7 +153,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     sb_mbar_wait(&full_bar[stage], phase);
                     sb_tc_fence_after();
-                    const uint32_t sa = sb_smem_u32(smem + stage * kStageBytes);
+                    const uint32_t sa = sb_smem_u32(smem + stage * p.stage_bytes);
                     const uint64_t da = sb_umma_desc_sw128(sa);
                     const uint64_t db = sb_umma_desc_sw128(sa + kABytes);
 #pragma unroll
@@ -158,7 +161,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                         sb_umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
                                      (kb | k) != 0 ? 1u : 0u);
                     sb_umma_commit(&empty_bar[stage]);  // frees the smem stage when the MMAs finish
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                 }
                 sb_umma_commit(&tfull_bar[as]);  // accumulator complete
             }
@@ -400,6 +403,9 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbSc
     p.n_tiles_m = (int)((L.rows_a + kBlockM - 1) / kBlockM);
     p.num_k_blocks = (L.k_full + kBlockK - 1) / kBlockK;
     p.chunks_per_tap = chunks_per_tap;
+    p.stage_bytes = kABytes + L.block_n * kBlockK * 2;
+    p.stages = kRingBytes / p.stage_bytes;
+    if (p.stages > kMaxStages) p.stages = kMaxStages;
     p.bias = L.bias;
     p.out = L.out;
     memset(&p.sc, 0, sizeof(p.sc));
