@@ -258,6 +258,13 @@ int sb_net_forward_score(sb_net* net, const uint8_t* codes, const int32_t* src,
 int sb_net_train_init(sb_net* net);
 /* floats in the flat gradient vector (per layer: W as (K x ld) then bias (ld)) */
 size_t sb_net_n_params(const sb_net* net);
+/* offset (floats) of `layer`'s block (W then bias) in the flat gradient vector; layers are laid out in forward order */
+size_t sb_net_param_offset(const sb_net* net, int layer);
+/* cuda_event (a cudaEvent_t, or NULL to clear) is recorded on the launching stream inside
+ * sb_net_forward_backward[_tc] as soon as the gradients of `layer` are complete.  Backward runs from the last layer
+ * to the first, so at that point the tail of the flat vector from sb_net_param_offset(layer) on is final: a caller can
+ * all-reduce that tail (fc1 = 89 % of DeepSEA's parameters) on another stream while the conv gradients are computed. */
+int sb_net_set_grad_event(sb_net* net, int layer, void* cuda_event);
 /* dropout probability applied to the output of `layer` (after ReLU / pool) in sb_net_forward_backward */
 int sb_net_set_dropout(sb_net* net, int layer, float p);
 size_t sb_net_train_workspace_bytes(const sb_net* net, int64_t batch);

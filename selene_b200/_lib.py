@@ -65,6 +65,8 @@ SIGNATURES = {
                                   _P, _P, _P, _P, _P, _P]),
     "sb_net_train_init": (_I, [_P]),
     "sb_net_n_params": (C.c_size_t, [_P]),
+    "sb_net_param_offset": (C.c_size_t, [_P, _I]),
+    "sb_net_set_grad_event": (_I, [_P, _I, _P]),
     "sb_net_set_dropout": (_I, [_P, _I, C.c_float]),
     "sb_net_train_workspace_bytes": (C.c_size_t, [_P, _L]),
     "sb_net_forward_backward": (_I, [_P, _P, _P, _L, _P, C.c_ulonglong, _P, C.c_size_t, _P, _P, _P]),

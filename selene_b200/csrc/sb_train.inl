@@ -251,6 +251,7 @@ struct sb_train_state {
     std::vector<float*> mom_w, mom_b;      // momentum buffers per layer
     std::vector<size_t> goff_w, goff_b;    // offsets (floats) into the flat gradient vector
     std::vector<float> dropout_p;
+    std::vector<cudaEvent_t> grad_event;   // per layer, recorded when its gradients (and those of later layers) are complete
     size_t n_params;
     long long steps;
 };
@@ -274,6 +275,7 @@ extern "C" int sb_net_train_init(sb_net* net) {
         T->goff_w.push_back(off); off += nw;
         T->goff_b.push_back(off); off += nb;
         T->dropout_p.push_back(0.f);
+        T->grad_event.push_back(nullptr);
     }
     T->n_params = off;
     T->steps = 0;
@@ -282,6 +284,18 @@ extern "C" int sb_net_train_init(sb_net* net) {
 }
 
 extern "C" size_t sb_net_n_params(const sb_net* net) { return (net && net->train) ? net->train->n_params : 0; }
+
+extern "C" size_t sb_net_param_offset(const sb_net* net, int layer) {
+    if (!net || !net->train || layer < 0 || layer >= (int)net->layers.size()) return 0;
+    return net->train->goff_w[(size_t)layer];
+}
+
+extern "C" int sb_net_set_grad_event(sb_net* net, int layer, void* cuda_event) {
+    SB_REQUIRE(net && net->train, "sb_net_set_grad_event: call sb_net_train_init first");
+    SB_REQUIRE(layer >= 0 && layer < (int)net->layers.size(), "sb_net_set_grad_event: bad layer %d", layer);
+    net->train->grad_event[(size_t)layer] = (cudaEvent_t)cuda_event;
+    return SB_OK;
+}
 
 extern "C" int sb_net_set_dropout(sb_net* net, int layer, float p) {
     SB_REQUIRE(net && net->train, "sb_net_set_dropout: call sb_net_train_init first");
@@ -438,6 +452,7 @@ extern "C" int sb_net_forward_backward(sb_net* net, const float* x, const float*
             dy, rows, N.cout, N.cout, gb);
         SB_COUNT_LAUNCH();
         SB_CHECK_LAUNCH();
+        if (T->grad_event[li]) SB_CHECK_CUDA(cudaEventRecord(T->grad_event[li], s));
         if (li == 0) break;
         if (conv) {
             // dgrad as a forward-style GEMM over the shifted view of dfull with the taps-flipped W^T; the

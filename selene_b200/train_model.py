@@ -46,6 +46,22 @@ class B200Trainer(object):
         if dropout:
             for layer, p in dropout.items():
                 _lib.check(self._lib.sb_net_set_dropout(self._h, int(layer), float(p)), "sb_net_set_dropout")
+        # data parallel: the classifier's gradients (the tail of the flat vector, 89 % of DeepSEA's parameters) are
+        # final early in the backward pass; an event recorded there lets their all-reduce overlap the conv backward
+        self._tail_layer = next((i for i, l in enumerate(layers) if l["type"] == "fc"), None)
+        self._tail_off = 0
+        self._tail_event = None
+        self._comm_stream = None
+
+    def _enable_overlap(self):
+        import torch
+        if self._tail_event is None and self._tail_layer is not None and self._tail_layer > 0:
+            self._tail_off = int(self._lib.sb_net_param_offset(self._h, self._tail_layer))
+            self._tail_event = torch.cuda.Event()
+            self._tail_event.record()                  # creates the underlying cudaEvent_t
+            _lib.check(self._lib.sb_net_set_grad_event(self._h, self._tail_layer,
+                                                       C.c_void_p(self._tail_event.cuda_event)), "sb_net_set_grad_event")
+            self._comm_stream = torch.cuda.Stream(device=self.device)
 
     @classmethod
     def dropout_of_module(cls, model):
@@ -87,11 +103,28 @@ class B200Trainer(object):
             _lib.ptr(ws), ws.numel(), _lib.ptr(self.grads), _lib.ptr(self.loss), _lib.stream_ptr()),
             "sb_net_forward_backward")
 
-    def allreduce_grads(self):
+    def allreduce_grads(self, overlap=True):
+        """Mean of the flat gradient vector over the ranks (NCCL).  With ``overlap`` the classifier tail is reduced
+        on a side stream as soon as ``sb_net_forward_backward`` has produced it (the event of sb_net_set_grad_event),
+        i.e. while the convolution gradients are still being computed; the head follows on the current stream."""
+        import torch
         import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.grads)
-            self.grads.div_(dist.get_world_size())
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        avg = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else dist.ReduceOp.SUM
+        div = None if avg == dist.ReduceOp.AVG else dist.get_world_size()
+        if overlap and self._tail_event is not None:
+            cur = torch.cuda.current_stream()
+            self._comm_stream.wait_event(self._tail_event)
+            with torch.cuda.stream(self._comm_stream):
+                tail = dist.all_reduce(self.grads[self._tail_off:], op=avg, async_op=True)
+            dist.all_reduce(self.grads[:self._tail_off], op=avg)
+            tail.wait()                                   # the current stream waits for the side-stream reduction
+            cur.wait_stream(self._comm_stream)
+        else:
+            dist.all_reduce(self.grads, op=avg)
+        if div:
+            self.grads.div_(div)
 
     def sgd_step(self):
         _lib.check(self._lib.sb_net_sgd_step(self._h, _lib.ptr(self.grads), self.lr, self.momentum, self.weight_decay,
@@ -100,6 +133,9 @@ class B200Trainer(object):
 
     def step(self, inputs, targets, masks=None):
         """One optimisation step; returns the mean BCE loss as a python float (device -> host read)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self._enable_overlap()
         self.forward_backward(inputs, targets, masks)
         self.allreduce_grads()
         self.sgd_step()

@@ -154,6 +154,14 @@ def test_ref_alt_strings_match_oracle_for_snvs():
         assert len(rs) == L and len(als) == L
 
 
+def test_is_positive_row_reference_kats():
+    """targets/tests/test_genomic_features.py:63-85 (the three known answers of _is_positive_row)."""
+    from selene_b200.targets.genomic_features import _is_positive_row
+    assert not _is_positive_row(16150, 16351, 16110, 16190, 0.50)
+    assert _is_positive_row(16110, 16309, 16110, 16190, 0.40)
+    assert _is_positive_row(16110, 16311, 16110, 16290, 0.80)
+
+
 def test_batchnorm_folding_matches_torch_eval():
     """nets.layers_from_module: eval-mode BatchNorm folded into the following layer."""
     import torch
