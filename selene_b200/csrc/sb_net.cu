@@ -39,6 +39,7 @@ struct NetLayer {
     // first layer from codes
     float* lut;  // dev (k x 5 x cout)
     uint16_t* w1_packed;  // dev, tcgen05 core-matrix layout (sb_conv1.cu); null if unsupported
+    uint16_t* w1l_packed; // dev, the same for sb_conv1l.cu (many taps, wide pool); null if unsupported
     float* bias1_padded;  // dev, n_pass*64
     // first layer too long / pooled too wide for sb_conv1.cu (DanQ: 26 taps, pool 13): generic layer kernel
     // on a (n, L, 8) bf16 one-hot (4 zero channels), K index = tap*8 + canonical base
@@ -105,6 +106,14 @@ int sb_lstm_perm_row(int n, int H);
 size_t sb_conv1_pack_weights(const float* w, int cout, int taps, const uint8_t perm[4], uint16_t* out,
                              uint16_t (*to_bf16)(float));
 int sb_conv1_tc_supported(int taps, int pool, int cout);
+// sb_conv1l.cu: many taps + wide pool (DanQ)
+int sb_conv1_long_supported(int taps, int pool, int cout);
+size_t sb_conv1_long_pack_weights(const float* w, int cout, int taps, const uint8_t perm[4], uint16_t* out,
+                                  uint16_t (*to_bf16)(float));
+int sb_conv1_long_launch(const uint8_t* codes, const int32_t* src, const int32_t* sub_pos, const uint8_t* sub_code,
+                         long long row0, long long n_rows, int L, int taps, int pool, int t_pool, int out_pitch, int cout,
+                         int out_ld, int relu, const void* wpacked, const float* bias_padded, void* out, int device,
+                         cudaStream_t stream);
 int sb_conv1_tc_launch(const uint8_t* codes, const int32_t* src, const int32_t* sub_pos, const uint8_t* sub_code,
                        long long row0, long long n_rows, int L, int taps, int pool, int t_pool, int out_pitch, int cout,
                        int out_ld, int relu, const void* wpacked, const float* bias_padded, void* out, int device,
@@ -614,6 +623,15 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
                 std::vector<float> bp((size_t)n_pass * 64, 0.f);
                 for (int o = 0; o < S.cout; ++o) bp[o] = S.bias[o];
                 rc = upload(&N.bias1_padded, bp); if (rc) return rc;
+            } else if (sb_conv1_long_supported(S.k, N.pool, S.cout) && !(force_lut && force_lut[0] == '1') &&
+                       !(getenv("SB_CONV1_LONG") && getenv("SB_CONV1_LONG")[0] == '0')) {
+                const int n_pass = (S.cout + 63) / 64;
+                std::vector<uint16_t> wp(sb_conv1_long_pack_weights(S.weight, S.cout, S.k, perm, nullptr, f32_to_bf16_bits), 0);
+                sb_conv1_long_pack_weights(S.weight, S.cout, S.k, perm, wp.data(), f32_to_bf16_bits);
+                rc = upload(&N.w1l_packed, wp); if (rc) return rc;
+                std::vector<float> bp((size_t)n_pass * 64, 0.f);
+                for (int o = 0; o < S.cout; ++o) bp[o] = S.bias[o];
+                rc = upload(&N.bias1_padded, bp); if (rc) return rc;
             } else {
                 N.w0_ld = S.k * 8;
                 std::vector<uint16_t> w0((size_t)S.cout * N.w0_ld, 0);
@@ -740,7 +758,7 @@ extern "C" int sb_net_destroy(sb_net* net) {
     for (auto& g : net->lstm_graphs) cudaGraphExecDestroy(g.exec);
     if (net->capture_stream) cudaStreamDestroy(net->capture_stream);
     for (auto& N : net->layers) {
-        cudaFree(N.wf); cudaFree(N.biasf); cudaFree(N.wb); cudaFree(N.wb_tap); cudaFree(N.biasb); cudaFree(N.lut); cudaFree(N.w1_packed); cudaFree(N.bias1_padded); cudaFree(N.w0_b); cudaFree(N.w0_bias);
+        cudaFree(N.wf); cudaFree(N.biasf); cudaFree(N.wb); cudaFree(N.wb_tap); cudaFree(N.biasb); cudaFree(N.lut); cudaFree(N.w1_packed); cudaFree(N.w1l_packed); cudaFree(N.bias1_padded); cudaFree(N.w0_b); cudaFree(N.w0_bias);
         cudaFree(N.whh_f[0]); cudaFree(N.whh_f[1]); cudaFree(N.whh_b[0]); cudaFree(N.whh_b[1]); cudaFree(N.zero_bias);
         cudaFree(N.wb_perm); cudaFree(N.biasb_perm); cudaFree(N.whh_perm[0]); cudaFree(N.whh_perm[1]);
     }
@@ -1084,6 +1102,11 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
                                             N.t_pool, N.pitch_out, N.cout, out_ld, N.relu, N.w1_packed,
                                             N.bias1_padded, act[cur], dev, stream);
                 if (rc) return rc;
+            } else if (bf && N.w1l_packed) {
+                int rc = sb_conv1_long_launch(in.codes, in.src, in.sub_pos, in.sub_code, r0, m, net->L, N.k, N.pool, N.t_pool,
+                                              N.pitch_out, N.cout, out_ld, N.relu, N.w1l_packed, N.bias1_padded, act[cur],
+                                              dev, stream);
+                if (rc) return rc;
             } else if (bf && N.w0_b) {
                 // one-hot (n, L, 8) -> generic tcgen05 layer kernel (unpooled) -> bf16 pool
                 uint4* oh = reinterpret_cast<uint4*>(full);
@@ -1120,7 +1143,7 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
                     in.codes, in.src, in.sub_pos, in.sub_code, r0, net->L, N.k, N.cout, out_ld, N.relu, N.pool,
                     N.t_pool, N.t_pool, N.lut, N.biasf, reinterpret_cast<float*>(act[cur]));
             }
-            if (!(bf && (N.w1_packed || N.w0_b))) {
+            if (!(bf && (N.w1_packed || N.w1l_packed || N.w0_b))) {
                 SB_COUNT_LAUNCH();
                 SB_CHECK_LAUNCH();
             }

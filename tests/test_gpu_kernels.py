@@ -460,6 +460,51 @@ def test_other_conv_stacks_vs_torch(torch, arch, precision, tol):
 
 
 # ------------------------------------------------------------------------------------------------
+# first conv with many taps and a wide pool (sb_conv1l.cu; DanQ's 26 taps / pool 13 and other shapes)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("taps,pool,cout,L", [(26, 13, 320, 1000), (11, 5, 70, 203), (32, 2, 64, 180), (9, 32, 130, 400),
+                                              (12, 3, 8, 97)])
+def test_long_first_conv_wide_pool_vs_torch(torch, taps, pool, cout, L):
+    import torch.nn as nn
+    from selene_b200.nets import B200Net, layers_from_module
+    torch.manual_seed(taps * 100 + pool)
+    t_pool = (L - taps + 1) // pool
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv_net = nn.Sequential(nn.Conv1d(4, cout, taps), nn.ReLU(inplace=True), nn.MaxPool1d(pool, pool))
+            self.classifier = nn.Sequential(nn.Linear(cout * t_pool, 24), nn.Sigmoid())
+
+        def forward(self, x):
+            o = self.conv_net(x)
+            return self.classifier(o.reshape(o.size(0), -1))
+    model = Net().eval()
+    with torch.no_grad():
+        model.classifier[0].weight.mul_(0.2)
+    codes = _rand_codes(9, L, taps + pool, p_unk=0.03)
+    x = torch.tensor(_onehot(codes)).transpose(1, 2)
+    with torch.no_grad():
+        exp = model(x).numpy()
+    net = B200Net(layers_from_module(model), L)
+    dev_codes = torch.from_numpy(codes).cuda()
+    got32 = net.forward_codes(dev_codes, precision="fp32").cpu().numpy()
+    assert np.abs(got32 - exp).max() <= 1e-5
+    got = net.forward_codes(dev_codes, precision="bf16").cpu().numpy()
+    assert np.abs(got - exp).max() <= 2e-2, np.abs(got - exp).max()
+    # substituted rows take the same path
+    src = torch.tensor([0, 1, 2, 3], dtype=torch.int32).cuda()
+    pos = torch.tensor([0, L - 1, L // 2, taps], dtype=torch.int32).cuda()
+    sub = torch.tensor([3, 0, 4, 1], dtype=torch.uint8).cuda()
+    rows = codes[:4].copy()
+    rows[np.arange(4), pos.cpu().numpy()] = sub.cpu().numpy()
+    with torch.no_grad():
+        exp_rows = model(torch.tensor(_onehot(rows)).transpose(1, 2)).numpy()
+    got = net.forward_codes(dev_codes, src, pos, sub, n=4, precision="bf16").cpu().numpy()
+    assert np.abs(got - exp_rows).max() <= 2e-2
+
+
+# ------------------------------------------------------------------------------------------------
 # NonStrandSpecific wrapper: both strands through the network, mean / max of the outputs
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("mode", ["mean", "max"])
