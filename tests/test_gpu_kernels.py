@@ -462,8 +462,8 @@ def test_other_conv_stacks_vs_torch(torch, arch, precision, tol):
 # ------------------------------------------------------------------------------------------------
 # first conv with many taps and a wide pool (sb_conv1l.cu; DanQ's 26 taps / pool 13 and other shapes)
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("taps,pool,cout,L", [(26, 13, 320, 1000), (11, 5, 70, 203), (32, 2, 64, 180), (9, 32, 130, 400),
-                                              (12, 3, 8, 97)])
+@pytest.mark.parametrize("taps,pool,cout,L", [(26, 13, 320, 1000), (11, 5, 70, 203), (32, 2, 64, 180), (9, 15, 130, 400),
+                                              (12, 3, 8, 97), (10, 7, 257, 300)])
 def test_long_first_conv_wide_pool_vs_torch(torch, taps, pool, cout, L):
     import torch.nn as nn
     from selene_b200.nets import B200Net, layers_from_module
