@@ -10,12 +10,13 @@
 //     reads as its A operand (double buffered: step s reads one copy while its epilogue writes h_s into
 //     the other);
 //   * c of the 128 units lives in TENSOR MEMORY next to the accumulators (lane = unit, column = hidden
-//     unit, fp32), read with tcgen05.ld and written back with tcgen05.st by the thread that owns the unit;
-//   * warp 0 (one lane) streams W_hh through a TMA ring in tiles of 64 gate rows x 64 k.  The rows are
-//     permuted on the host so that a tile holds 2 halves x 4 gates x 8 hidden units (sb_lstm_perm_row):
+//     unit, fp32), read with tcgen05.ld and written back with tcgen05.st by the thread that owns the unit; the
+//     256 columns left after the accumulators hold hidden units 0..255, the rest (DanQ: 64) stay in registers;
+//   * warp 0 (one lane) streams W_hh through a TMA ring in tiles of 128 gate rows x 64 k.  The rows are
+//     permuted on the host so that every 64 rows hold 2 halves x 4 gates x 8 hidden units (sb_lstm_perm_row):
 //     one contiguous TMA box per tile, identical every step (L2-resident);
-//   * warp 1 (one lane) issues the MMAs: per step H/16 N-tiles x H/64 k-blocks x 4 x (128 x 64 x 16), fp32
-//     accumulators in TMEM (3 x 64 columns, so the cell math of a tile overlaps the MMAs of the next two);
+//   * warp 1 (one lane) issues the MMAs: per step H/32 N-tiles x H/64 k-blocks x 4 x (128 x 128 x 16), fp32
+//     accumulators in TMEM (2 x 128 columns, so the cell math of a tile overlaps the MMAs of the next);
 //   * warps 2-9 (thread = unit x half tile) do the cell update: gates = acc + xW, where xW is the input
 //     projection (+ bias) written by the projection GEMM as bf16 in the same permuted column order, so the 64
 //     bytes one thread needs per tile are contiguous; every thread loads its own one tile ahead into
@@ -24,24 +25,30 @@
 
 #include <cuda.h>
 
+#include <type_traits>
+
 namespace {
 
 constexpr int kUnits = 128;
-constexpr int kNTile = 64;           // 2 halves x 4 gates x 8 hidden units
-constexpr int kHidPerTile = 16;
-constexpr int kBStages = 8;          // 64 KB of W_hh in flight: the ring must cover the L2 latency x bandwidth product
-constexpr int kBStageBytes = kNTile * 64 * 2;   // 8192
+constexpr int kSubTile = 64;         // 2 halves x 4 gates x 8 hidden units (the unit of the row permutation)
+constexpr int kNTile = 128;          // one MMA tile = two sub-tiles
+constexpr int kHidPerSub = 16;
+constexpr int kBStages = 4;          // 64 KB of W_hh in flight: the ring must cover the L2 latency x bandwidth product
+constexpr int kBStageBytes = kNTile * 64 * 2;   // 16384
 constexpr int kEpiThreads = 256;
 constexpr int kLThreads = 64 + kEpiThreads;
-constexpr int kAccStages = 3;        // accumulator stages: tiles are short, the handshake latency needs depth
-constexpr int kAccCols = kAccStages * kNTile; // c state starts at this TMEM column
+constexpr int kAccStages = 2;
+constexpr int kAccCols = kAccStages * kNTile;   // 256: c state starts at this TMEM column
+constexpr int kCTmemHidden = 512 - kAccCols;    // hidden units whose c lives in tensor memory; the rest in registers
+constexpr int kCRegSubTiles = 4;                // up to 4 sub-tiles (64 hidden units) of c in registers
 
 struct LstmParams {
     long long m_rows;        // rows of the chunk
     long long n_units;       // chains * T
     int H, T, G, I, steps;
     int kblocks;             // H / 64
-    int n_tiles;             // H / 16
+    int n_sub;               // H / 16 sub-tiles
+    int n_tiles;             // n_sub / 2 MMA tiles
     const __nv_bfloat16* xw; // (m_rows*T, 8H) bf16, permuted columns, bias included
     __nv_bfloat16* out;      // (m_rows*T, out_ld)
     int out_ld;
@@ -164,19 +171,24 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
         // element offset of this thread's 32 projection values of tile nt at step s: row(s) * xw_ld + col0 + 64 nt
         const long long col0 = (long long)dir * 4 * p.H + half * 32;
         auto row_of = [&](int s) { return (first + (long long)p.I * (dir == 0 ? s : len - 1 - s)) * p.T + pos; };
-        // every thread loads its OWN 64 bytes of the projection one tile ahead, straight into registers (the line
-        // was pulled into L2 during the previous step)
-        auto fetch = [&](int s, int nt, uint4 (&x)[4]) {
+        // every thread loads its OWN 64 bytes of the projection one sub-tile ahead, straight into registers (the
+        // line was pulled into L2 during the previous step)
+        auto fetch = [&](int s, int sub_tile, uint4 (&x)[4]) {
             if (s < len) {
-                const uint4* src = reinterpret_cast<const uint4*>(p.xw + row_of(s) * xw_ld + col0 + nt * kNTile);
+                const uint4* src = reinterpret_cast<const uint4*>(p.xw + row_of(s) * xw_ld + col0 + sub_tile * kSubTile);
 #pragma unroll
                 for (int g = 0; g < 4; ++g) x[g] = __ldg(src + g);
             }
         };
         uint4 xn[4] = {};
-        int fs = 0, fnt = 0;   // next tile to fetch
+        int fs = 0, fst = 0;   // next sub-tile to fetch
         fetch(0, 0, xn);
-        if (++fnt == p.n_tiles) { fnt = 0; ++fs; }
+        if (++fst == p.n_sub) { fst = 0; ++fs; }
+        float creg[kCRegSubTiles * 8];   // c of the hidden units beyond kCTmemHidden (DanQ: 256..319)
+#pragma unroll
+        for (int i = 0; i < kCRegSubTiles * 8; ++i) creg[i] = 0.f;
+        const int n_tmem_sub = (p.H < kCTmemHidden ? p.H : kCTmemHidden) / kHidPerSub;   // sub-tiles with c in TMEM
+
         uint32_t as = 0, aphase = 0;
         for (int s = 0; s < p.steps; ++s) {
             const bool live = s < len;
@@ -185,27 +197,29 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
             // the next step's projection row: pull it towards L2 while this step computes
             const __nv_bfloat16* nxt = (s + 1 < len) ? p.xw + row_of(s + 1) * xw_ld + col0 : nullptr;
             uint8_t* hnext = hA + ((s + 1) & 1) * a_bytes;
-            for (int nt = 0; nt < p.n_tiles; ++nt) {
-                if (nxt) sb_prefetch_l2(nxt + nt * kNTile);
+
+            // one 64-column sub-tile (16 hidden units, this thread: 8 of them); RS >= 0: c in creg[RS*8 ...]
+            auto sub_tile = [&](int st, uint32_t acc_col, bool release, auto rs_tag) {
+                constexpr int RS = decltype(rs_tag)::value;
+                if (nxt) sb_prefetch_l2(nxt + st * kSubTile);
                 uint4 xv[4];   // gates i, f, g, o: 8 bf16 each
 #pragma unroll
                 for (int g = 0; g < 4; ++g) xv[g] = xn[g];
-                if (fs < p.steps) fetch(fs, fnt, xn);   // tile gt + 1
-                if (++fnt == p.n_tiles) { fnt = 0; ++fs; }
-                sb_mbar_wait(&tfull[as], aphase);
-                sb_tc_fence_after();
-                const uint32_t taddr = tmem_base + lane_bits + as * kNTile + half * 32;
-                const uint32_t caddr = tmem_base + lane_bits + kAccCols + nt * kHidPerTile + half * 8;
+                if (fs < p.steps) fetch(fs, fst, xn);   // the next sub-tile
+                if (++fst == p.n_sub) { fst = 0; ++fs; }
+                const uint32_t taddr = tmem_base + lane_bits + acc_col + half * 32;
+                const uint32_t caddr = tmem_base + lane_bits + kAccCols + st * kHidPerSub + half * 8;
                 uint32_t ri[8], rf[8], rg[8], ro[8], rc[8];
                 sb_tmem_ld8(taddr + 0, ri);
                 sb_tmem_ld8(taddr + 8, rf);
                 sb_tmem_ld8(taddr + 16, rg);
                 sb_tmem_ld8(taddr + 24, ro);
-                if (s > 0) sb_tmem_ld8(caddr, rc);
+                if (RS < 0) { if (s > 0) sb_tmem_ld8(caddr, rc); }
                 sb_tmem_wait_ld();
-                sb_tc_fence_before();
-                sb_mbar_arrive(&tempty[as]);    // accumulators are in registers: this stage may be overwritten
-                if (++as == kAccStages) { as = 0; aphase ^= 1; }
+                if (release) {     // the whole 128-column stage is in registers now: the MMAs of tile + 2 may overwrite it
+                    sb_tc_fence_before();
+                    sb_mbar_arrive(&tempty[as]);
+                }
                 const uint32_t xi[4] = {xv[0].x, xv[0].y, xv[0].z, xv[0].w};
                 const uint32_t xf[4] = {xv[1].x, xv[1].y, xv[1].z, xv[1].w};
                 const uint32_t xg[4] = {xv[2].x, xv[2].y, xv[2].z, xv[2].w};
@@ -221,22 +235,40 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
                         const float af = __uint_as_float(rf[j]) + (q ? bf16_hi(xf[j2]) : bf16_lo(xf[j2]));
                         const float ag = __uint_as_float(rg[j]) + (q ? bf16_hi(xg[j2]) : bf16_lo(xg[j2]));
                         const float ao = __uint_as_float(ro[j]) + (q ? bf16_hi(xo[j2]) : bf16_lo(xo[j2]));
-                        const float c_old = s > 0 ? __uint_as_float(rc[j]) : 0.f;
+                        float c_old;
+                        if (RS >= 0) c_old = creg[(RS >= 0 ? RS : 0) * 8 + j];
+                        else c_old = s > 0 ? __uint_as_float(rc[j]) : 0.f;
                         const float c_new = fmaf(sigmoid_fast(af), c_old, sigmoid_fast(ai) * tanh_fast(ag));
-                        rc[j] = __float_as_uint(c_new);
+                        if (RS >= 0) creg[(RS >= 0 ? RS : 0) * 8 + j] = c_new;
+                        else rc[j] = __float_as_uint(c_new);
                         hv[q] = sigmoid_fast(ao) * tanh_fast(c_new);
                     }
                     __nv_bfloat162 a = __floats2bfloat162_rn(hv[0], hv[1]);
                     hp[j2] = *reinterpret_cast<uint32_t*>(&a);
                 }
-                sb_tmem_st8(caddr, rc);
+                if (RS < 0) sb_tmem_st8(caddr, rc);
                 const uint4 hq = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-                const int k0 = nt * kHidPerTile + half * 8;          // first hidden unit of this thread's group
-                if (live) *reinterpret_cast<uint4*>(orow + nt * kHidPerTile) = hq;   // layer output (bf16, 16 bytes)
+                const int k0 = st * kHidPerSub + half * 8;          // first hidden unit of this thread's group
+                if (live) *reinterpret_cast<uint4*>(orow + st * kHidPerSub) = hq;   // layer output (bf16, 16 bytes)
                 // h_s into the other A copy: k-block k0/64, 128-byte rows, 16-byte chunks XOR-swizzled by row&7
                 *reinterpret_cast<uint4*>(hnext + (k0 >> 6) * (kUnits * 128) + r * 128 + ((((k0 & 63) >> 3) ^ (r & 7)) << 4)) = hq;
+            };
+            // one 128-column MMA tile = sub-tiles 2 nt and 2 nt + 1
+            auto tile = [&](int nt, auto rs0, auto rs1) {
+                sb_mbar_wait(&tfull[as], aphase);
+                sb_tc_fence_after();
+                sub_tile(2 * nt, as * kNTile, false, rs0);
+                sub_tile(2 * nt + 1, as * kNTile + kSubTile, true, rs1);
                 sb_tmem_wait_st();
-            }
+                if (++as == kAccStages) { as = 0; aphase ^= 1; }
+            };
+            using Tm = std::integral_constant<int, -1>;
+            const int n_tmem_tiles = n_tmem_sub / 2 < p.n_tiles ? n_tmem_sub / 2 : p.n_tiles;
+            for (int nt = 0; nt < n_tmem_tiles; ++nt) tile(nt, Tm{}, Tm{});
+            if (p.n_tiles > n_tmem_tiles)
+                tile(n_tmem_tiles, std::integral_constant<int, 0>{}, std::integral_constant<int, 1>{});
+            if (p.n_tiles > n_tmem_tiles + 1)
+                tile(n_tmem_tiles + 1, std::integral_constant<int, 2>{}, std::integral_constant<int, 3>{});
             sb_fence_proxy_async();           // this step's h is visible to the tensor core
             sb_mbar_arrive(&h_ready[(s + 1) & 1]);
         }
@@ -257,15 +289,15 @@ size_t lstm_smem_bytes(int H) {
 }  // namespace
 
 int sb_lstm_persistent_supported(int H) {
-    return H % 64 == 0 && H >= 64 && lstm_smem_bytes(H) <= 227 * 1024 && kAccCols + H <= 512;
+    return H % 64 == 0 && H >= 64 && lstm_smem_bytes(H) <= 227 * 1024 && H <= kCTmemHidden + kCRegSubTiles * kHidPerSub;
 }
 
 // Row order of the permuted recurrent / projection matrices of one direction: tile nt holds, for each half,
 // the four gates of 8 consecutive hidden units.  Returns the torch row (gate*H + hidden) stored at row n.
 int sb_lstm_perm_row(int n, int H) {
-    const int nt = n / kNTile, rem = n % kNTile;
+    const int nt = n / kSubTile, rem = n % kSubTile;
     const int half = rem / 32, g = (rem % 32) / 8, j = rem % 8;
-    return g * H + nt * kHidPerTile + half * 8 + j;
+    return g * H + nt * kHidPerSub + half * 8 + j;
 }
 
 // whh[d]: (4H x h_ld) bf16 K-major, rows permuted by sb_lstm_perm_row; xw: (m*T, 8H) bf16 projection + bias with
@@ -300,7 +332,7 @@ int sb_lstm_persistent_launch(const void* whh0, const void* whh1, int h_ld, cons
     p.H = H; p.T = T; p.G = G; p.I = I;
     long long steps = (m_rows + I - 1) / I;
     p.steps = (int)(steps > G ? G : steps);
-    p.kblocks = H / 64; p.n_tiles = H / kHidPerTile;
+    p.kblocks = H / 64; p.n_sub = H / kHidPerSub; p.n_tiles = p.n_sub / 2;
     p.xw = reinterpret_cast<const __nv_bfloat16*>(xw); p.out = reinterpret_cast<__nv_bfloat16*>(out); p.out_ld = out_ld;
     const size_t smem = lstm_smem_bytes(H);
     static size_t attr = 0;
