@@ -288,6 +288,35 @@ def test_labels_many_intervals_and_long_bins(torch, tmp_path, thr):
         assert np.array_equal(got[i], exp), (qc[i], qs[i], qe[i])
 
 
+def test_labels_many_contigs_and_negative_starts(torch, tmp_path):
+    """More than 512 contigs (the per-contig offsets then stay in global memory instead of shared memory), bins that
+    start before position 0 and bins past the last interval of a contig."""
+    from selene_b200.targets import GenomicFeatures
+    rng = np.random.default_rng(23)
+    n_feat = 7
+    feats = ["f%d" % i for i in range(n_feat)]
+    names = ["ctg%04d" % i for i in range(600)]
+    rows = []
+    for c in names:
+        for _ in range(int(rng.integers(0, 12))):
+            s = int(rng.integers(0, 3000))
+            rows.append((c, s, s + int(rng.integers(1, 500)), feats[rng.integers(0, n_feat)]))
+    rows.sort(key=lambda r: (r[0], r[1], r[2]))
+    path = str(tmp_path / "contigs.bed.gz")
+    H.write_bed(rows, path)
+    GF = GenomicFeatures(path, feats, feature_thresholds=0.3)
+    by = H.rows_by_chrom(rows)
+    fid = {f: i for i, f in enumerate(feats)}
+    qc = [names[rng.integers(0, 600)] for _ in range(400)]
+    qs = [int(rng.integers(-150, 4000)) for _ in range(400)]
+    qe = [s + 200 for s in qs]
+    got = GF.label_bins(qc, qs, qe, out_dtype="int64").cpu().numpy()
+    for i in range(400):
+        r = O.query_rows(by, qc[i], qs[i], qe[i])
+        exp = O.fast_get_feature_data(qs[i], qe[i], GF._feature_thresholds_vec, fid, r)
+        assert np.array_equal(got[i], exp), (qc[i], qs[i], qe[i])
+
+
 def test_labels_reference_goldens(torch, tmp_path):
     """Rows and expected vectors of selene_sdk/targets/tests/test_genomic_features.py:24-42,151-187."""
     from selene_b200.targets import GenomicFeatures
