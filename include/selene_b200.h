@@ -301,6 +301,11 @@ int sb_net_forward_backward_tc(sb_net* net, const float* x, const float* targets
  * at out + row_off[r]. */
 int sb_format_e2_row_bytes(const float* x, int64_t n_rows, int F, int64_t* row_bytes, void* stream);
 int sb_format_e2_rows(const float* x, int64_t n_rows, int F, const int64_t* row_off, uint8_t* out, void* stream);
+/* The same with the id columns spliced in: row r = prefix[prefix_off[r] : prefix_off[r+1]] (dev bytes, e.g.
+ * "pos\tref\talt\t") followed by the values; row_off must then be the prefix sum of (prefix length + value bytes),
+ * and the whole file body is one buffer. */
+int sb_format_e2_rows_prefixed(const float* x, int64_t n_rows, int F, const int64_t* row_off, const uint8_t* prefix,
+                               const int64_t* prefix_off, uint8_t* out, void* stream);
 
 /* Score two prediction matrices that already exist (handlers called on their own). */
 int sb_score_pairs(const float* ref /* dev (n_ref,F) */, const float* alt /* dev (n,F) */,

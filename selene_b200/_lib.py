@@ -78,6 +78,7 @@ SIGNATURES = {
     "sb_score_pairs": (_I, [_P, _P, _P, _L, _L, _I, _P, _P, _P, _I, _P]),
     "sb_format_e2_row_bytes": (_I, [_P, _L, _I, _P, _P]),
     "sb_format_e2_rows": (_I, [_P, _L, _I, _P, _P, _P]),
+    "sb_format_e2_rows_prefixed": (_I, [_P, _L, _I, _P, _P, _P, _P, _P]),
     "sb_tc_wgrad_selftest": (_I, [_P, _P, _L, _I, _I, _I, _P, _P]),
     "sb_tc_gemm_selftest": (_I, [_P, _P, _I, _I, _I, _P, _P]),
 }

@@ -185,11 +185,18 @@ __global__ void __launch_bounds__(kFmtWarps * 32) e2_row_bytes_kernel(const floa
 
 __global__ void __launch_bounds__(kFmtWarps * 32) e2_rows_kernel(const float* __restrict__ x, long long n_rows, int F,
                                                                 const long long* __restrict__ row_off,
+                                                                const uint8_t* __restrict__ prefix,
+                                                                const long long* __restrict__ prefix_off,
                                                                 uint8_t* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const long long warps = (long long)gridDim.x * kFmtWarps;
     for (long long r = (long long)blockIdx.x * kFmtWarps + (threadIdx.x >> 5); r < n_rows; r += warps) {
         long long base = row_off[r];
+        if (prefix) {   // the row's id columns (bytes supplied by the caller) come first
+            const long long p0 = prefix_off[r], plen = prefix_off[r + 1] - p0;
+            for (long long i = lane; i < plen; i += 32) out[base + i] = prefix[p0 + i];
+            base += plen;
+        }
         for (int f0 = 0; f0 < F; f0 += 32) {
             const int f = f0 + lane;
             const float v = f < F ? x[r * F + f] : 0.f;
@@ -227,19 +234,31 @@ extern "C" int sb_format_e2_row_bytes(const float* x, int64_t n_rows, int F, int
     return SB_OK;
 }
 
-extern "C" int sb_format_e2_rows(const float* x, int64_t n_rows, int F, const int64_t* row_off, uint8_t* out,
-                                 void* stream) {
+static int format_rows(const float* x, int64_t n_rows, int F, const int64_t* row_off, const uint8_t* prefix,
+                       const int64_t* prefix_off, uint8_t* out, void* stream) {
     SB_REQUIRE(n_rows >= 0 && F > 0, "sb_format_e2_rows: bad sizes");
     if (n_rows == 0) return SB_OK;
     SB_REQUIRE(x && row_off && out, "sb_format_e2_rows: null argument");
+    SB_REQUIRE((prefix == nullptr) == (prefix_off == nullptr), "sb_format_e2_rows_prefixed: prefix and prefix_off go together");
     int dev = 0;
     SB_CHECK_CUDA(cudaGetDevice(&dev));
     long long blocks = (n_rows + kFmtWarps - 1) / kFmtWarps;
     const long long cap = (long long)sb_sm_count(dev) * 8;
     if (blocks > cap) blocks = cap;
     e2_rows_kernel<<<(int)blocks, kFmtWarps * 32, 0, (cudaStream_t)stream>>>(
-        x, n_rows, F, reinterpret_cast<const long long*>(row_off), out);
+        x, n_rows, F, reinterpret_cast<const long long*>(row_off), prefix, reinterpret_cast<const long long*>(prefix_off), out);
     SB_COUNT_LAUNCH();
     SB_CHECK_LAUNCH();
     return SB_OK;
+}
+
+extern "C" int sb_format_e2_rows(const float* x, int64_t n_rows, int F, const int64_t* row_off, uint8_t* out,
+                                 void* stream) {
+    return format_rows(x, n_rows, F, row_off, nullptr, nullptr, out, stream);
+}
+
+extern "C" int sb_format_e2_rows_prefixed(const float* x, int64_t n_rows, int F, const int64_t* row_off,
+                                          const uint8_t* prefix, const int64_t* prefix_off, uint8_t* out, void* stream) {
+    SB_REQUIRE(prefix && prefix_off, "sb_format_e2_rows_prefixed: null prefix");
+    return format_rows(x, n_rows, F, row_off, prefix, prefix_off, out, stream);
 }

@@ -59,10 +59,11 @@ def _scores_filepath(output_path_prefix, handler_filename):
     return output_path, filename_prefix, os.path.join(output_path, handler_filename)
 
 
-def format_e2_rows(data):
+def format_e2_rows(data, row_prefixes=None):
     """``"{:.2e}"`` text of a float32 score matrix, formatted on the device (handler.py:36-42).
     ``data``: (n, F) numpy array or CUDA tensor.  Returns (bytes of all rows as one uint8 numpy array, offsets
-    (n+1,) int64): row r is ``buf[off[r]:off[r+1]]`` = the values joined by tabs + a newline."""
+    (n+1,) int64): row r is ``buf[off[r]:off[r+1]]`` = the values joined by tabs + a newline, preceded by
+    ``row_prefixes[r]`` (bytes, e.g. the id columns and a tab) when given."""
     import torch
     lib = _lib.load()
     t = data if isinstance(data, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32))
@@ -72,25 +73,38 @@ def format_e2_rows(data):
         return np.zeros(0, np.uint8), np.zeros(1, np.int64)
     sizes = torch.empty(n, dtype=torch.int64, device=t.device)
     _lib.check(lib.sb_format_e2_row_bytes(_lib.ptr(t), n, F, _lib.ptr(sizes), _lib.stream_ptr()), "sb_format_e2_row_bytes")
+    pre = pre_off = None
+    if row_prefixes is not None:
+        if len(row_prefixes) != n:
+            raise ValueError("one prefix per row is needed")
+        lens = np.fromiter((len(p) for p in row_prefixes), dtype=np.int64, count=n)
+        po = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(lens, out=po[1:])
+        pre = torch.from_numpy(np.frombuffer(b"".join(row_prefixes), dtype=np.uint8).copy()).to(t.device)
+        pre_off = torch.from_numpy(po).to(t.device)
+        sizes += pre_off[1:] - pre_off[:-1]
     off = torch.zeros(n + 1, dtype=torch.int64, device=t.device)
     torch.cumsum(sizes, 0, out=off[1:])
     total = int(off[-1].item())
     buf = torch.empty(total, dtype=torch.uint8, device=t.device)
-    _lib.check(lib.sb_format_e2_rows(_lib.ptr(t), n, F, _lib.ptr(off), _lib.ptr(buf), _lib.stream_ptr()), "sb_format_e2_rows")
+    if pre is None:
+        _lib.check(lib.sb_format_e2_rows(_lib.ptr(t), n, F, _lib.ptr(off), _lib.ptr(buf), _lib.stream_ptr()),
+                   "sb_format_e2_rows")
+    else:
+        _lib.check(lib.sb_format_e2_rows_prefixed(_lib.ptr(t), n, F, _lib.ptr(off), _lib.ptr(pre), _lib.ptr(pre_off),
+                                                  _lib.ptr(buf), _lib.stream_ptr()), "sb_format_e2_rows_prefixed")
     return buf.cpu().numpy(), off.cpu().numpy()
 
 
 def write_tsv(path, columns_for_ids, features, ids, data, append=False):
-    """Rows ``id columns + "{:.2e}" per value`` (handler.py:36-42,99-114); the numbers are formatted by
-    ``sb_format_e2_rows`` on the device, the host only splices the id columns in."""
-    buf, off = format_e2_rows(data)
-    view = memoryview(buf)
+    """Rows ``id columns + "{:.2e}" per value`` (handler.py:36-42,99-114).  The whole file body — id columns and
+    numbers — is assembled by ``sb_format_e2_rows_prefixed`` on the device and written with one call."""
+    prefixes = [("\t".join(str(i) for i in info) + "\t").encode() for info in ids]
+    buf, _off = format_e2_rows(data, prefixes)
     with open(path, "ab" if append else "wb") as fh:
         if not append:
             fh.write("{0}\n".format("\t".join(list(columns_for_ids) + list(features))).encode())
-        for r, info in enumerate(ids):
-            fh.write(("\t".join(str(i) for i in info) + "\t").encode())
-            fh.write(view[off[r]:off[r + 1]])
+        fh.write(memoryview(buf))
 
 
 def write_hdf5(path, data):

@@ -703,6 +703,14 @@ def test_format_e2_matches_python(torch):
             raise AssertionError("row %d differs: %r" % (bad[0], diff))
     buf, off = format_e2_rows(np.zeros((0, 5), np.float32))
     assert buf.size == 0 and off.tolist() == [0]
+    # id columns spliced in on the device (sb_format_e2_rows_prefixed), empty and long prefixes included
+    pre = [b"", b"12\tA\tC\t", b"x" * 70 + b"\t", b"chr1\t1000\trs1\tA\tG\t"] * 8
+    a = small[:32, :40]
+    buf, off = format_e2_rows(a, pre)
+    exp = _py_rows(a)
+    for i in range(32):
+        assert bytes(buf[off[i]:off[i + 1]]) == pre[i] + exp[i].encode()
+    assert bytes(buf) == b"".join(p + e.encode() for p, e in zip(pre, exp))
 
 
 def test_tsv_writer_uses_device_formatter(torch, tmp_path):
