@@ -476,6 +476,12 @@ extern "C" int sb_net_forward_backward(sb_net* net, const float* x, const float*
     return SB_OK;
 }
 
+// sb_train_tc.inl: SGD update of layer li's weights fused with the bf16 repacking the tcgen05 training step needs
+// (returns false when the tensor-core training state does not exist)
+static bool sgd_pack_layer_tc(sb_net* net, size_t li, const float* g, float lr, float momentum, float weight_decay,
+                              int first, cudaStream_t s);
+static void sgd_pack_done_tc(sb_net* net);
+
 extern "C" int sb_net_sgd_step(sb_net* net, const float* grads, float lr, float momentum, float weight_decay,
                                void* stream) {
     SB_REQUIRE(net && net->train && grads, "sb_net_sgd_step: call sb_net_train_init first");
@@ -486,14 +492,16 @@ extern "C" int sb_net_sgd_step(sb_net* net, const float* grads, float lr, float 
     for (size_t li = 0; li < net->layers.size(); ++li) {
         NetLayer& N = net->layers[li];
         const long long nw = (long long)N.k_f32 * N.ldw_f32, nb = N.ldw_f32;
-        sgd_kernel<<<grid_for(nw, net->device), 256, 0, s>>>(N.wf, T->mom_w[li], grads + T->goff_w[li], nw, lr, momentum,
-                                                             weight_decay, first);
+        if (!(li > 0 && sgd_pack_layer_tc(net, li, grads + T->goff_w[li], lr, momentum, weight_decay, first, s)))
+            sgd_kernel<<<grid_for(nw, net->device), 256, 0, s>>>(N.wf, T->mom_w[li], grads + T->goff_w[li], nw, lr, momentum,
+                                                                 weight_decay, first);
         sgd_kernel<<<grid_for(nb, net->device), 256, 0, s>>>(N.biasf, T->mom_b[li], grads + T->goff_b[li], nb, lr, momentum,
                                                              weight_decay, first);
         SB_COUNT_LAUNCH();
         SB_COUNT_LAUNCH();
     }
     SB_CHECK_LAUNCH();
+    sgd_pack_done_tc(net);
     T->steps += 1;
     net->inference_weights_stale = true;
     return SB_OK;

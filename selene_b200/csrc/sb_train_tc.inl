@@ -61,6 +61,48 @@ __global__ void __launch_bounds__(256) pack_fwd_kernel(const float* __restrict__
     }
 }
 
+// SGD update (torch.optim.SGD with momentum and weight decay, as sgd_kernel) of one layer's fp32 master weights fused
+// with both repackings above: one pass over w / momentum / gradient instead of three passes over w.
+__global__ void __launch_bounds__(256) sgd_pack_kernel(float* __restrict__ wf, float* __restrict__ v, const float* __restrict__ g,
+                                                       int ldw, long long K, int cout, float lr, float mom, float wd, int first,
+                                                       int ch, int ch_ld, bf16* __restrict__ wb, int w_ld, int taps, int C,
+                                                       int cout_ld, bf16* __restrict__ wt, int wt_ld) {
+    __shared__ float tile[32][33];
+    const long long k0 = (long long)blockIdx.x * 32;
+    const int o0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const long long kk = k0 + r;
+        const int o = o0 + tx;
+        float wn = 0.f;
+        if (kk < K && o < ldw) {
+            const long long i = kk * ldw + o;
+            const float gi = g[i] + wd * wf[i];
+            const float vi = first ? gi : mom * v[i] + gi;
+            v[i] = vi;
+            wn = wf[i] - lr * vi;
+            wf[i] = wn;
+            if (o < cout) {   // dgrad operand, same orientation: wt[c][tap' * cout_ld + o], taps flipped
+                const int c = (int)(kk % C);
+                const int tp = taps - 1 - (int)(kk / C);
+                wt[(long long)c * wt_ld + (long long)tp * cout_ld + o] = __float2bfloat16_rn(wn);
+            }
+        }
+        tile[r][tx] = wn;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {   // forward operand, transposed: wb[o][col(kk)]
+        const int o = o0 + r;
+        const long long kk = k0 + tx;
+        if (o < cout && kk < K) {
+            const long long col = (kk / ch) * ch_ld + kk % ch;
+            wb[(long long)o * w_ld + col] = __float2bfloat16_rn(tile[tx][r]);
+        }
+    }
+}
+
 // dgrad B operand: wt[c][tap'*cout_ld + o] = W[(taps-1-tap')*C + c][o]   (taps = 1: plain W^T rows)
 __global__ void __launch_bounds__(256) pack_dgrad_kernel(const float* __restrict__ wf, int ldw, int taps, int C, int cout,
                                                          int cout_ld, bf16* __restrict__ wt, int wt_ld) {
@@ -258,6 +300,7 @@ struct TcTrainLayer {
 
 struct sb_train_tc_state {
     std::vector<TcTrainLayer> L;
+    bool packed_fresh;   // the bf16 operands match the fp32 master weights (sb_net_sgd_step repacks while it updates)
 };
 
 namespace {
@@ -329,6 +372,7 @@ extern "C" int sb_net_train_init_tc(sb_net* net) {
     const char* why = "";
     SB_REQUIRE(tc_trainable(net, &why), "sb_net_train_init_tc: unsupported on the tcgen05 training path (%s); use fp32", why);
     sb_train_tc_state* S = new sb_train_tc_state();
+    S->packed_fresh = false;
     S->L.resize(net->layers.size());
     size_t max_cols = 256;
     for (size_t li = 1; li < net->layers.size(); ++li) {
@@ -379,8 +423,8 @@ extern "C" int sb_net_forward_backward_tc(sb_net* net, const float* x, const flo
     auto ext_mask = [&](size_t li) -> const float* { return dropout_masks ? dropout_masks[li] : nullptr; };
     auto seed_of = [&](size_t li) { return dropout_seed * 1315423911ull + li; };
 
-    // ---- repack the bf16 operands from the fp32 master weights (they changed in the last SGD step)
-    for (size_t li = 1; li < L; ++li) {
+    // ---- repack the bf16 operands from the fp32 master weights unless the last SGD step already did
+    for (size_t li = 1; li < L && !S->packed_fresh; ++li) {
         const NetLayer& N = net->layers[li];
         const bool conv = N.type == SB_LAYER_CONV;
         const int ch = conv ? N.cin : (N.fc_prev_c > 0 ? N.fc_prev_c : N.cin);
@@ -541,4 +585,25 @@ extern "C" int sb_net_forward_backward_tc(sb_net* net, const float* x, const flo
         SB_CHECK_LAUNCH();
     }
     return SB_OK;
+}
+
+
+static bool sgd_pack_layer_tc(sb_net* net, size_t li, const float* g, float lr, float momentum, float weight_decay,
+                              int first, cudaStream_t s) {
+    if (!net->train_tc || li == 0 || li >= net->train_tc->L.size()) return false;
+    const char* off = getenv("SB_SGD_FUSED_PACK");   // "0": plain SGD kernel, repack at the start of the next step
+    if (off && off[0] == '0') return false;
+    const NetLayer& N = net->layers[li];
+    const TcTrainLayer& T = net->train_tc->L[li];
+    const bool conv = N.type == SB_LAYER_CONV;
+    const int ch = conv ? N.cin : (N.fc_prev_c > 0 ? N.fc_prev_c : N.cin);
+    sgd_pack_kernel<<<dim3((unsigned)((N.k_f32 + 31) / 32), (unsigned)((N.ldw_f32 + 31) / 32)), 256, 0, s>>>(
+        N.wf, net->train->mom_w[li], g, N.ldw_f32, N.k_f32, N.cout, lr, momentum, weight_decay, first, ch, round_up(ch, 8),
+        N.wb, N.w_ld, conv ? N.k : 1, N.cin, T.cout_ld, T.wt, T.wt_ld);
+    return true;
+}
+
+static void sgd_pack_done_tc(sb_net* net) {
+    const char* off = getenv("SB_SGD_FUSED_PACK");
+    if (net->train_tc) net->train_tc->packed_fresh = !(off && off[0] == '0');
 }

@@ -152,3 +152,31 @@ def test_train_step_tcgen05_close_to_torch(with_masks):
         got_losses.append(float(tr.loss.item()))
     assert np.allclose(got_losses, ref_losses, rtol=0, atol=1e-3), (got_losses, ref_losses)
     assert got_losses[-1] < got_losses[0]
+
+
+def test_fused_sgd_repack_equals_separate_passes(monkeypatch):
+    """sb_net_sgd_step on the tensor-core path updates the fp32 master weights AND rewrites both bf16 operand layouts
+    in one kernel; the loss trajectory and the weights must equal those of the plain SGD kernel + repacking passes (up
+    to the run-to-run noise of the atomically accumulated gradients and loss, ~1e-7)."""
+    import torch
+    import sb_models as M
+    from selene_b200.train_model import B200Trainer
+    rng = np.random.default_rng(11)
+    n = 4
+    codes = rng.integers(0, 4, (n, 1000))
+    x = np.zeros((n, 1000, 4), np.float32)
+    for b in range(4):
+        x[codes == b, b] = 1
+    y = (rng.random((n, 919)) < 0.1).astype(np.float32)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    runs = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("SB_SGD_FUSED_PACK", fused)
+        torch.manual_seed(3)
+        tr = B200Trainer(M.DeepSEA(1000, 919), 1000, lr=0.1, momentum=0.9, weight_decay=1e-4, precision="bf16")
+        losses = [tr.step(xd, yd) for _ in range(5)]
+        w, b = tr.layer_params(3)
+        runs.append((losses, w.copy(), b.copy()))
+    assert np.allclose(runs[0][0], runs[1][0], rtol=0, atol=2e-6), (runs[0][0], runs[1][0])
+    assert np.abs(runs[0][1] - runs[1][1]).max() <= 2e-6 and np.abs(runs[0][2] - runs[1][2]).max() <= 2e-6
+    assert runs[0][0][-1] < runs[0][0][0]
