@@ -103,14 +103,14 @@ __device__ __forceinline__ void finish_chunk(const uint32_t (&r)[4][16], const f
 }
 
 template <int POOL>
-__global__ void __launch_bounds__(288, 1) conv1_tc_kernel(const Conv1Params p) {
+__global__ void __launch_bounds__(288, POOL == 4 ? 1 : 2) conv1_tc_kernel(const Conv1Params p) {
     extern __shared__ uint8_t smem_raw[];
     // pointer arithmetic on the __shared__ array (not an integer round trip) keeps the shared address
     // space visible to the compiler: LDS/STS instead of generic LD/ST
     uint8_t* smem = smem_raw + ((1024u - (sb_smem_u32(smem_raw) & 1023u)) & 1023u);
     // layout: [A buf0: 4 x 8 KB][A buf1: 4 x 8 KB][B: n_pass x 4 KB][bias][codes x2][barriers]
     uint8_t* a_buf = smem;
-    uint8_t* b_smem = smem + 2 * kMaxPool * kATileBytes;
+    uint8_t* b_smem = smem + 2 * POOL * kATileBytes;
     float* bias_s = reinterpret_cast<float*>(b_smem + p.n_pass * kPassN * kRowBytes);
     uint8_t* codes_s = reinterpret_cast<uint8_t*>(bias_s + p.n_pass * kPassN);
     uint8_t* stage_s = codes_s + kMaxCodes;                              // [2][128 rows][kStagePitch]
@@ -132,7 +132,10 @@ __global__ void __launch_bounds__(288, 1) conv1_tc_kernel(const Conv1Params p) {
         }
         sb_fence_mbar_init();
     }
-    if (warp == 8) sb_tmem_alloc(tmem_slot, 512);
+    // 2 accumulator stages x POOL x 64 columns: pool 1 / 2 leave tensor memory (and shared memory) for a second or
+    // third CTA on the SM, whose builder / MMA / epilogue phases then interleave with this one's
+    constexpr uint32_t kTmem = 2 * POOL * kPassN;
+    if (warp == 8) sb_tmem_alloc(tmem_slot, kTmem);
     // weights + bias -> smem (once per CTA)
     {
         const int n16 = p.n_pass * kPassN * kRowBytes / 16;
@@ -164,10 +167,10 @@ __global__ void __launch_bounds__(288, 1) conv1_tc_kernel(const Conv1Params p) {
                     sb_mbar_wait(&tempty[stage], ((gpass >> 1) & 1) ^ 1);
                     sb_tc_fence_after();
                     for (int q = 0; q < p.pool; ++q) {
-                        const uint32_t d = tmem_base + stage * 256 + q * kPassN;
+                        const uint32_t d = tmem_base + stage * (POOL * kPassN) + q * kPassN;
                         for (int ks = 0; ks < ksteps; ++ks) {
                             // one K step = 2 core matrices = 256 B along K
-                            const uint64_t da = desc_nosw(a_addr + (buf * kMaxPool + q) * kATileBytes + ks * 256);
+                            const uint64_t da = desc_nosw(a_addr + (buf * POOL + q) * kATileBytes + ks * 256);
                             const uint64_t db = desc_nosw(b_addr + pass * (kPassN * kRowBytes) + ks * 256);
                             sb_umma_bf16(d, da, db, idesc, ks > 0 ? 1u : 0u);
                         }
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(288, 1) conv1_tc_kernel(const Conv1Params p) {
                 const int c = (k < p.pool + 7) ? cs[p.pool * i + k] : 4;
                 pat[k] = tap_pattern(c);
             }
-            uint8_t* a_row = a_buf + (size_t)buf * kMaxPool * kATileBytes + (i >> 3) * 512 + (i & 7) * 16;
+            uint8_t* a_row = a_buf + (size_t)buf * POOL * kATileBytes + (i >> 3) * 512 + (i & 7) * 16;
 #pragma unroll
             for (int q = 0; q < kMaxPool; ++q) {
                 // the two halves split the q blocks between them (pool 4: {0,1} / {2,3}; pool 2: {0} / {1})
@@ -244,7 +247,7 @@ __global__ void __launch_bounds__(288, 1) conv1_tc_kernel(const Conv1Params p) {
                 const uint32_t stage = gpass & 1;
                 sb_mbar_wait(&tfull[stage], (gpass >> 1) & 1);
                 sb_tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + stage * 256;
+                const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + stage * (POOL * kPassN);
                 // this warp's two 16-column chunks of the pass; the second chunk's TMEM loads are in
                 // flight while the first is finished
                 const int c0 = half, c1 = half + 2;
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(288, 1) conv1_tc_kernel(const Conv1Params p) {
     __syncthreads();
     if (warp == 8) {
         sb_tc_fence_after();
-        sb_tmem_dealloc(tmem_base, 512);
+        sb_tmem_dealloc(tmem_base, 2 * POOL * kPassN);
     }
 }
 
@@ -326,20 +329,27 @@ int sb_conv1_tc_launch(const uint8_t* codes, const int32_t* src, const int32_t* 
     p.wpacked = reinterpret_cast<const uint4*>(wpacked);
     p.bias = bias_padded;
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
-    size_t smem = 1024 + 2 * kMaxPool * kATileBytes + (size_t)p.n_pass * kPassN * (kRowBytes + 4) + kMaxCodes +
+    size_t smem = 1024 + 2 * (size_t)pool * kATileBytes + (size_t)p.n_pass * kPassN * (kRowBytes + 4) + kMaxCodes +
                   2 * kRows * kStagePitch + 64 + 64;
-    if (smem < 120 * 1024) smem = 120 * 1024;  // one CTA per SM: each CTA owns all 512 TMEM columns
+    if (pool == 4 && smem < 120 * 1024) smem = 120 * 1024;  // pool 4: one CTA per SM, it owns all 512 TMEM columns
+    const int per_sm = pool == 4 ? 1 : 2;     // pool 1 / 2: two CTAs fit (tensor memory 128-256 columns each, 108 registers x 288 threads)
     SB_REQUIRE(smem <= 220 * 1024, "sb_conv1_tc_launch: %zu bytes of shared memory needed", smem);
     static size_t attr = 0;
     if (smem > attr) {
         SB_CHECK_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SB_CHECK_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         SB_CHECK_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // two CTAs per SM for pool 1 / 2 need the large shared-memory carve-out even though one CTA would fit a small one
+        SB_CHECK_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           cudaSharedmemCarveoutMaxShared));
+        SB_CHECK_CUDA(cudaFuncSetAttribute(conv1_tc_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           cudaSharedmemCarveoutMaxShared));
         attr = smem;
     }
     const long long tiles = n_rows * p.tiles_per_seq;
     const int sms = sb_sm_count(device);
-    const int grid = (int)(tiles < sms ? tiles : sms);
+    const long long ctas = (long long)sms * per_sm;
+    const int grid = (int)(tiles < ctas ? tiles : ctas);
     if (pool == 4) conv1_tc_kernel<4><<<grid, 288, smem, stream>>>(p);
     else if (pool == 2) conv1_tc_kernel<2><<<grid, 288, smem, stream>>>(p);
     else conv1_tc_kernel<1><<<grid, 288, smem, stream>>>(p);

@@ -46,6 +46,10 @@ struct TcParams {
     int block_n, n_tiles_n, n_tiles_m, num_k_blocks;
     int chunks_per_tap;  // 0: overlapping-stride A view; >0: per-tap boxes
     int stages, stage_bytes;   // smem ring: stage = A tile (16 KB) + B tile (block_n x 128 B)
+    // narrow layers (block_n <= 128) run TWO CTAs per SM: half the ring, 256 TMEM columns (2 x 128) each.  One
+    // issuing thread needs ~600 cycles per k-block (wait, descriptors, 4 MMAs, commit) but a 128 x 64 x 64 k-block
+    // is only ~190 tensor-pipe cycles: the second CTA's issuer fills the gap
+    int ring_bytes, tmem_cols, acc_stride;
     const float* bias;
     void* out;
     SbScoreEpilogue sc;
@@ -80,7 +84,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (sb_smem_u32(smem_raw) & 1023u)) & 1023u);  // stays a shared pointer
-    uint8_t* aux = smem + kRingBytes;
+    uint8_t* aux = smem + p.ring_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tfull_bar = empty_bar + kMaxStages;
@@ -107,7 +111,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
         sb_fence_mbar_init();
     }
-    if (warp == 2) sb_tmem_alloc(tmem_slot, kTmemCols);
+    if (warp == 2) sb_tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     sb_tc_fence_before();
     __syncthreads();
     sb_tc_fence_after();
@@ -149,7 +153,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 const uint32_t as = it & 1, aphase = (it >> 1) & 1;
                 sb_mbar_wait(&tempty_bar[as], aphase ^ 1);
                 sb_tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * kMaxN;
+                const uint32_t tmem_d = tmem_base + as * p.acc_stride;
                 for (int kb = 0; kb < p.num_k_blocks; ++kb) {
                     sb_mbar_wait(&full_bar[stage], phase);
                     sb_tc_fence_after();
@@ -192,7 +196,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
             sb_mbar_wait(&tfull_bar[as], aphase);
             sb_tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * kMaxN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * p.acc_stride;
             const int n_chunks = p.block_n / 16;
             for (int c = 0; c < n_chunks; ++c) {
                 const int nb = n0 + c * 16;
@@ -308,7 +312,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     __syncthreads();
     if (warp == 2) {
         sb_tc_fence_after();
-        sb_tmem_dealloc(tmem_base, kTmemCols);
+        sb_tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
 }
 
@@ -403,8 +407,13 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbSc
     p.n_tiles_m = (int)((L.rows_a + kBlockM - 1) / kBlockM);
     p.num_k_blocks = (L.k_full + kBlockK - 1) / kBlockK;
     p.chunks_per_tap = chunks_per_tap;
+    const char* narrow_env = getenv("SB_TC_NARROW");
+    const bool narrow = L.block_n <= 128 && !(narrow_env && narrow_env[0] == '0');
+    p.ring_bytes = narrow ? kRingBytes / 2 : kRingBytes;
+    p.tmem_cols = narrow ? 256 : kTmemCols;
+    p.acc_stride = narrow ? 128 : kMaxN;
     p.stage_bytes = kABytes + L.block_n * kBlockK * 2;
-    p.stages = kRingBytes / p.stage_bytes;
+    p.stages = p.ring_bytes / p.stage_bytes;
     if (p.stages > kMaxStages) p.stages = kMaxStages;
     p.bias = L.bias;
     p.out = L.out;
@@ -419,8 +428,10 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbSc
     }
     const int64_t tiles = (int64_t)p.n_tiles_m * p.n_tiles_n;
     const int sms = sb_sm_count(device);
-    const int grid = (int)(tiles < sms ? tiles : sms);
-    tc_layer_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tm_a, tm_b, p);
+    const int ctas = narrow ? 2 * sms : sms;
+    const int grid = (int)(tiles < ctas ? tiles : ctas);
+    const int smem_bytes = p.ring_bytes + kAuxBytes + 1024;
+    tc_layer_kernel<<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, p);
     SB_COUNT_LAUNCH();
     SB_CHECK_LAUNCH();
     return SB_OK;
