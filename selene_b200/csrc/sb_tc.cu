@@ -424,6 +424,9 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbSc
     if (!attr_set) {
         SB_CHECK_CUDA(cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kSmemBytes));
+        // narrow layers put two CTAs of ~103 KB on an SM: ask for the largest shared-memory carve-out
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     const int64_t tiles = (int64_t)p.n_tiles_m * p.n_tiles_n;
