@@ -752,9 +752,14 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
     return SB_OK;
 }
 
+static void free_train_states(sb_net* net);   // sb_train_tc.inl (the training structs are defined there)
+
 extern "C" int sb_net_destroy(sb_net* net) {
     if (!net) return SB_OK;
     cudaSetDevice(net->device);
+    free_train_states(net);
+    for (auto& v : net->ev)
+        for (cudaEvent_t e : v) cudaEventDestroy(e);
     for (auto& g : net->lstm_graphs) cudaGraphExecDestroy(g.exec);
     if (net->capture_stream) cudaStreamDestroy(net->capture_stream);
     for (auto& N : net->layers) {

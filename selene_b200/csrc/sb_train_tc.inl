@@ -607,3 +607,20 @@ static void sgd_pack_done_tc(sb_net* net) {
     const char* off = getenv("SB_SGD_FUSED_PACK");
     if (net->train_tc) net->train_tc->packed_fresh = !(off && off[0] == '0');
 }
+
+// momentum buffers, dgrad operands and the zero bias of the training paths (sb_net_destroy)
+static void free_train_states(sb_net* net) {
+    if (net->train) {
+        for (float* p : net->train->mom_w) cudaFree(p);
+        for (float* p : net->train->mom_b) cudaFree(p);
+        delete net->train;
+        net->train = nullptr;
+    }
+    if (net->train_tc) {
+        for (auto& T : net->train_tc->L) cudaFree(T.wt);
+        delete net->train_tc;
+        net->train_tc = nullptr;
+    }
+    cudaFree(net->zero_bias_tc);
+    net->zero_bias_tc = nullptr;
+}
