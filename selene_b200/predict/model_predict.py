@@ -141,10 +141,34 @@ def _write_outputs(results, ids, features, cols, output_path_prefix, output_form
                 labels_written = True
 
 
+_PINNED = {}   # (name, shape, dtype) -> persistent pinned staging tensor (allocating pinned memory per call is slow)
+
+
 def _to_host(tensors):
-    """Device -> host as fresh numpy arrays (what the reference's handlers receive)."""
+    """Device -> host as fresh numpy arrays (what the reference's handlers receive): all copies go through
+    persistent pinned staging buffers and are in flight together, then one synchronisation and a host copy each
+    (a pageable ``.cpu()`` of 22 MB of ISM scores runs at ~6 GB/s)."""
     import torch
-    return {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in tensors.items()}
+    staged = {}
+    for k, v in tensors.items():
+        if isinstance(v, torch.Tensor) and v.is_cuda and v.numel() >= (1 << 16):
+            key = (k, tuple(v.shape), v.dtype)
+            h = _PINNED.get(key)
+            if h is None:
+                if len(_PINNED) >= 16:
+                    _PINNED.clear()
+                h = _PINNED[key] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+            h.copy_(v, non_blocking=True)
+            staged[k] = h
+    if staged:
+        torch.cuda.current_stream().synchronize()
+    out = {}
+    for k, v in tensors.items():
+        if k in staged:
+            out[k] = staged[k].numpy().copy()
+        else:
+            out[k] = v.cpu().numpy() if isinstance(v, torch.Tensor) else v
+    return out
 
 
 class AnalyzeSequences(object):
