@@ -265,6 +265,17 @@ def main():
                     tr.step(xb, yb)
                 torch.cuda.synchronize()
                 dt_ = (time.perf_counter() - t0) / ns
+                # the same with the next batch drawn while the GPU steps (loss of every step still read on the host)
+                t0 = time.perf_counter()
+                nxt = smp.sample_device(64, seq_dtype="float32", label_dtype="float32")
+                for _ in range(ns):
+                    tr.step_async(*nxt)
+                    nxt = smp.sample_device(64, seq_dtype="float32", label_dtype="float32")
+                    tr.loss_value()
+                torch.cuda.synchronize()
+                dt_pipe = (time.perf_counter() - t0) / ns
+                emit(config="3: sample + training step end to end, next batch drawn during the step", precision=prec, batch=64,
+                     seconds_per_step=dt_pipe, samples_per_s=64 / dt_pipe)
                 emit(config="3: sample + training step end to end (RandomPositionsSampler -> step -> loss to host)",
                      precision=prec, batch=64, seconds_per_step=dt_, samples_per_s=64 / dt_)
             del tr

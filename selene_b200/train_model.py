@@ -131,6 +131,19 @@ class B200Trainer(object):
                                              _lib.stream_ptr()), "sb_net_sgd_step")
         self.step_count += 1
 
+    def step_async(self, inputs, targets, masks=None):
+        """Enqueues one optimisation step and returns without synchronising; read the loss with ``loss_value()``
+        (before the next step overwrites it).  Lets the host draw the next batch while the GPU steps."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            self._enable_overlap()
+        self.forward_backward(inputs, targets, masks)
+        self.allreduce_grads()
+        self.sgd_step()
+
+    def loss_value(self):
+        return float(self.loss.item())
+
     def step(self, inputs, targets, masks=None):
         """One optimisation step; returns the mean BCE loss as a python float (device -> host read)."""
         import torch.distributed as dist
@@ -179,8 +192,22 @@ class TrainModel(object):
         self._time_per_step, self._train_loss = [], []
 
     def train(self):
-        """train_model.py:469-508."""
+        """train_model.py:469-508.  With ``self.prefetch`` (off by default: it draws batch i+1 before the loss of
+        step i is read, i.e. one batch ahead of the reference's call order) the host-side sampling overlaps the
+        GPU step."""
         t_i = time()
+        if getattr(self, "prefetch", False):
+            if getattr(self, "_next_batch", None) is None:
+                self._next_batch = self.sampler.sample_device(self.batch_size, seq_dtype="float32", label_dtype="float32")
+            inputs, targets = self._next_batch
+            self.trainer.step_async(inputs, targets)
+            self._next_batch = self.sampler.sample_device(self.batch_size, seq_dtype="float32", label_dtype="float32")
+            t_sampling = time() - t_i
+            loss = self.trainer.loss_value()
+            self._train_loss.append(loss)
+            self._time_per_step.append(time() - t_i)
+            self.step += 1
+            return loss, t_sampling
         inputs, targets = self.sampler.sample_device(self.batch_size, seq_dtype="float32", label_dtype="float32")
         t_sampling = time() - t_i
         loss = self.trainer.step(inputs, targets)
