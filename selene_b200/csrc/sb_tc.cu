@@ -186,13 +186,15 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             asm volatile("bar.sync 1, 128;" ::: "memory");
 
             // output row of this lane's pool window
-            const long long r = (long long)m0 + row_in_tile;
-            const long long rg = r - (r % p.pool);  // first row of the pool window
-            const long long seq = rg / p.t_in;
-            const int t = (int)(rg - seq * p.t_in);
-            const int tp = t / p.pool;
-            const bool valid = (rg < p.rows_a) && (tp < p.t_pool);
-            const long long out_row = seq * p.out_pitch + tp;
+            // (32-bit arithmetic: rows_a < 2^31 is checked at launch; pool is 1, 2 or 4 and t_in % pool == 0, so the
+            // window start is a mask and the only division left is the one by t_in)
+            const uint32_t r = (uint32_t)m0 + (uint32_t)row_in_tile;
+            const uint32_t rg = r & ~(uint32_t)(p.pool - 1);  // first row of the pool window
+            const uint32_t seq = rg / (uint32_t)p.t_in;
+            const int t = (int)(rg - seq * (uint32_t)p.t_in);
+            const int tp = p.pool == 4 ? t >> 2 : (p.pool == 2 ? t >> 1 : t);
+            const bool valid = ((long long)rg < p.rows_a) && (tp < p.t_pool);
+            const long long out_row = (long long)seq * p.out_pitch + tp;
 
             sb_mbar_wait(&tfull_bar[as], aphase);
             sb_tc_fence_after();
@@ -371,6 +373,8 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbSc
                "sb_tc_launch: bad out_ld %d / missing score epilogue", L.out_ld);
     SB_REQUIRE(!(L.out_f32 && L.pool != 1), "sb_tc_launch: fp32 output cannot pool");
     if (L.rows_a <= 0) return SB_OK;
+    SB_REQUIRE(L.rows_a < (1ll << 31) - 256, "sb_tc_launch: %lld rows exceed the 32-bit row arithmetic of the epilogue",
+               (long long)L.rows_a);
 
     // The last rows' windows would run past the buffer: shrink the row count so TMA zero-fills them
     // (they are windows that straddle the end of the last sequence and are dropped anyway).
