@@ -21,6 +21,12 @@
 //     projection (+ bias) written by the projection GEMM as bf16 in the same permuted column order, so the 64
 //     bytes one thread needs per tile are contiguous; every thread loads its own one tile ahead into
 //     registers (and prefetches the next step's line into L2 a whole step ahead).
+//
+// Small chunks (<= SMs/4 unit tiles, e.g. a 3000-mutant ISM) launch CLUSTERS of two CTAs per unit tile: each CTA
+// computes the gate columns of half of the hidden units (half of the MMA tiles, half of W_hh, half of the cell
+// math per step) and writes its half of h_s into BOTH CTAs' shared memory (st.shared::cluster through mapa);
+// the per-step barrier counts the arrivals of both CTAs (mbarrier.arrive.release.cluster on the peer's barrier,
+// try_wait.acquire.cluster + fence.proxy.async before the MMAs that read the peer-written rows).
 #include "sb_common.cuh"
 
 #include <cuda.h>
@@ -49,6 +55,7 @@ struct LstmParams {
     int kblocks;             // H / 64
     int n_sub;               // H / 16 sub-tiles
     int n_tiles;             // n_sub / 2 MMA tiles
+    int csize;               // CTAs per unit tile (cluster size 1 or 2): each takes n_tiles / csize tiles of every step
     const __nv_bfloat16* xw; // (m_rows*T, 8H) bf16, permuted columns, bias included
     __nv_bfloat16* out;      // (m_rows*T, out_ld)
     int out_ld;
@@ -83,12 +90,18 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int dir = blockIdx.y;
     const CUtensorMap* tmap_w = dir == 0 ? &tmap_w0 : &tmap_w1;
+    // cluster of `csize` CTAs per unit tile: CTA `crank` computes the gate columns of hidden units
+    // [crank, crank + 1) * H / csize and writes its part of h_s into EVERY CTA's shared memory (DSMEM)
+    const uint32_t crank = p.csize > 1 ? sb_cluster_ctarank() : 0u;
+    const int tiles_local = p.n_tiles / p.csize;
+    const int tile_off = (int)crank * tiles_local;
+    const int sub_local = 2 * tiles_local, sub_off = 2 * tile_off;
 
     if (warp == 0 && lane == 0) sb_prefetch_tmap(tmap_w);
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kBStages; ++i) { sb_mbar_init(&b_full[i], 1); sb_mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < kAccStages; ++i) { sb_mbar_init(&tfull[i], 1); sb_mbar_init(&tempty[i], kEpiThreads); }
-        for (int i = 0; i < 2; ++i) sb_mbar_init(&h_ready[i], kEpiThreads);
+        for (int i = 0; i < 2; ++i) sb_mbar_init(&h_ready[i], kEpiThreads * p.csize);
         sb_fence_mbar_init();
     }
     if (warp == 2) sb_tmem_alloc(tmem_slot, 512);
@@ -97,6 +110,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
     sb_fence_proxy_async();
     sb_tc_fence_before();
     __syncthreads();
+    if (p.csize > 1) sb_cluster_sync();   // the peer's barriers and h buffers exist before anything remote touches them
     sb_tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -105,11 +119,11 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (int s = 0; s < p.steps; ++s)
-                for (int nt = 0; nt < p.n_tiles; ++nt)
+                for (int nt = 0; nt < tiles_local; ++nt)
                     for (int kb = 0; kb < p.kblocks; ++kb) {
                         sb_mbar_wait(&b_empty[stage], phase ^ 1);
                         sb_mbar_expect_tx(&b_full[stage], kBStageBytes);
-                        sb_tma_load_2d(bring + stage * kBStageBytes, tmap_w, &b_full[stage], kb * 64, nt * kNTile);
+                        sb_tma_load_2d(bring + stage * kBStageBytes, tmap_w, &b_full[stage], kb * 64, (tile_off + nt) * kNTile);
                         if (++stage == kBStages) { stage = 0; phase ^= 1; }
                     }
         }
@@ -120,12 +134,17 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
             const uint32_t idesc = sb_umma_idesc_bf16(kUnits, kNTile);
             uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
             for (int s = 0; s < p.steps; ++s) {
-                if (s > 0) {   // h_{s-1} has been written by the epilogue of step s-1
-                    sb_mbar_wait(&h_ready[s & 1], ((s - 1) >> 1) & 1);
+                if (s > 0) {   // h_{s-1} has been written by the epilogue of step s-1 (of every CTA of the cluster)
+                    if (p.csize > 1) {
+                        sb_mbar_wait_cluster(&h_ready[s & 1], ((s - 1) >> 1) & 1);
+                        sb_fence_proxy_async();   // the peer's generic-proxy writes -> this CTA's tensor core reads
+                    } else {
+                        sb_mbar_wait(&h_ready[s & 1], ((s - 1) >> 1) & 1);
+                    }
                     sb_tc_fence_after();
                 }
                 const uint32_t a_addr = sb_smem_u32(hA + (s & 1) * a_bytes);
-                for (int nt = 0; nt < p.n_tiles; ++nt) {
+                for (int nt = 0; nt < tiles_local; ++nt) {
                     sb_mbar_wait(&tempty[as], aphase ^ 1);
                     sb_tc_fence_after();
                     const uint32_t tmem_d = tmem_base + as * kNTile;
@@ -151,7 +170,7 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
         const int quad = warp & 3;                            // TMEM lane quadrant this warp may touch
         const int half = (warp - 2) >> 2;
         const int r = quad * 32 + lane;                       // row of the tile = unit
-        const long long unit = (long long)blockIdx.x * kUnits + r;
+        const long long unit = (long long)(blockIdx.x / p.csize) * kUnits + r;
         // unit -> (chain, position) -> rows of the chunk
         long long first = 0;
         int len = 0, pos = 0;
@@ -181,13 +200,14 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
             }
         };
         uint4 xn[4] = {};
-        int fs = 0, fst = 0;   // next sub-tile to fetch
-        fetch(0, 0, xn);
-        if (++fst == p.n_sub) { fst = 0; ++fs; }
+        int fs = 0, fst = 0;   // next (local) sub-tile to fetch
+        fetch(0, sub_off, xn);
+        if (++fst == sub_local) { fst = 0; ++fs; }
         float creg[kCRegSubTiles * 8];   // c of the hidden units beyond kCTmemHidden (DanQ: 256..319)
 #pragma unroll
         for (int i = 0; i < kCRegSubTiles * 8; ++i) creg[i] = 0.f;
-        const int n_tmem_sub = (p.H < kCTmemHidden ? p.H : kCTmemHidden) / kHidPerSub;   // sub-tiles with c in TMEM
+        const int h_local = p.H / p.csize;                                               // hidden units of this CTA
+        const int n_tmem_sub = (h_local < kCTmemHidden ? h_local : kCTmemHidden) / kHidPerSub;   // (local) sub-tiles with c in TMEM
 
         uint32_t as = 0, aphase = 0;
         for (int s = 0; s < p.steps; ++s) {
@@ -199,16 +219,17 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
             uint8_t* hnext = hA + ((s + 1) & 1) * a_bytes;
 
             // one 64-column sub-tile (16 hidden units, this thread: 8 of them); RS >= 0: c in creg[RS*8 ...]
-            auto sub_tile = [&](int st, uint32_t acc_col, bool release, auto rs_tag) {
+            auto sub_tile = [&](int st_local, uint32_t acc_col, bool release, auto rs_tag) {
                 constexpr int RS = decltype(rs_tag)::value;
+                const int st = sub_off + st_local;       // sub-tile of the whole hidden state
                 if (nxt) sb_prefetch_l2(nxt + st * kSubTile);
                 uint4 xv[4];   // gates i, f, g, o: 8 bf16 each
 #pragma unroll
                 for (int g = 0; g < 4; ++g) xv[g] = xn[g];
-                if (fs < p.steps) fetch(fs, fst, xn);   // the next sub-tile
-                if (++fst == p.n_sub) { fst = 0; ++fs; }
+                if (fs < p.steps) fetch(fs, sub_off + fst, xn);   // the next sub-tile
+                if (++fst == sub_local) { fst = 0; ++fs; }
                 const uint32_t taddr = tmem_base + lane_bits + acc_col + half * 32;
-                const uint32_t caddr = tmem_base + lane_bits + kAccCols + st * kHidPerSub + half * 8;
+                const uint32_t caddr = tmem_base + lane_bits + kAccCols + st_local * kHidPerSub + half * 8;
                 uint32_t ri[8], rf[8], rg[8], ro[8], rc[8];
                 sb_tmem_ld8(taddr + 0, ri);
                 sb_tmem_ld8(taddr + 8, rf);
@@ -251,7 +272,9 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
                 const int k0 = st * kHidPerSub + half * 8;          // first hidden unit of this thread's group
                 if (live) *reinterpret_cast<uint4*>(orow + st * kHidPerSub) = hq;   // layer output (bf16, 16 bytes)
                 // h_s into the other A copy: k-block k0/64, 128-byte rows, 16-byte chunks XOR-swizzled by row&7
-                *reinterpret_cast<uint4*>(hnext + (k0 >> 6) * (kUnits * 128) + r * 128 + ((((k0 & 63) >> 3) ^ (r & 7)) << 4)) = hq;
+                uint8_t* hdst = hnext + (k0 >> 6) * (kUnits * 128) + r * 128 + ((((k0 & 63) >> 3) ^ (r & 7)) << 4);
+                *reinterpret_cast<uint4*>(hdst) = hq;
+                if (p.csize > 1) sb_st_cluster_v4(sb_mapa(sb_smem_u32(hdst), crank ^ 1u), hq);   // the peer needs all of h_s
             };
             // one 128-column MMA tile = sub-tiles 2 nt and 2 nt + 1
             auto tile = [&](int nt, auto rs0, auto rs1) {
@@ -263,18 +286,20 @@ lstm_persistent_kernel(const __grid_constant__ CUtensorMap tmap_w0, const __grid
                 if (++as == kAccStages) { as = 0; aphase ^= 1; }
             };
             using Tm = std::integral_constant<int, -1>;
-            const int n_tmem_tiles = n_tmem_sub / 2 < p.n_tiles ? n_tmem_sub / 2 : p.n_tiles;
+            const int n_tmem_tiles = n_tmem_sub / 2 < tiles_local ? n_tmem_sub / 2 : tiles_local;
             for (int nt = 0; nt < n_tmem_tiles; ++nt) tile(nt, Tm{}, Tm{});
-            if (p.n_tiles > n_tmem_tiles)
+            if (tiles_local > n_tmem_tiles)
                 tile(n_tmem_tiles, std::integral_constant<int, 0>{}, std::integral_constant<int, 1>{});
-            if (p.n_tiles > n_tmem_tiles + 1)
+            if (tiles_local > n_tmem_tiles + 1)
                 tile(n_tmem_tiles + 1, std::integral_constant<int, 2>{}, std::integral_constant<int, 3>{});
             sb_fence_proxy_async();           // this step's h is visible to the tensor core
             sb_mbar_arrive(&h_ready[(s + 1) & 1]);
+            if (p.csize > 1) sb_mbar_arrive_cluster(sb_mapa(sb_smem_u32(&h_ready[(s + 1) & 1]), crank ^ 1u));
         }
     }
     sb_tc_fence_before();
     __syncthreads();
+    if (p.csize > 1) sb_cluster_sync();   // no CTA exits while its peer may still write into its shared memory
     if (warp == 2) { sb_tc_fence_after(); sb_tmem_dealloc(tmem_base, 512); }
 }
 
@@ -340,8 +365,30 @@ int sb_lstm_persistent_launch(const void* whh0, const void* whh1, int h_ld, cons
         SB_CHECK_CUDA(cudaFuncSetAttribute(lstm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
-    dim3 grid((unsigned)((p.n_units + kUnits - 1) / kUnits), 2);
-    lstm_persistent_kernel<<<grid, kLThreads, smem, stream>>>(tm[0], tm[1], p);
+    // split every unit tile over a cluster of 2 CTAs when the unit tiles leave half of the SMs idle anyway and the
+    // tiles divide evenly (SB_LSTM_CLUSTER=0/1 overrides)
+    const long long unit_tiles = (p.n_units + kUnits - 1) / kUnits;
+    int sms = 0;
+    SB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const char* cl = getenv("SB_LSTM_CLUSTER");
+    bool cluster = p.n_tiles % 2 == 0 && unit_tiles * 4 <= sms;
+    if (cl && cl[0] == '0') cluster = false;
+    if (cl && cl[0] == '1') cluster = p.n_tiles % 2 == 0;
+    p.csize = cluster ? 2 : 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(unit_tiles * p.csize), 2);
+    cfg.blockDim = dim3(kLThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = (unsigned)p.csize;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    SB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, lstm_persistent_kernel, tm[0], tm[1], p));
     SB_COUNT_LAUNCH();
     SB_CHECK_LAUNCH();
     (void)device;

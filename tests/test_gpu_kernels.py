@@ -624,13 +624,16 @@ def test_danq_batch_axis_recurrence_vs_torch(torch, precision, tol):
         assert np.abs(got[0::2] - exp_even).max() <= tol and np.abs(got[1::2] - exp_odd).max() <= tol
 
 
-@pytest.mark.parametrize("stepwise", ["0", "1"])
-def test_danq_recurrence_paths(torch, monkeypatch, stepwise):
-    """bf16 recurrence both ways — the one-launch persistent kernel (sb_lstm.cu, default) and the per-step
-    launches (SB_LSTM_STEPWISE=1) — against torch, ragged groups and interleaved ref/alt chains included."""
+@pytest.mark.parametrize("stepwise,cluster", [("0", "1"), ("0", "0"), ("1", "0")])
+def test_danq_recurrence_paths(torch, monkeypatch, stepwise, cluster):
+    """bf16 recurrence three ways — the one-launch persistent kernel (sb_lstm.cu) with 2-CTA clusters exchanging h
+    through distributed shared memory (default for small jobs), the same kernel with one CTA per unit tile, and
+    the per-step launches (SB_LSTM_STEPWISE=1) — against torch, ragged groups and interleaved ref/alt chains
+    included."""
     import sb_models as M
     from selene_b200.nets import B200Net, layers_from_module
     monkeypatch.setenv("SB_LSTM_STEPWISE", stepwise)
+    monkeypatch.setenv("SB_LSTM_CLUSTER", cluster)
     torch.manual_seed(10)
     model = M.DanQ(1000, 919).eval()
     codes = _rand_codes(11, 1000, 32)
