@@ -96,20 +96,63 @@ def format_e2_rows(data, row_prefixes=None):
     return buf.cpu().numpy(), off.cpu().numpy()
 
 
+_TEXT_STAGE = {}   # device index -> (pinned uint8 staging buffer for formatted text)
+_TEXT_CHUNK_BYTES = 96 << 20
+
+
+def _format_rows_device(t, prefixes):
+    """Formats rows of CUDA float32 tensor ``t`` with their byte prefixes; returns (device uint8 buffer, total)."""
+    import torch
+    lib = _lib.load()
+    n, F = int(t.shape[0]), int(t.shape[1])
+    sizes = torch.empty(n, dtype=torch.int64, device=t.device)
+    _lib.check(lib.sb_format_e2_row_bytes(_lib.ptr(t), n, F, _lib.ptr(sizes), _lib.stream_ptr()), "sb_format_e2_row_bytes")
+    lens = np.fromiter((len(p) for p in prefixes), dtype=np.int64, count=n)
+    po = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=po[1:])
+    pre = torch.from_numpy(np.frombuffer(b"".join(prefixes), dtype=np.uint8).copy()).to(t.device)
+    pre_off = torch.from_numpy(po).to(t.device)
+    sizes += pre_off[1:] - pre_off[:-1]
+    off = torch.zeros(n + 1, dtype=torch.int64, device=t.device)
+    torch.cumsum(sizes, 0, out=off[1:])
+    total = int(off[-1].item())
+    buf = torch.empty(total, dtype=torch.uint8, device=t.device)
+    _lib.check(lib.sb_format_e2_rows_prefixed(_lib.ptr(t), n, F, _lib.ptr(off), _lib.ptr(pre), _lib.ptr(pre_off),
+                                              _lib.ptr(buf), _lib.stream_ptr()), "sb_format_e2_rows_prefixed")
+    return buf, total
+
+
 def write_tsv(path, columns_for_ids, features, ids, data, append=False):
-    """Rows ``id columns + "{:.2e}" per value`` (handler.py:36-42,99-114).  The whole file body — id columns and
-    numbers — is assembled by ``sb_format_e2_rows_prefixed`` on the device and written with one call."""
-    prefixes = [("\t".join(str(i) for i in info) + "\t").encode() for info in ids]
-    buf, _off = format_e2_rows(data, prefixes)
+    """Rows ``id columns + "{:.2e}" per value`` (handler.py:36-42,99-114).  ``data``: (n, F) numpy array or CUDA
+    tensor.  The file body — id columns and numbers — is assembled by ``sb_format_e2_rows_prefixed`` on the device in
+    chunks of <= 96 MB of text, each read back through a persistent pinned buffer and written with one call."""
+    import torch
+    t = data if isinstance(data, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32))
+    t = t.to(device="cuda", dtype=torch.float32).contiguous()
+    n, F = int(t.shape[0]), int(t.shape[1])
+    dev = t.device.index or 0
+    rows_per_chunk = max(1, _TEXT_CHUNK_BYTES // (F * 10 + 64))
     with open(path, "ab" if append else "wb") as fh:
         if not append:
             fh.write("{0}\n".format("\t".join(list(columns_for_ids) + list(features))).encode())
-        fh.write(memoryview(buf))
+        for r0 in range(0, n, rows_per_chunk):
+            r1 = min(n, r0 + rows_per_chunk)
+            prefixes = [("\t".join(str(i) for i in info) + "\t").encode() for info in ids[r0:r1]]
+            buf, total = _format_rows_device(t[r0:r1], prefixes)
+            stage = _TEXT_STAGE.get(dev)
+            if stage is None or stage.numel() < total:
+                stage = _TEXT_STAGE[dev] = torch.empty(max(total, _TEXT_CHUNK_BYTES + (8 << 20)), dtype=torch.uint8,
+                                                       pin_memory=True)
+            stage[:total].copy_(buf, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            fh.write(memoryview(stage.numpy())[:total])
 
 
 def write_hdf5(path, data):
     """Dataset ``data`` float64 (n_rows, n_features) (handler.py:205-218)."""
     import h5py
+    if hasattr(data, "is_cuda"):
+        data = data.cpu().numpy()
     with h5py.File(path, "w") as fh:
         fh.create_dataset("data", data=np.asarray(data, dtype=np.float64))
 
@@ -458,7 +501,9 @@ class AnalyzeSequences(object):
         names = [s for s in want if s != "predictions"]
         if "predictions" in want:
             names += ["ref_predictions", "alt_predictions"]
-        arrays = {k: np.zeros((n, F), dtype=np.float32) for k in names}
+        import torch
+        dev = torch.device("cuda", int(self.net.device))
+        arrays = {k: torch.zeros((n, F), dtype=torch.float32, device=dev) for k in names}   # scores stay in HBM
         match = np.ones(n, dtype=bool)
         unk = np.zeros(n, dtype=bool)
         snv = np.fromiter((len(v[3]) == 1 and len(v[4]) == 1 and v[4] not in "*-" for v in variants),
@@ -468,10 +513,15 @@ class AnalyzeSequences(object):
             r = self.score_snvs([variants[i][0] for i in idx], [variants[i][1] for i in idx],
                                 [_CODE.get(variants[i][3], 4) for i in idx],
                                 [_CODE.get(variants[i][4], 4) for i in idx],
-                                strands=[variants[i][5] for i in idx], save_data=want)
-            for k in names:
-                arrays[k][idx] = r[k]
-            match[idx], unk[idx] = r["ref_match"], r["contains_unk"]
+                                strands=[variants[i][5] for i in idx], save_data=want, to_host=False)
+            if len(idx) == n:
+                for k in names:
+                    arrays[k] = r[k]
+            else:
+                didx = torch.from_numpy(idx).to(dev)
+                for k in names:
+                    arrays[k][didx] = r[k]
+            match[idx], unk[idx] = r["ref_match"].cpu().numpy(), r["contains_unk"].cpu().numpy()
         idx = np.nonzero(~snv)[0]
         if len(idx):
             refs, alts = [], []
@@ -480,9 +530,10 @@ class AnalyzeSequences(object):
                                                       self._start_radius, self._end_radius)
                 refs.append(codes_of_string(rs)); alts.append(codes_of_string(als))
                 match[i], unk[i] = m, u
-            r = self.score_code_pairs(np.stack(refs), np.stack(alts), save_data=want)
+            r = self.score_code_pairs(np.stack(refs), np.stack(alts), save_data=want, to_host=False)
+            didx = torch.from_numpy(idx).to(dev)
             for k in names:
-                arrays[k][idx] = r[k]
+                arrays[k][didx] = r[k]
         for i, v in enumerate(variants):
             if unk[i]:
                 warnings.warn("For variant ({0}, {1}, {2}, {3}, {4}, {5}), reference sequence contains "
@@ -494,13 +545,10 @@ class AnalyzeSequences(object):
                               "use '{3}' in the input sequence--will be marked `False` in the `ref_match` "
                               "column of the .tsv or the row_labels .txt file".format(*v))
         if world > 1:
-            import torch
             from ..sharding import gather_tiles
-            dev = torch.device("cuda", int(self.net.device))
             n_all = len(all_variants)
             for k in list(arrays.keys()):
-                g = gather_tiles(torch.from_numpy(arrays[k]).to(dev), n_all, dst=0)
-                arrays[k] = g.cpu().numpy() if g is not None else None
+                arrays[k] = gather_tiles(arrays[k], n_all, dst=0)
             mu = torch.from_numpy(np.stack([match, unk], axis=1).astype(np.float32)).to(dev)
             g = gather_tiles(mu, n_all, dst=0)
             if rank != 0:
