@@ -34,7 +34,7 @@ def timed(fn, warmup=3, iters=10):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--only", default="", help="comma list of sections: encode,labels,ism,danq,sweep,sampler,train")
+    ap.add_argument("--only", default="", help="comma list of sections: encode,labels,ism,vepfile,danq,sweep,sampler,train")
     args = ap.parse_args()
     only = set(x for x in args.only.split(",") if x)
     want = lambda name: not only or name in only
@@ -156,6 +156,35 @@ def main():
         emit(config="1: DeepSEA ISM incl. writing abs_diffs + logits TSV files (2 x 3000 x 919 values)", precision="bf16",
              seconds=dt_files, mutants_per_s=3000 / dt_files, tsv_bytes_per_file=size,
              host_savetxt_seconds_per_matrix=host_fmt)
+
+    # ---------------------------------------------------------------- config 2 through the public API with files
+    if want('vepfile'):
+        import shutil, tempfile
+        nv = 20000 if args.quick else 100000
+        tmpd = tempfile.mkdtemp(prefix="sb_vep_")
+        vcf = os.path.join(tmpd, "v.vcf")
+        vr = np.random.default_rng(2024)
+        ci_, pos_, alt_ = vr.integers(0, len(names), nv), vr.integers(600, per - 600, nv), vr.integers(0, 4, nv)
+        with open(vcf, "w") as fh:
+            fh.write("#CHROM\tPOS\tID\tREF\tALT\n")
+            for i in range(nv):
+                ref_ = chr(seqs[ci_[i]][pos_[i] - 1]).upper()
+                fh.write("%s\t%d\trs%d\t%s\t%s\n" % (names[ci_[i]], pos_[i], i, ref_ if ref_ in "ACGT" else "A", "ACGT"[alt_[i]]))
+        azv = AnalyzeSequences(M.DeepSEA(1000, 919), sequence_length=1000, features=feats, reference_sequence=G)
+        import warnings as _w
+        with _w.catch_warnings():
+            _w.simplefilter("ignore")
+            azv.variant_effect_prediction(vcf, ["abs_diffs", "logits"], output_dir=os.path.join(tmpd, "w"))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            azv.variant_effect_prediction(vcf, ["abs_diffs", "logits"], output_dir=os.path.join(tmpd, "o"))
+            torch.cuda.synchronize()
+        dtv = time.perf_counter() - t0
+        mb = sum(os.path.getsize(os.path.join(tmpd, "o", f)) for f in os.listdir(os.path.join(tmpd, "o"))) / 1e6
+        shutil.rmtree(tmpd, ignore_errors=True)
+        emit(config="2: AnalyzeSequences.variant_effect_prediction from a VCF file to abs_diffs + logits TSV files",
+             precision="bf16", variants=nv, seconds=dtv, variants_per_s=nv / dtv, predictions_per_s=2 * nv / dtv,
+             tsv_mb_written=mb)
 
     # ---------------------------------------------------------------- config 4: DanQ ISM
     torch.manual_seed(0)

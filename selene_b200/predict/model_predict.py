@@ -122,7 +122,7 @@ def _format_rows_device(t, prefixes):
     return buf, total
 
 
-def write_tsv(path, columns_for_ids, features, ids, data, append=False):
+def write_tsv(path, columns_for_ids, features, ids, data, append=False, id_bytes=None):
     """Rows ``id columns + "{:.2e}" per value`` (handler.py:36-42,99-114).  ``data``: (n, F) numpy array or CUDA
     tensor.  The file body — id columns and numbers — is assembled by ``sb_format_e2_rows_prefixed`` on the device in
     chunks of <= 96 MB of text, each read back through a persistent pinned buffer and written with one call."""
@@ -137,7 +137,8 @@ def write_tsv(path, columns_for_ids, features, ids, data, append=False):
             fh.write("{0}\n".format("\t".join(list(columns_for_ids) + list(features))).encode())
         for r0 in range(0, n, rows_per_chunk):
             r1 = min(n, r0 + rows_per_chunk)
-            prefixes = [("\t".join(str(i) for i in info) + "\t").encode() for info in ids[r0:r1]]
+            prefixes = (id_bytes[r0:r1] if id_bytes is not None else
+                        [("\t".join(str(i) for i in info) + "\t").encode() for info in ids[r0:r1]])
             buf, total = _format_rows_device(t[r0:r1], prefixes)
             stage = _TEXT_STAGE.get(dev)
             if stage is None or stage.numel() < total:
@@ -167,11 +168,14 @@ def write_row_labels(path, columns_for_ids, ids):
 def _write_outputs(results, ids, features, cols, output_path_prefix, output_format):
     """results: ordered list of (handler_filename, prefix_override or None, array)."""
     labels_written = False
+    # the id columns of a row are the same in every file: encode them once
+    id_bytes = ([("\t".join(str(i) for i in info) + "\t").encode() for info in ids]
+                if output_format == "tsv" and len(results) > 1 else None)
     for name, prefix, arr in results:
         opp = output_path_prefix if prefix is None else prefix
         out_dir, fprefix, sp = _scores_filepath(opp, name)
         if output_format == "tsv":
-            write_tsv(sp + ".tsv", cols, features, ids, arr)
+            write_tsv(sp + ".tsv", cols, features, ids, arr, id_bytes=id_bytes)
         else:
             write_hdf5(sp + ".h5", arr)
             if not labels_written:
