@@ -450,7 +450,10 @@ class AnalyzeSequences(object):
             sequence = sequence[start:int(start + self.sequence_length)]
         sequence = str.upper(sequence)
         want = self._want(save_data)
-        (pos, alt), out, base = self.ism_scores(sequence, want, start_position, end_position)
+        # scores stay in HBM: the writers format them there (only the mutation list comes to the host)
+        import torch
+        (pos, alt), out, base = self.ism_scores(sequence, want, start_position, end_position, to_host=False)
+        pos, alt = pos.cpu().numpy(), alt.cpu().numpy()
         ids = [(str(int(p)), sequence[int(p)], "ACGT"[int(a)]) for p, a in zip(pos, alt)]
         results = []
         for s in want:
@@ -458,7 +461,7 @@ class AnalyzeSequences(object):
                 arr = out["alt_predictions"]
                 if output_format == "tsv":
                     # model_predict.py:789-792: the baseline row leads the predictions TSV
-                    arr = np.concatenate([base, arr], axis=0)
+                    arr = torch.cat([base, arr], dim=0)
                     _out_dir, _p, sp = _scores_filepath(output_path_prefix, "predictions")
                     write_tsv(sp + ".tsv", ISM_COLS, self.features,
                               [("input_sequence", "NA", "NA")] + ids, arr)
