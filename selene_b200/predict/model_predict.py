@@ -12,6 +12,7 @@ formats (handler.py:15-114,190-235; write_ref_alt_handler.py:83-108).
 import io
 import math
 import os
+import threading
 import warnings
 
 import numpy as np
@@ -140,9 +141,10 @@ def write_tsv(path, columns_for_ids, features, ids, data, append=False, id_bytes
             prefixes = (id_bytes[r0:r1] if id_bytes is not None else
                         [("\t".join(str(i) for i in info) + "\t").encode() for info in ids[r0:r1]])
             buf, total = _format_rows_device(t[r0:r1], prefixes)
-            stage = _TEXT_STAGE.get(dev)
+            skey = (dev, threading.get_ident())
+            stage = _TEXT_STAGE.get(skey)
             if stage is None or stage.numel() < total:
-                stage = _TEXT_STAGE[dev] = torch.empty(max(total, _TEXT_CHUNK_BYTES + (8 << 20)), dtype=torch.uint8,
+                stage = _TEXT_STAGE[skey] = torch.empty(max(total, _TEXT_CHUNK_BYTES + (8 << 20)), dtype=torch.uint8,
                                                        pin_memory=True)
             stage[:total].copy_(buf, non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -168,14 +170,23 @@ def write_row_labels(path, columns_for_ids, ids):
 def _write_outputs(results, ids, features, cols, output_path_prefix, output_format):
     """results: ordered list of (handler_filename, prefix_override or None, array)."""
     labels_written = False
+    errors_box = []
     # the id columns of a row are the same in every file: encode them once
     id_bytes = ([("\t".join(str(i) for i in info) + "\t").encode() for info in ids]
                 if output_format == "tsv" and len(results) > 1 else None)
+    writers = []
     for name, prefix, arr in results:
         opp = output_path_prefix if prefix is None else prefix
         out_dir, fprefix, sp = _scores_filepath(opp, name)
         if output_format == "tsv":
-            write_tsv(sp + ".tsv", cols, features, ids, arr, id_bytes=id_bytes)
+            if len(results) > 1 and len(ids) >= 4096:
+                # big files: one writer thread per file (the file writes release the GIL and dominate the time)
+                th = threading.Thread(target=_write_tsv_thread, args=(errors_box, torch_device_of(arr), sp + ".tsv", cols,
+                                                                      features, ids, arr, id_bytes))
+                th.start()
+                writers.append(th)
+            else:
+                write_tsv(sp + ".tsv", cols, features, ids, arr, id_bytes=id_bytes)
         else:
             write_hdf5(sp + ".h5", arr)
             if not labels_written:
@@ -186,6 +197,24 @@ def _write_outputs(results, ids, features, cols, output_path_prefix, output_form
                     lf = "{0}_{1}".format(fprefix, lf)
                 write_row_labels(os.path.join(out_dir, lf), cols, ids)
                 labels_written = True
+    for th in writers:
+        th.join()
+    if errors_box:
+        raise errors_box[0]
+
+
+def torch_device_of(arr):
+    return arr.device.index if hasattr(arr, "is_cuda") and arr.is_cuda else None
+
+
+def _write_tsv_thread(errors, device_index, *args):
+    try:
+        import torch
+        if device_index is not None:
+            torch.cuda.set_device(device_index)
+        write_tsv(*args[:-1], id_bytes=args[-1])
+    except BaseException as e:   # re-raised by the caller
+        errors.append(e)
 
 
 _PINNED = {}   # (name, shape, dtype) -> persistent pinned staging tensor (allocating pinned memory per call is slow)
