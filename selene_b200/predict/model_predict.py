@@ -504,6 +504,144 @@ class AnalyzeSequences(object):
                 results.append((s, None, out[s]))
         _write_outputs(results, ids, self.features, ISM_COLS, output_path_prefix, output_format)
 
+    # ----------------------------------------------------------------------------------------------
+    # predictions for sequences / FASTA / BED inputs (model_predict.py:265-597) and ISM over a FASTA file (:801-950)
+    # ----------------------------------------------------------------------------------------------
+    def _pad_or_truncate_sequence(self, sequence):
+        """model_predict.py:1143-1153 with _pad_sequence / _truncate_sequence (_common.py:8-34)."""
+        n = len(sequence)
+        if n < self.sequence_length:
+            diff = (self.sequence_length - n) / 2
+            pad_l, pad_r = int(np.floor(diff)), math.ceil(diff)
+            sequence = (self.reference_sequence.UNK_BASE * pad_l) + sequence + (self.reference_sequence.UNK_BASE * pad_r)
+        elif n > self.sequence_length:
+            start = int((n - self.sequence_length) // 2)
+            sequence = sequence[start:int(start + self.sequence_length)]
+        return sequence
+
+    def _predict_codes(self, codes):
+        """(n, L) uint8 codes on the device -> (n, F) CUDA predictions; rows are grouped into the reference's batches
+        of ``batch_size`` (matters for DanQ's batch-axis recurrence)."""
+        self.net.set_recurrence(self.batch_size, 1)
+        return self.net.forward_codes(codes, precision=self.precision)
+
+    def get_predictions_for_fasta_file(self, input_path, output_dir, output_format="tsv"):
+        """model_predict.py:444-524: one prediction row per FASTA record, ids (index, name)."""
+        import torch
+        from ..sequences.genome import read_fasta
+        os.makedirs(output_dir, exist_ok=True)
+        _, filename = os.path.split(input_path)
+        output_prefix = '.'.join(filename.split('.')[:-1])
+        records = read_fasta(input_path)
+        ids, rows = [], []
+        for i, (name, arr) in enumerate(records):
+            seq = self._pad_or_truncate_sequence(arr.tobytes().decode("latin-1"))
+            rows.append(codes_of_string(seq))
+            ids.append((i, name))
+        codes = torch.from_numpy(np.stack(rows)).cuda() if rows else torch.zeros((0, self.sequence_length), dtype=torch.uint8).cuda()
+        preds = self._predict_codes(codes) if len(rows) else torch.zeros((0, len(self.features)), device="cuda")
+        _write_outputs([("predictions", None, preds)], ids, self.features, ["index", "name"],
+                       os.path.join(output_dir, output_prefix), output_format)
+
+    def _get_sequences_from_bed_file(self, input_path, strand_index=None, output_NAs_to_file=None,
+                                     reference_sequence=None):
+        """model_predict.py:265-345."""
+        sequences, labels, na_rows = [], [], []
+        check_chr = all(c.startswith("chr") for c in reference_sequence.get_chrs())
+        chrs = set(reference_sequence.get_chrs())
+        with open(input_path, 'r') as read_handle:
+            for i, line in enumerate(read_handle):
+                cols = line.strip().split('\t')
+                if len(cols) < 3:
+                    na_rows.append(line)
+                    continue
+                chrom, start, end = cols[0], cols[1], cols[2]
+                strand = '.'
+                if isinstance(strand_index, int) and len(cols) > strand_index:
+                    strand = cols[strand_index]
+                if 'chr' not in chrom and check_chr is True:
+                    chrom = "chr{0}".format(chrom)
+                if not str.isdigit(start) or not str.isdigit(end) or chrom not in chrs:
+                    na_rows.append(line)
+                    continue
+                start, end = int(start), int(end)
+                mid_pos = start + ((end - start) // 2)
+                seq_start = mid_pos - self._start_radius
+                seq_end = mid_pos + self._end_radius
+                if reference_sequence:
+                    if not reference_sequence.coords_in_bounds(chrom, seq_start, seq_end):
+                        na_rows.append(line)
+                        continue
+                sequences.append((chrom, seq_start, seq_end, strand))
+                labels.append((i, chrom, start, end, strand))
+        if reference_sequence and output_NAs_to_file:
+            with open(output_NAs_to_file, 'w') as file_handle:
+                for na_row in na_rows:
+                    file_handle.write(na_row)
+        return sequences, labels
+
+    def get_predictions_for_bed_file(self, input_path, output_dir, output_format="tsv", strand_index=None):
+        """model_predict.py:347-442: predictions centred on every BED region, ids (index, chrom, start, end, strand,
+        contains_unk); rows that cannot be fetched go to ``<prefix>.NA``."""
+        import torch
+        os.makedirs(output_dir, exist_ok=True)
+        _, filename = os.path.split(input_path)
+        output_prefix = '.'.join(filename.split('.')[:-1])
+        G = self.reference_sequence
+        seq_coords, labels = self._get_sequences_from_bed_file(
+            input_path, strand_index=strand_index,
+            output_NAs_to_file="{0}.NA".format(os.path.join(output_dir, output_prefix)), reference_sequence=G)
+        n = len(labels)
+        if n:
+            strands = [c[3] for c in seq_coords]
+            for st in strands:
+                if st not in ('+', '-', '.'):
+                    raise ValueError("Strand must be one of '+', '-', or '.'. Input was {0}".format(st))
+            codes, flags = G.window_codes([c[0] for c in seq_coords], [c[1] for c in seq_coords], self.sequence_length,
+                                          strands=strands)
+            unk = ((flags & _lib.SB_FLAG_HAS_UPPER_N) != 0).cpu().numpy()
+            preds = self._predict_codes(codes)
+        else:
+            unk = np.zeros(0, dtype=bool)
+            preds = torch.zeros((0, len(self.features)), device="cuda")
+        ids = [label + (bool(unk[i]),) for i, label in enumerate(labels)]
+        for i, label in enumerate(labels):
+            if unk[i]:
+                warnings.warn(("For region {0}, reference sequence contains unknown base(s). --will be marked `True` "
+                               "in the `contains_unk` column of the .tsv or row_labels .txt file.").format(label))
+        _write_outputs([("predictions", None, preds)], ids, self.features,
+                       ["index", "chrom", "start", "end", "strand", "contains_unk"],
+                       os.path.join(output_dir, output_prefix), output_format)
+
+    def get_predictions(self, input_path, output_dir=None, output_format="tsv", strand_index=None):
+        """model_predict.py:526-597: a raw sequence (returns the (1, F) prediction), or a FASTA / BED file."""
+        import torch
+        if output_dir is None:
+            sequence = self._pad_or_truncate_sequence(input_path)
+            codes = torch.from_numpy(codes_of_string(sequence)[None]).cuda()
+            return self._predict_codes(codes).cpu().numpy()
+        elif input_path.endswith('.fa') or input_path.endswith('.fasta'):
+            self.get_predictions_for_fasta_file(input_path, output_dir, output_format=output_format)
+        else:
+            self.get_predictions_for_bed_file(input_path, output_dir, output_format=output_format,
+                                              strand_index=strand_index)
+        return None
+
+    def in_silico_mutagenesis_from_file(self, input_path, save_data, output_dir, mutate_n_bases=1,
+                                        use_sequence_name=True, output_format="tsv", start_position=0,
+                                        end_position=None):
+        """model_predict.py:801-950: ISM of every record of a FASTA file, one set of output files per record
+        (prefixed by the record name, or its index)."""
+        from ..sequences.genome import read_fasta
+        if end_position is None:
+            end_position = self.sequence_length
+        os.makedirs(output_dir, exist_ok=True)
+        for i, (name, arr) in enumerate(read_fasta(input_path)):
+            file_prefix = os.path.join(output_dir, name.replace(' ', '_') if use_sequence_name else str(i))
+            self.in_silico_mutagenesis(arr.tobytes().decode("latin-1"), save_data, output_path_prefix=file_prefix,
+                                       mutate_n_bases=mutate_n_bases, output_format=output_format,
+                                       start_position=start_position, end_position=end_position)
+
     def variant_effect_prediction(self, vcf_file, save_data, output_dir=None, output_format="tsv",
                                   strand_index=None, require_strand=False):
         """model_predict.py:952-1141."""

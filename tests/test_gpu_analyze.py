@@ -131,3 +131,82 @@ def test_ism_with_non_strand_specific_model():
         exp = wrapped(torch.tensor(rows).transpose(1, 2)).numpy()
     assert np.abs(base - exp_base).max() <= 1e-5
     assert np.abs(out["abs_diffs"] - np.abs(exp_base - exp)).max() <= 2e-5
+
+
+def test_get_predictions_fasta_bed_and_ism_from_file(tmp_path):
+    """model_predict.py:347-597,801-950: predictions for a raw sequence / FASTA / BED input and ISM over a FASTA
+    file write the reference's files; numbers against torch on the oracle's encodings."""
+    import torch
+    from selene_b200.predict.model_predict import AnalyzeSequences
+    from selene_b200.sequences import Genome
+    g = H.synth_genome(n_chrom=2, length=6000)
+    fa = str(tmp_path / "g.fa")
+    H.write_fasta(g, fa)
+    Genome.update_bases_order(['A', 'C', 'G', 'T'])
+    G = Genome(fa)
+    import sb_models as M
+    torch.manual_seed(0)
+    model = M.DeepSEA(1000, 919).eval()
+    az = AnalyzeSequences(model, sequence_length=1000, features=FEATS, reference_sequence=G, precision="fp32", batch_size=4)
+
+    def torch_pred(seqs):
+        x = torch.tensor(np.stack([O.sequence_to_encoding(s) for s in seqs])).transpose(1, 2)
+        with torch.no_grad():
+            return model(x).numpy()
+
+    # ---- raw sequence (short: padded with N on both sides)
+    r = np.random.default_rng(3)
+    raw = "".join(np.array(list("ACGTacgtN"))[r.integers(0, 9, 700)].tolist())
+    got = az.get_predictions(raw)
+    assert got.shape == (1, 919) and np.abs(got - torch_pred([az._pad_or_truncate_sequence(raw)])).max() <= 1e-5
+
+    # ---- FASTA: records shorter, equal and longer than the model input
+    recs = {"s_short": raw, "s_exact": "".join(np.array(list("ACGT"))[r.integers(0, 4, 1000)].tolist()),
+            "s_long": "".join(np.array(list("ACGT"))[r.integers(0, 4, 1300)].tolist())}
+    qfa = str(tmp_path / "q.fa")
+    with open(qfa, "w") as fh:
+        for k, v in recs.items():
+            fh.write(">%s\n" % k)
+            for i in range(0, len(v), 60):
+                fh.write(v[i:i + 60] + "\n")
+    out = str(tmp_path / "pf")
+    az.get_predictions(qfa, out)
+    header, ids, data = _read_tsv(os.path.join(out, "q_predictions.tsv"), 2)
+    assert header == ["index", "name"] + FEATS and ids == [(str(i), k) for i, k in enumerate(recs)]
+    exp = torch_pred([az._pad_or_truncate_sequence(v) for v in recs.values()])
+    assert np.abs(data - exp).max() <= 6e-3 * max(1.0, np.abs(exp).max())      # "{:.2e}" keeps 3 digits
+
+    # ---- BED: centred windows, strand column, one row out of bounds, one unknown contig
+    c0, c1 = sorted(g.keys())[:2]
+    bed = str(tmp_path / "r.bed")
+    rows = [(c0, 1500, 1700, "+"), (c1, 3000, 3001, "-"), (c0, 10, 20, "+"), ("chrNope", 5, 9, "+"), (c1, 2500, 2600, ".")]
+    open(bed, "w").write("".join("%s\t%d\t%d\t%s\n" % r_ for r_ in rows))
+    out = str(tmp_path / "pb")
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        az.get_predictions_for_bed_file(bed, out, strand_index=3)
+    header, ids, data = _read_tsv(os.path.join(out, "r_predictions.tsv"), 6)
+    assert header[:6] == ["index", "chrom", "start", "end", "strand", "contains_unk"]
+    assert [i[0] for i in ids] == ["0", "1", "4"]
+    assert len(open(os.path.join(out, "r.NA")).read().strip().split("\n")) == 2
+    seqs = []
+    for (c, s, e, st) in (rows[0], rows[1], rows[4]):
+        mid = s + (e - s) // 2
+        seqs.append(O.get_sequence_from_coords(g, c, mid - 500, mid + 500, st if st != "." else "+", True))
+    exp = torch_pred(seqs)
+    assert np.abs(data - exp).max() <= 6e-3 * max(1.0, np.abs(exp).max())
+    assert [i[5] for i in ids] == [str("N" in s) for s in seqs]
+
+    # ---- ISM over a FASTA file = in_silico_mutagenesis per record
+    out = str(tmp_path / "ismf")
+    az.in_silico_mutagenesis_from_file(qfa, ["abs_diffs"], out, start_position=495, end_position=505)
+    az.in_silico_mutagenesis(recs["s_long"], ["abs_diffs"], output_path_prefix=str(tmp_path / "single" / "x"),
+                             start_position=495, end_position=505)
+    a = open(os.path.join(out, "s_long_abs_diffs.tsv")).read()
+    b = open(str(tmp_path / "single" / "x_abs_diffs.tsv")).read()
+    assert a == b and len(a.split("\n")) == 32
+    assert sorted(os.listdir(out)) == ["s_exact_abs_diffs.tsv", "s_long_abs_diffs.tsv", "s_short_abs_diffs.tsv"]
+    az.in_silico_mutagenesis_from_file(qfa, ["abs_diffs"], str(tmp_path / "ismi"), use_sequence_name=False,
+                                       start_position=0, end_position=2)
+    assert sorted(os.listdir(str(tmp_path / "ismi"))) == ["0_abs_diffs.tsv", "1_abs_diffs.tsv", "2_abs_diffs.tsv"]
