@@ -227,6 +227,25 @@ def main():
              precision="bf16", seconds_per_sequence=dt2, mutants_per_s=3000 / dt2,
              tflops=3000 / dt2 * azd.net.flops_per_seq / 1e12)
 
+    # config 4 through the public API: ISM over a FASTA file of sequences, both TSV files per sequence written
+    if want('danq'):
+        import shutil, tempfile
+        tmpd = tempfile.mkdtemp(prefix="sb_ismf_")
+        nrec = 8 if args.quick else 24
+        r11 = np.random.default_rng(11)
+        with open(os.path.join(tmpd, "q.fa"), "w") as fh:
+            for i in range(nrec):
+                fh.write(">seq%d\n%s\n" % (i, "".join(np.array(list("ACGT"))[r11.integers(0, 4, 1000)].tolist())))
+        azd.in_silico_mutagenesis_from_file(os.path.join(tmpd, "q.fa"), ["abs_diffs", "logits"], os.path.join(tmpd, "w"))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        azd.in_silico_mutagenesis_from_file(os.path.join(tmpd, "q.fa"), ["abs_diffs", "logits"], os.path.join(tmpd, "o"))
+        torch.cuda.synchronize()
+        dtf = (time.perf_counter() - t0) / nrec
+        shutil.rmtree(tmpd, ignore_errors=True)
+        emit(config="4: DanQ in_silico_mutagenesis_from_file (FASTA in, abs_diffs + logits TSV files out), per sequence",
+             precision="bf16", seconds_per_sequence=dtf, mutants_per_s=3000 / dtf)
+
     # ---------------------------------------------------------------- config 5: Seqweaver / HeartENN sweep
     for name, model in ((("Seqweaver(217)", M.Seqweaver(217)), ("HeartENN(1000, 90)", M.HeartENN(1000, 90)),
                          ("DeeperDeepSEA(1000, 919) [SURVEY 8 f4]", M.DeeperDeepSEA(1000, 919)),

@@ -167,24 +167,35 @@ def write_row_labels(path, columns_for_ids, ids):
             fh.write("{0}\n".format("\t".join(str(i) for i in info)))
 
 
-def _write_outputs(results, ids, features, cols, output_path_prefix, output_format):
-    """results: ordered list of (handler_filename, prefix_override or None, array)."""
+_WRITER_POOL = None
+
+
+def _writer_pool():
+    """Two persistent writer threads (persistent so that their pinned text buffers are allocated once)."""
+    global _WRITER_POOL
+    if _WRITER_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _WRITER_POOL = ThreadPoolExecutor(max_workers=2, thread_name_prefix="sb_writer")
+    return _WRITER_POOL
+
+
+def _write_outputs(results, ids, features, cols, output_path_prefix, output_format, defer=False):
+    """results: ordered list of (handler_filename, prefix_override or None, array).  TSV files of one call are written
+    by the two writer threads side by side (the file writes release the GIL and dominate the time).  With ``defer``
+    the futures are returned instead of awaited, so the caller can score the next input meanwhile."""
     labels_written = False
-    errors_box = []
     # the id columns of a row are the same in every file: encode them once
     id_bytes = ([("\t".join(str(i) for i in info) + "\t").encode() for info in ids]
                 if output_format == "tsv" and len(results) > 1 else None)
-    writers = []
+    futures = []
+    threaded = output_format == "tsv" and (defer or (len(results) > 1 and len(ids) >= 1024))
     for name, prefix, arr in results:
         opp = output_path_prefix if prefix is None else prefix
         out_dir, fprefix, sp = _scores_filepath(opp, name)
         if output_format == "tsv":
-            if len(results) > 1 and len(ids) >= 4096:
-                # big files: one writer thread per file (the file writes release the GIL and dominate the time)
-                th = threading.Thread(target=_write_tsv_thread, args=(errors_box, torch_device_of(arr), sp + ".tsv", cols,
-                                                                      features, ids, arr, id_bytes))
-                th.start()
-                writers.append(th)
+            if threaded:
+                futures.append(_writer_pool().submit(_write_tsv_job, torch_device_of(arr), sp + ".tsv", cols, features, ids,
+                                                     arr, id_bytes))
             else:
                 write_tsv(sp + ".tsv", cols, features, ids, arr, id_bytes=id_bytes)
         else:
@@ -197,24 +208,22 @@ def _write_outputs(results, ids, features, cols, output_path_prefix, output_form
                     lf = "{0}_{1}".format(fprefix, lf)
                 write_row_labels(os.path.join(out_dir, lf), cols, ids)
                 labels_written = True
-    for th in writers:
-        th.join()
-    if errors_box:
-        raise errors_box[0]
+    if defer:
+        return futures
+    for f in futures:
+        f.result()      # re-raises a writer's exception
+    return []
 
 
 def torch_device_of(arr):
     return arr.device.index if hasattr(arr, "is_cuda") and arr.is_cuda else None
 
 
-def _write_tsv_thread(errors, device_index, *args):
-    try:
-        import torch
-        if device_index is not None:
-            torch.cuda.set_device(device_index)
-        write_tsv(*args[:-1], id_bytes=args[-1])
-    except BaseException as e:   # re-raised by the caller
-        errors.append(e)
+def _write_tsv_job(device_index, path, cols, features, ids, arr, id_bytes):
+    import torch
+    if device_index is not None:
+        torch.cuda.set_device(device_index)
+    write_tsv(path, cols, features, ids, arr, id_bytes=id_bytes)
 
 
 _PINNED = {}   # (name, shape, dtype) -> persistent pinned staging tensor (allocating pinned memory per call is slow)
@@ -440,7 +449,7 @@ class AnalyzeSequences(object):
     # reference entry points
     # ----------------------------------------------------------------------------------------------
     def in_silico_mutagenesis(self, sequence, save_data, output_path_prefix="ism", mutate_n_bases=1,
-                              output_format="tsv", start_position=0, end_position=None):
+                              output_format="tsv", start_position=0, end_position=None, _defer_writes=False):
         """model_predict.py:662-799 (``mutate_n_bases`` is ignored there too: hard-wired to 1, :763-764)."""
         if end_position is None:
             end_position = self.sequence_length
@@ -502,7 +511,8 @@ class AnalyzeSequences(object):
                                  [("input_sequence",)])
             else:
                 results.append((s, None, out[s]))
-        _write_outputs(results, ids, self.features, ISM_COLS, output_path_prefix, output_format)
+        return _write_outputs(results, ids, self.features, ISM_COLS, output_path_prefix, output_format,
+                              defer=_defer_writes) or None
 
     # ----------------------------------------------------------------------------------------------
     # predictions for sequences / FASTA / BED inputs (model_predict.py:265-597) and ISM over a FASTA file (:801-950)
@@ -636,11 +646,18 @@ class AnalyzeSequences(object):
         if end_position is None:
             end_position = self.sequence_length
         os.makedirs(output_dir, exist_ok=True)
+        pending = []    # the files of record i are written while record i+1 is scored
         for i, (name, arr) in enumerate(read_fasta(input_path)):
             file_prefix = os.path.join(output_dir, name.replace(' ', '_') if use_sequence_name else str(i))
-            self.in_silico_mutagenesis(arr.tobytes().decode("latin-1"), save_data, output_path_prefix=file_prefix,
-                                       mutate_n_bases=mutate_n_bases, output_format=output_format,
-                                       start_position=start_position, end_position=end_position)
+            nxt = self.in_silico_mutagenesis(arr.tobytes().decode("latin-1"), save_data, output_path_prefix=file_prefix,
+                                             mutate_n_bases=mutate_n_bases, output_format=output_format,
+                                             start_position=start_position, end_position=end_position,
+                                             _defer_writes=True)
+            for f in pending:
+                f.result()
+            pending = nxt or []
+        for f in pending:
+            f.result()
 
     def variant_effect_prediction(self, vcf_file, save_data, output_dir=None, output_format="tsv",
                                   strand_index=None, require_strand=False):
