@@ -7,7 +7,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libselene_b200.so")
+# SELENE_B200_LIB points the binding at another build of the same C ABI (the mutation check of the parity suite,
+# scripts/mutation_check.sh); there is still no fallback: a missing file raises.
+LIB_PATH = os.environ.get("SELENE_B200_LIB") or os.path.join(_HERE, "libselene_b200.so")
 
 SB_OK = 0
 SB_F32, SB_BF16, SB_U8, SB_I64, SB_F64 = 0, 1, 2, 3, 4

@@ -251,8 +251,13 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                             for (int j = 0; j < 8; ++j) {
                                 const int col = nb + (odd ? 8 : 0) + j;
                                 if (col < sc.F)
+#ifdef SB_MUTANT_SWAP_LANES   // test-only build (scripts/mutation_check.sh): ref/alt lanes swapped on purpose
+                                    tc_store_scores(sc, pair * sc.F + col, odd ? mine[j] : other[j],
+                                                    odd ? other[j] : mine[j], true);
+#else
                                     tc_store_scores(sc, pair * sc.F + col, odd ? other[j] : mine[j],
                                                     odd ? mine[j] : other[j], true);
+#endif
                             }
                         }
                     } else if (valid) {

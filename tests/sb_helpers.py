@@ -75,3 +75,49 @@ def rows_by_chrom(rows):
     for c, s, e, f in rows:
         by.setdefault(c, []).append([c, str(s), str(e), f])
     return by
+
+
+def stack_forward_rounded(x_bl4, layers, presigmoid=False):
+    """The oracle's conv-stack forward (oracle.stack_forward) with the ROUNDING POINTS of the bf16 throughput
+    path made explicit: weights rounded to bf16, every layer's (pooled) output rounded to bf16, fp32
+    accumulation, biases and the last layer's output in fp32.  A checker for the tcgen05 path that is ~10x
+    tighter than the fp32 oracle (what is left is summation order)."""
+    import torch
+    import torch.nn.functional as F
+    bf = lambda t: t.to(torch.bfloat16).to(torch.float32)
+    with torch.no_grad():
+        x = torch.tensor(np.asarray(x_bl4, dtype=np.float32)).transpose(1, 2)
+        flat = False
+        for i, lay in enumerate(layers):
+            w = bf(torch.tensor(np.asarray(lay["weight"], dtype=np.float32)))
+            b = torch.tensor(np.asarray(lay["bias"], dtype=np.float32))
+            if lay["type"] == "conv":
+                x = F.conv1d(x, w, b)
+                if lay.get("relu"):
+                    x = F.relu(x)
+                if lay.get("pool", 1) > 1:
+                    x = F.max_pool1d(x, lay["pool"], lay["pool"])
+            else:
+                if not flat:
+                    x = x.reshape(x.size(0), -1)
+                    flat = True
+                x = F.linear(x, w, b)
+                if lay.get("relu"):
+                    x = F.relu(x)
+            if i < len(layers) - 1:
+                x = bf(x)
+        return (x if presigmoid else torch.sigmoid(x)).numpy()
+
+
+def scaled_deepsea(scale, seed=0):
+    """tests/sb_models.DeepSEA under torch.manual_seed(seed) with the three conv weights multiplied by ``scale``
+    — the same weights as oracle.deepsea_layers(1000, 919, seed, scale)."""
+    import torch
+    import sb_models
+    torch.manual_seed(seed)
+    m = sb_models.DeepSEA(1000, 919)
+    with torch.no_grad():
+        for mod in m.conv_net:
+            if isinstance(mod, torch.nn.Conv1d):
+                mod.weight.mul_(scale)
+    return m
