@@ -232,3 +232,22 @@ def test_golden_sampler():
     assert np.array_equal(b.astype(np.float32), GOLD["sampler_seq_val"])
     assert np.array_equal(tb.astype(np.float32), GOLD["sampler_tgt_val"])
     assert (GOLD["sampler_seq_train"] == 0.25).any() and GOLD["sampler_tgt_train"].sum() > 0
+
+
+def test_oracle_vep_scores_equal_installed_reference(tmp_path):
+    """The oracle port against the UNMODIFIED reference installed in baseline/_ref (baseline/build_ref.py), driven
+    through its public AnalyzeSequences.variant_effect_prediction: abs_diffs and logits are bit-identical
+    (same torch CPU kernels, same order of operations).  Skipped where the reference is not installed."""
+    import bench as B
+    from baseline import reference_arm as R
+    if not R.available():
+        pytest.skip("baseline/_ref not installed (python baseline/build_ref.py in the authoring container)")
+    names, seqs = B.synth_genome_arrays(1.2)
+    chrom, pos, ref, alt = B.synth_snvs(names, seqs, 70, 5)
+    rv = R.ReferenceVEP(names, seqs, str(tmp_path), threads=4)
+    got = rv.score(chrom, pos, ref, alt)
+    genome = {n: B._SeqView(s) for n, s in zip(names, seqs)}
+    variants = [(names[chrom[i]], int(pos[i]), "ACGT"[ref[i]], "ACGT"[alt[i]], "+") for i in range(70)]
+    absd, logits, _m, _u = O.vep_scores(genome, variants, O.deepsea_layers(1000, 919, seed=0), 1000)
+    assert np.array_equal(got["abs_diffs"], absd)
+    assert np.array_equal(got["logits"], logits)
