@@ -377,8 +377,10 @@ def strong_leg(az, names, seqs, args, rank, world):
     shards_s = max_over_ranks(time.perf_counter() - t0)
     # (b) one NCCL gather of the score tiles to rank 0, then rank 0 reads the whole matrix back
     gather_bytes = 0
+    full = {k: gather_tiles(tiles[k], M, dst=0) for k in save}   # untimed: NCCL channel set-up, receive buffers
+    sync_all()
     t0 = time.perf_counter()
-    full = {k: gather_tiles(tiles[k], M, dst=0) for k in save}
+    full = {k: gather_tiles(tiles[k], M, dst=0, out=full[k] if rank == 0 else None) for k in save}
     sync_all()
     gather_s = max_over_ranks(time.perf_counter() - t0)
     if world > 1:

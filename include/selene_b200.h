@@ -281,6 +281,10 @@ int sb_net_sgd_step(sb_net* net, const float* grads, float lr, float momentum, f
 /* fp32 parameters (from_grads NULL) or gradients (from_grads = the flat vector) of one layer, to host,
  * in torch layout: conv (cout, cin, k), fc (cout, cin); bias (cout).  Synchronises the device. */
 int sb_net_get_layer_params(const sb_net* net, int layer, const float* from_grads, float* w_host, float* b_host);
+/* SGD momentum buffers of one layer, torch layout, to / from host: the ``momentum_buffer`` entries of the
+ * ``optimizer`` state a Selene checkpoint holds (selene_sdk/train_model.py:430-437 writes it, :296-326 restores it). */
+int sb_net_get_layer_momentum(const sb_net* net, int layer, float* w_host, float* b_host);
+int sb_net_set_layer_momentum(sb_net* net, int layer, const float* w_host, const float* b_host);
 
 /* The same step with the layer GEMMs (forward, dgrad, wgrad) on tcgen05: bf16 operands, fp32 accumulation,
  * fp32 master weights and gradients; the 4-channel first conv stays on CUDA cores.  Same arguments and

@@ -6,7 +6,7 @@ set -u
 cd "$(dirname "$0")/.."
 MUT=selene_b200/libselene_b200_mutant.so
 if [ "${1:-build}" == "build" ]; then
-  make -C selene_b200/csrc OUT=../libselene_b200_mutant.so FLAGS_EXTRA=-DSB_MUTANT_SWAP_LANES > /dev/null && echo "built $MUT"
+  make -C selene_b200/csrc OUT=../libselene_b200_mutant.so FLAGS_EXTRA=-DSB_MUTANT_SWAP_LANES > /dev/null 2>&1 && echo "built $MUT"
 else
   mkdir -p gpurun_out
   SELENE_B200_LIB=$PWD/$MUT timeout 900 python -m pytest tests/test_gpu_score_parity.py -q -m gpu -p no:cacheprovider \

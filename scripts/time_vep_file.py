@@ -33,4 +33,5 @@ for rep in range(2):
     if rep == 1 and len(sys.argv) > 2:
         pr.disable(); pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
     sz = sum(os.path.getsize(os.path.join(out, f)) for f in os.listdir(out))
+    print("stages:", {k: round(v, 3) for k, v in az.last_timing.items()})
     print("rep %d: %d variants in %.2f s = %.0f variants/s (%.0f predictions/s), %.1f MB written" % (rep, n, dt, n / dt, 2 * n / dt, sz / 1e6))

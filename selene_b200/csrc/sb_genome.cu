@@ -2,9 +2,7 @@
 //
 // All of these are HBM-bound byte movers: a 1000-bp fp32 window reads 250 B of 2-bit codes +
 // 2 x 125 B of masks and writes 16 000 B, so the design goal is simply "every store is a full
-// 128-bit coalesced store and nothing is read twice from DRAM".  One CTA owns one output row
-// (window / mutant / variant): the packed bytes it needs are served by L1 after the first touch,
-// thread t writes bases t, t+blockDim, ... so a warp writes 512 contiguous bytes per instruction.
+// 128-bit coalesced store, every load is a full word, and nothing is read twice from DRAM".
 //
 // Reference semantics restated here (each cited at the function that implements it):
 //   selene_sdk/sequences/_sequence.pyx:11-25, selene_sdk/sequences/genome.py:96-166,542,
@@ -33,42 +31,6 @@ struct GenomeView {
     const int64_t* __restrict__ chrom_off;
     const int64_t* __restrict__ chrom_len;
 };
-
-// code (0..3, 4 = unknown) of image base `gi`; sets *upper_n when the character was 'N'.
-__device__ __forceinline__ int image_code(const GenomeView& g, int64_t gi, bool* upper_n) {
-    const int byte = __ldg(g.packed + (gi >> 2));
-    const int code = (byte >> (2 * (int)(gi & 3))) & 3;
-    const int m = __ldg(g.unk + (gi >> 3));
-    const int un = (m >> (int)(gi & 7)) & 1;
-    if (un) {
-        const int u = __ldg(g.upn + (gi >> 3));
-        *upper_n = ((u >> (int)(gi & 7)) & 1) != 0;
-        return 4;
-    }
-    *upper_n = false;
-    return code;
-}
-
-// Code of output position i of window [start, start+L) on chromosome of length clen at image
-// offset coff.  Out-of-range parts are 'N' (genome.py:156-166); with rc the in-bounds part alone is
-// reverse-complemented and the padding stays where it was (the reference concatenates
-// N*start_pad + revcomp(inner) + N*end_pad, genome.py:164-166).
-__device__ __forceinline__ int window_code(const GenomeView& g, int64_t coff, int64_t clen,
-                                           int64_t start, int L, bool rc, int i, bool* upper_n) {
-    const int64_t end = start + L;
-    const int64_t s0 = start < 0 ? 0 : start;
-    const int64_t e0 = end > clen ? clen : end;
-    const int64_t start_pad = s0 - start;
-    const int64_t inner = e0 - s0;
-    const int64_t j = (int64_t)i - start_pad;
-    if (j < 0 || j >= inner) {
-        *upper_n = true;  // Genome.UNK_BASE == "N"
-        return 4;
-    }
-    if (!rc) return image_code(g, coff + s0 + j, upper_n);
-    const int c = image_code(g, coff + e0 - 1 - j, upper_n);
-    return c < 4 ? 3 - c : 4;  // A<->T, C<->G; unknown stays unknown (pyfaidx complement keeps N/n)
-}
 
 struct Perm {
     uint8_t p[4];
@@ -104,72 +66,254 @@ __device__ __forceinline__ void store_onehot(void* out, int64_t base_index, int 
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-// One WARP per window, grid-stride over windows.  MODE 0: codes only; 1: one-hot fp32; 2: one-hot bf16.
-// Lane l of iteration k owns BPL consecutive bases (1 for fp32, 2 for bf16, 16 for codes) so that every
-// store is one 16-byte store and a warp writes 512 contiguous bytes per instruction; the per-window
-// flags are a warp reduction (no block barrier, no shared memory).
-template <int MODE>
-__global__ void __launch_bounds__(256) window_kernel(GenomeView g, const int32_t* __restrict__ chrom,
-                                                     const int64_t* __restrict__ start,
-                                                     const uint8_t* __restrict__ strand_rc, int n, int L,
-                                                     Perm perm, void* __restrict__ out,
-                                                     uint8_t* __restrict__ flags_out) {
-    constexpr int BPL = MODE == 1 ? 1 : (MODE == 2 ? 2 : 16);
+// One WARP per window (or SNV), grid-stride.  A window is handled in chunks of 512 output positions:
+//
+//   decode   lane l owns output positions c0 + 16 l ... + 15.  They are 16 CONSECUTIVE genome bases (descending for
+//            the minus strand), so the lane fetches them with two aligned 32-bit loads of the 2-bit image and two of
+//            each mask, funnel-shifted to the base offset — 6 load instructions per lane per chunk instead of two
+//            dependent byte loads per base — expands them to 16 code bytes with bit spreads (complemented and
+//            byte-reversed for the minus strand, 4 = unknown where the mask or the chromosome end says so) and parks
+//            them in the warp's 512-byte slice of shared memory as one 16-byte store;
+//   emit     lane l then reads the codes of the positions it STORES: one base per lane and instruction for fp32
+//            (a warp writes 512 contiguous bytes), two for bf16, sixteen for code rows, always one 16-byte store.
+//
+// Flags are mask arithmetic on the decode side plus one warp OR-reduction.  MODE 0: codes only; 1: one-hot fp32;
+// 2: one-hot bf16.  SNV = false: sb_encode_windows / sb_genome_codes (the minus strand reverse-complements the
+// in-bounds part only, genome.py:164-166).  SNV = true: sb_snv_pairs — ref and alt tensors with the VCF alleles forced
+// at the variant row, ref_match, the strand applied to the finished encodings (model_predict.py:1102-1110).
+constexpr int kWinChunk = 512;
+constexpr int kWinWarps = 8;
+constexpr int kWinMaxChromSmem = 256;   // chromosome offsets / lengths staged in shared memory up to this many
+
+__device__ __forceinline__ uint32_t spread_codes4(uint32_t bits8) {   // 4 x 2-bit fields -> 4 bytes
+    uint32_t x = bits8 & 0xFFu;
+    x = (x | (x << 12)) & 0x000F000Fu;
+    return (x | (x << 6)) & 0x03030303u;
+}
+__device__ __forceinline__ uint32_t spread_bits4(uint32_t bits4) {    // 4 bits -> bit 0 of 4 bytes
+    uint32_t m = bits4 & 0xFu;
+    m = (m | (m << 14)) & 0x00030003u;
+    return (m | (m << 7)) & 0x01010101u;
+}
+
+struct WinMeta {          // what is read per window from the caller's arrays (prefetched one window ahead)
+    int c;
+    int64_t st;
+    int rc, sub_ref, sub_alt;
+};
+struct WinRaw {           // the image words of one lane's 16 positions (prefetched one chunk ahead)
+    uint32_t pw, uw, nw, vm;
+};
+
+template <int MODE, bool SNV>
+__global__ void __launch_bounds__(kWinWarps * 32, 5) window_kernel(
+    GenomeView g, int64_t n_image, int n_chrom, const int32_t* __restrict__ chrom, const int64_t* __restrict__ start,
+    const uint8_t* __restrict__ strand_rc, int n, int L, Perm perm, void* __restrict__ out,
+    uint8_t* __restrict__ flags_out,
+    // SNV only
+    const uint8_t* __restrict__ ref_code, const uint8_t* __restrict__ alt_code, int var_row,
+    void* __restrict__ alt_out, uint8_t* __restrict__ codes_out, uint8_t* __restrict__ ref_match) {
+    __shared__ __align__(16) uint8_t stage[kWinWarps][kWinChunk];
+    __shared__ __align__(16) float4 lut_f32[5];      // one-hot rows by code, in the caller's channel order
+    __shared__ __align__(16) uint2 lut_bf16[5];
+    __shared__ int64_t chrom_meta[2 * kWinMaxChromSmem];
     const int lane = threadIdx.x & 31;
-    const int warps_total = gridDim.x * (blockDim.x >> 5);
-    for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n; w += warps_total) {
-        const int c = chrom[w];
-        const int64_t coff = g.chrom_off[c];
-        const int64_t clen = g.chrom_len[c];
-        const int64_t st = start[w];
-        const bool rc = strand_rc != nullptr && strand_rc[w] != 0;
+    uint8_t* sm = stage[threadIdx.x >> 5];
+    if (threadIdx.x < 5) {
+        lut_f32[threadIdx.x] = onehot_f32(threadIdx.x, perm);
+        lut_bf16[threadIdx.x] = onehot_bf16(threadIdx.x, perm);
+    }
+    const bool meta_smem = n_chrom <= kWinMaxChromSmem;
+    if (meta_smem)
+        for (int i = threadIdx.x; i < n_chrom; i += blockDim.x) {
+            chrom_meta[i] = g.chrom_off[i];
+            chrom_meta[kWinMaxChromSmem + i] = g.chrom_len[i];
+        }
+    __syncthreads();
+    const uint32_t* __restrict__ packed32 = reinterpret_cast<const uint32_t*>(g.packed);
+    const uint32_t* __restrict__ unk32 = reinterpret_cast<const uint32_t*>(g.unk);
+    const uint32_t* __restrict__ upn32 = reinterpret_cast<const uint32_t*>(g.upn);
+    const int64_t max_w2 = (n_image >> 4) + 1, max_w1 = (n_image >> 5) + 1;   // the allocations are padded by 16 bytes
+    const int warps_total = gridDim.x * kWinWarps;
+
+    auto load_meta = [&](int w) {
+        WinMeta m;
+        m.c = chrom[w];
+        m.st = start[w];
+        m.rc = strand_rc != nullptr && strand_rc[w] != 0;
+        m.sub_ref = SNV ? ref_code[w] : 4;
+        m.sub_alt = SNV ? alt_code[w] : 4;
+        return m;
+    };
+    // window geometry: in-bounds genome range [s0, e0), image offset, and the genome coordinate of output position p,
+    // base + p (plus strand) or base - p (minus strand)
+    auto geometry = [&](const WinMeta& m, int64_t& coff, int64_t& s0, int64_t& e0, int64_t& base) {
+        coff = meta_smem ? chrom_meta[m.c] : g.chrom_off[m.c];
+        const int64_t clen = meta_smem ? chrom_meta[kWinMaxChromSmem + m.c] : g.chrom_len[m.c];
+        const int64_t end = m.st + L;
+        s0 = m.st < 0 ? 0 : m.st;
+        e0 = end > clen ? clen : end;
+        if (e0 < s0) e0 = s0;
+        base = !m.rc ? m.st : (SNV ? end - 1 : e0 - 1 + (s0 - m.st));
+    };
+    auto load_raw = [&](int64_t coff, int64_t s0, int64_t e0, int64_t base, int rc, int c0) {
+        WinRaw r;
+        const int p0 = c0 + 16 * lane;
+        const int64_t lo = rc ? base - (p0 + 15) : base + p0;           // lowest genome coordinate of the 16
+        const int64_t a64 = s0 - lo, b64 = e0 - lo;
+        const int a = a64 < 0 ? 0 : (a64 > 16 ? 16 : (int)a64);
+        const int b = b64 < 0 ? 0 : (b64 > 16 ? 16 : (int)b64);
+        r.vm = b > a ? (((1u << b) - 1u) & ~((1u << a) - 1u)) : 0u;     // in-bounds bases (ascending-coordinate space)
+        r.pw = r.uw = r.nw = 0;
+        if (r.vm != 0u && p0 < L) {
+            const int64_t gi = coff + lo;
+            int64_t w2 = gi >> 4, w1 = gi >> 5;
+            w2 = w2 < 0 ? 0 : (w2 > max_w2 ? max_w2 : w2);
+            w1 = w1 < 0 ? 0 : (w1 > max_w1 ? max_w1 : w1);
+            r.pw = __funnelshift_r(__ldg(packed32 + w2), __ldg(packed32 + w2 + 1), (uint32_t)(gi & 15) * 2u);
+            r.uw = __funnelshift_r(__ldg(unk32 + w1), __ldg(unk32 + w1 + 1), (uint32_t)(gi & 31)) & 0xFFFFu;
+            r.nw = __funnelshift_r(__ldg(upn32 + w1), __ldg(upn32 + w1 + 1), (uint32_t)(gi & 31)) & 0xFFFFu;
+        }
+        return r;
+    };
+
+    int w = blockIdx.x * kWinWarps + (threadIdx.x >> 5);
+    if (w >= n) return;
+    WinMeta m = load_meta(w);
+    WinMeta m_next = m;
+    if (w + warps_total < n) m_next = load_meta(w + warps_total);
+    int64_t coff, s0, e0, base;
+    geometry(m, coff, s0, e0, base);
+    WinRaw raw = load_raw(coff, s0, e0, base, m.rc, 0);
+    for (; w < n; w += warps_total) {
+        const int rc = m.rc;
+        int sub_at = -1, sub_ref = m.sub_ref, sub_alt = m.sub_alt;
+        if (SNV) {
+            sub_at = rc ? L - 1 - var_row : var_row;
+            if (rc) {
+                sub_ref = sub_ref < 4 ? 3 - sub_ref : 4;
+                sub_alt = sub_alt < 4 ? 3 - sub_alt : 4;
+            }
+        }
         int flags = 0;
-        for (int i0 = lane * BPL; i0 < L; i0 += 32 * BPL) {
-            int codes[BPL];
-#pragma unroll
-            for (int b = 0; b < BPL; ++b) {
-                bool upn = false;
-                int code = 4;
-                if (i0 + b < L) {
-                    code = window_code(g, coff, clen, st, L, rc, i0 + b, &upn);
-                    if (code > 3) flags |= SB_FLAG_HAS_UNK;
-                    if (upn) flags |= SB_FLAG_HAS_UPPER_N;
-                }
-                codes[b] = code;
+        for (int c0 = 0; c0 < L; c0 += kWinChunk) {
+            // ---------------------------------------------- loads of the NEXT chunk (this window's or the next one's)
+            WinRaw raw_next = raw;
+            int64_t coff_n = coff, s0_n = s0, e0_n = e0, base_n = base;
+            const bool last_chunk = c0 + kWinChunk >= L;
+            if (!last_chunk) {
+                raw_next = load_raw(coff, s0, e0, base, rc, c0 + kWinChunk);
+            } else if (w + warps_total < n) {
+                geometry(m_next, coff_n, s0_n, e0_n, base_n);
+                raw_next = load_raw(coff_n, s0_n, e0_n, base_n, m_next.rc, 0);
             }
-            const int64_t o = (int64_t)w * L + i0;
-            if (MODE == 1) {
-                reinterpret_cast<float4*>(out)[o] = onehot_f32(codes[0], perm);
-            } else if (MODE == 2) {
-                // two bases = 16 bytes when both exist and the address is 16-byte aligned
-                uint2* p = reinterpret_cast<uint2*>(out) + o;
-                if (i0 + 1 < L && ((o & 1) == 0)) {
-                    const uint2 a = onehot_bf16(codes[0], perm), b2 = onehot_bf16(codes[1], perm);
-                    *reinterpret_cast<uint4*>(p) = make_uint4(a.x, a.y, b2.x, b2.y);
-                } else {
-                    p[0] = onehot_bf16(codes[0], perm);
-                    if (i0 + 1 < L) p[1] = onehot_bf16(codes[1], perm);
+            // ---------------------------------------------- decode this lane's 16 positions
+            const int p0 = c0 + 16 * lane;
+            uint4 v;
+            {
+                const uint32_t vm = raw.vm, pw = raw.pw, uw = raw.uw, nw = raw.nw;
+                const uint32_t um = (uw & vm) | (~vm & 0xFFFFu);            // unknown: masked bases and padding
+                const uint32_t nm = (nw & uw & vm) | (~vm & 0xFFFFu);       // 'N': upper-case N bases and padding
+                const int cnt = L - p0 < 0 ? 0 : (L - p0 > 16 ? 16 : L - p0);
+                const uint32_t tm = (1u << cnt) - 1u;                       // positions of this lane inside the window
+                const uint32_t pm = rc ? (__brev(tm) >> 16) : tm;           // the same in ascending-coordinate space
+                if (um & pm) flags |= SB_FLAG_HAS_UNK;
+                if (nm & pm) flags |= SB_FLAG_HAS_UPPER_N;
+                uint32_t wd[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t x = spread_codes4(pw >> (8 * k));
+                    const uint32_t mk = spread_bits4(um >> (4 * k));
+                    if (rc) x ^= 0x03030303u;                               // complement: code -> 3 - code
+                    wd[k] = (x & ((mk ^ 0x01010101u) * 3u)) | (mk << 2);    // unknown -> 4
                 }
-            } else {
-                uint8_t* p = reinterpret_cast<uint8_t*>(out) + o;
-                if (i0 + 16 <= L && ((o & 15) == 0)) {
-                    uint32_t wd[4];
+                if (!rc) v = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+                else v = make_uint4(__byte_perm(wd[3], 0, 0x0123), __byte_perm(wd[2], 0, 0x0123),
+                                    __byte_perm(wd[1], 0, 0x0123), __byte_perm(wd[0], 0, 0x0123));
+            }
+            const int c1 = L - c0 < kWinChunk ? L - c0 : kWinChunk;         // positions in this chunk
+            const int64_t row0 = (int64_t)w * L + c0;
+            // ---------------------------------------------- code rows and ref_match come straight from registers
+            if (SNV && ref_match && sub_at >= p0 && sub_at < p0 + 16) {
+                const int k = sub_at - p0;
+                const uint32_t word = k < 4 ? v.x : (k < 8 ? v.y : (k < 12 ? v.z : v.w));
+                ref_match[w] = (uint8_t)((int)((word >> (8 * (k & 3))) & 0xFFu) == sub_ref);
+            }
+            if (MODE == 0 || (SNV && codes_out != nullptr)) {
+                uint8_t* cp = (MODE == 0 && !SNV) ? reinterpret_cast<uint8_t*>(out) : codes_out;
+                const int i = 16 * lane;
+                if (i < c1) {
+                    uint8_t* p = cp + row0 + i;
+                    const uintptr_t addr = reinterpret_cast<uintptr_t>(p);
+                    if (i + 16 <= c1 && (addr & 15) == 0) {
+                        *reinterpret_cast<uint4*>(p) = v;
+                    } else if (i + 16 <= c1 && (addr & 7) == 0) {
+                        *reinterpret_cast<uint2*>(p) = make_uint2(v.x, v.y);
+                        *reinterpret_cast<uint2*>(p + 8) = make_uint2(v.z, v.w);
+                    } else {
+                        const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        wd[k] = (uint32_t)codes[4 * k] | ((uint32_t)codes[4 * k + 1] << 8) |
-                                ((uint32_t)codes[4 * k + 2] << 16) | ((uint32_t)codes[4 * k + 3] << 24);
-                    *reinterpret_cast<uint4*>(p) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-                } else {
-#pragma unroll
-                    for (int b = 0; b < BPL; ++b)
-                        if (i0 + b < L) p[b] = (uint8_t)codes[b];
+                        for (int b = 0; b < 16; ++b)
+                            if (i + b < c1) p[b] = (uint8_t)(wds[b >> 2] >> (8 * (b & 3)));
+                    }
                 }
             }
+            // ---------------------------------------------- one-hot rows: stage the codes, store 16 bytes per lane
+            if (MODE != 0) {
+                reinterpret_cast<uint4*>(sm)[lane] = v;
+                __syncwarp();
+                if (MODE == 1) {
+                    float4* o4 = reinterpret_cast<float4*>(out) + row0;
+                    float4* a4 = reinterpret_cast<float4*>(alt_out) + row0;
+#pragma unroll 4
+                    for (int i = lane; i < c1; i += 32) {
+                        const int code = sm[i];
+                        if (SNV) {
+                            const bool hit = c0 + i == sub_at;
+                            if (out) o4[i] = lut_f32[hit ? sub_ref : code];
+                            if (alt_out) a4[i] = lut_f32[hit ? sub_alt : code];
+                        } else {
+                            o4[i] = lut_f32[code];
+                        }
+                    }
+                } else {
+                    const bool aligned = (row0 & 1) == 0;                   // 16-byte alignment of position pairs
+#pragma unroll 4
+                    for (int i = 2 * lane; i < c1; i += 64) {
+                        const bool two = i + 1 < c1;
+                        const int ca = sm[i], cb = two ? sm[i + 1] : 4;
+#pragma unroll
+                        for (int which = 0; which < (SNV ? 2 : 1); ++which) {
+                            void* dst = which == 0 ? out : alt_out;
+                            if (dst == nullptr) continue;
+                            int xa = ca, xb = cb;
+                            if (SNV) {
+                                const int sub = which == 0 ? sub_ref : sub_alt;
+                                if (c0 + i == sub_at) xa = sub;
+                                if (c0 + i + 1 == sub_at) xb = sub;
+                            }
+                            uint2* p = reinterpret_cast<uint2*>(dst) + row0 + i;
+                            const uint2 ua = lut_bf16[xa], ub = lut_bf16[xb];
+                            if (two && aligned) {
+                                *reinterpret_cast<uint4*>(p) = make_uint4(ua.x, ua.y, ub.x, ub.y);
+                            } else {
+                                p[0] = ua;
+                                if (two) p[1] = ub;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            raw = raw_next;
+            if (last_chunk) { coff = coff_n; s0 = s0_n; e0 = e0_n; base = base_n; }
         }
         if (flags_out != nullptr) {
             flags = __reduce_or_sync(0xffffffffu, flags);
             if (lane == 0) flags_out[w] = (uint8_t)flags;
         }
+        m = m_next;
+        if (w + 2 * warps_total < n) m_next = load_meta(w + 2 * warps_total);
     }
 }
 
@@ -263,56 +407,6 @@ __global__ void __launch_bounds__(256) ism_expand_kernel(const uint8_t* __restri
     }
 }
 
-// One CTA per variant: '+' window codes, forced ref row / alt row, optional reverse complement of
-// the finished encodings (which mirrors the variant row to L-1-var_row and complements the codes).
-template <int MODE>  // 0: no one-hot outputs, 1: fp32, 2: bf16
-__global__ void __launch_bounds__(256) snv_pairs_kernel(
-    GenomeView g, const int32_t* __restrict__ chrom, const int64_t* __restrict__ start,
-    const uint8_t* __restrict__ ref_code, const uint8_t* __restrict__ alt_code,
-    const uint8_t* __restrict__ strand_rc, int L, int var_row, Perm perm, void* __restrict__ ref_out,
-    void* __restrict__ alt_out, uint8_t* __restrict__ codes_out, uint8_t* __restrict__ ref_match,
-    uint8_t* __restrict__ flags_out) {
-    const int v = blockIdx.x;
-    const int c = chrom[v];
-    const int64_t coff = g.chrom_off[c];
-    const int64_t clen = g.chrom_len[c];
-    const int64_t st = start[v];
-    const bool rc = strand_rc != nullptr && strand_rc[v] != 0;
-    const int rcode = ref_code[v];
-    const int acode = alt_code[v];
-    int flags = 0;
-    for (int i = threadIdx.x; i < L; i += blockDim.x) {
-        bool upn;
-        const int code = window_code(g, coff, clen, st, L, false, i, &upn);
-        if (code > 3) flags |= SB_FLAG_HAS_UNK;
-        if (upn) flags |= SB_FLAG_HAS_UPPER_N;
-        if (codes_out) {  // strand-applied, unsubstituted window codes for sb_net_forward_*
-            const int oc = rc ? L - 1 - i : i;
-            codes_out[(int64_t)v * L + oc] = (uint8_t)(rc ? (code < 4 ? 3 - code : 4) : code);
-        }
-        if (i == var_row && ref_match) ref_match[v] = (uint8_t)(code == rcode);
-        if (MODE != 0) {
-            int rc_ref = (i == var_row) ? rcode : code;
-            int rc_alt = (i == var_row) ? acode : code;
-            int o = i;
-            if (rc) {
-                o = L - 1 - i;
-                rc_ref = rc_ref < 4 ? 3 - rc_ref : 4;
-                rc_alt = rc_alt < 4 ? 3 - rc_alt : 4;
-            }
-            if (ref_out) store_onehot<MODE == 2>(ref_out, (int64_t)v * L + o, rc_ref, perm);
-            if (alt_out) store_onehot<MODE == 2>(alt_out, (int64_t)v * L + o, rc_alt, perm);
-        }
-    }
-    if (flags_out != nullptr) {
-        const int any_unk = __syncthreads_or(flags & SB_FLAG_HAS_UNK);
-        const int any_upn = __syncthreads_or(flags & SB_FLAG_HAS_UPPER_N);
-        if (threadIdx.x == 0)
-            flags_out[v] = (uint8_t)((any_unk ? SB_FLAG_HAS_UNK : 0) |
-                                     (any_upn ? SB_FLAG_HAS_UPPER_N : 0));
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
@@ -331,8 +425,8 @@ static bool perm_ok(const uint8_t perm[4]) {
     return seen == 15;
 }
 static int window_grid(int n, int device) {
-    const long long blocks = ((long long)n + 7) / 8;           // 8 warps (windows) per CTA
-    const long long cap = (long long)sb_sm_count(device) * 8;  // persistent: 8 CTAs of 256 threads per SM
+    const long long blocks = ((long long)n + kWinWarps - 1) / kWinWarps;   // one warp per window
+    const long long cap = (long long)sb_sm_count(device) * 5;              // persistent: 5 CTAs of 8 warps per SM
     return (int)(blocks < cap ? blocks : cap);
 }
 
@@ -400,8 +494,9 @@ extern "C" int sb_genome_codes(const sb_genome* g, const int32_t* chrom, const i
     SB_REQUIRE(n >= 0 && L > 0, "sb_genome_codes: bad sizes n=%d L=%d", n, L);
     if (n == 0) return SB_OK;
     Perm p = {{0, 1, 2, 3}};
-    window_kernel<0><<<window_grid(n, g->device), 256, 0, (cudaStream_t)stream>>>(view_of(g), chrom, start, strand_rc,
-                                                                                  n, L, p, codes_out, flags_out);
+    window_kernel<0, false><<<window_grid(n, g->device), kWinWarps * 32, 0, (cudaStream_t)stream>>>(
+        view_of(g), g->n_image, g->n_chrom, chrom, start, strand_rc, n, L, p, codes_out, flags_out, nullptr, nullptr, 0, nullptr,
+        nullptr, nullptr);
     SB_COUNT_LAUNCH();
     SB_CHECK_LAUNCH();
     return SB_OK;
@@ -419,11 +514,13 @@ extern "C" int sb_encode_windows(const sb_genome* g, const int32_t* chrom, const
     const Perm p = make_perm(perm);
     cudaStream_t s = (cudaStream_t)stream;
     if (out_dtype == SB_F32)
-        window_kernel<1><<<window_grid(n, g->device), 256, 0, s>>>(view_of(g), chrom, start, strand_rc, n, L, p, out,
-                                                                   flags_out);
+        window_kernel<1, false><<<window_grid(n, g->device), kWinWarps * 32, 0, s>>>(
+            view_of(g), g->n_image, g->n_chrom, chrom, start, strand_rc, n, L, p, out, flags_out, nullptr, nullptr, 0, nullptr, nullptr,
+            nullptr);
     else
-        window_kernel<2><<<window_grid(n, g->device), 256, 0, s>>>(view_of(g), chrom, start, strand_rc, n, L, p, out,
-                                                                   flags_out);
+        window_kernel<2, false><<<window_grid(n, g->device), kWinWarps * 32, 0, s>>>(
+            view_of(g), g->n_image, g->n_chrom, chrom, start, strand_rc, n, L, p, out, flags_out, nullptr, nullptr, 0, nullptr, nullptr,
+            nullptr);
     SB_COUNT_LAUNCH();
     SB_CHECK_LAUNCH();
     return SB_OK;
@@ -505,18 +602,19 @@ extern "C" int sb_snv_pairs(const sb_genome* g, const int32_t* chrom, const int6
     const Perm p = make_perm(perm);
     cudaStream_t s = (cudaStream_t)stream;
     const GenomeView v = view_of(g);
+    const int grid = window_grid(n, g->device);
     if (!ref_out && !alt_out)
-        snv_pairs_kernel<0><<<n, 256, 0, s>>>(v, chrom, start, ref_code, alt_code, strand_rc, L,
-                                              var_row, p, nullptr, nullptr, codes_out, ref_match,
-                                              flags_out);
+        window_kernel<0, true><<<grid, kWinWarps * 32, 0, s>>>(v, g->n_image, g->n_chrom, chrom, start, strand_rc, n, L, p, nullptr,
+                                                               flags_out, ref_code, alt_code, var_row, nullptr, codes_out,
+                                                               ref_match);
     else if (out_dtype == SB_F32)
-        snv_pairs_kernel<1><<<n, 256, 0, s>>>(v, chrom, start, ref_code, alt_code, strand_rc, L,
-                                              var_row, p, ref_out, alt_out, codes_out, ref_match,
-                                              flags_out);
+        window_kernel<1, true><<<grid, kWinWarps * 32, 0, s>>>(v, g->n_image, g->n_chrom, chrom, start, strand_rc, n, L, p, ref_out,
+                                                               flags_out, ref_code, alt_code, var_row, alt_out, codes_out,
+                                                               ref_match);
     else
-        snv_pairs_kernel<2><<<n, 256, 0, s>>>(v, chrom, start, ref_code, alt_code, strand_rc, L,
-                                              var_row, p, ref_out, alt_out, codes_out, ref_match,
-                                              flags_out);
+        window_kernel<2, true><<<grid, kWinWarps * 32, 0, s>>>(v, g->n_image, g->n_chrom, chrom, start, strand_rc, n, L, p, ref_out,
+                                                               flags_out, ref_code, alt_code, var_row, alt_out, codes_out,
+                                                               ref_match);
     SB_COUNT_LAUNCH();
     SB_CHECK_LAUNCH();
     return SB_OK;

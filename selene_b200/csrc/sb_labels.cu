@@ -7,19 +7,22 @@
 //
 // Layout in HBM: all intervals sorted by (chromosome, start) as four int32 arrays — start, end,
 // feature, and a running maximum of `end` inside each chromosome — plus per-chromosome offsets
-// (16 B per interval).  One WARP owns one query bin:
-//   1. a bucket table over positions (one int32 per 1024 bases, L2-resident) brackets the first interval whose
-//      running max end exceeds the bin start; the warp finishes the search with 32 probes per round, normally
-//      one round (exact for any interval-length mix; once per QUERY, not per feature),
-//   2. the warp loads the next 32 intervals (coalesced); a feature that occurs once among the overlapping ones
-//      is labelled straight from registers, features with several intervals are replayed in start order into a
-//      per-feature union state (coverage and covered_until packed in one shared-memory word for bins shorter
-//      than 2^15 bases),
-//   3. the row is zero-filled with 16-byte stores and only the features of overlapping intervals are
-//      compared with the host-computed integer thresholds and set (labels are sparse; thresholds are >= 0,
-//      so an untouched feature is always 0).
-// Algorithmic traffic per query: F x sizeof(out) written + 12 B per overlapping interval read; for
-// large batches the kernel is bound by those output writes.
+// (16 B per interval).  One WARP owns one query bin, 48 warps per SM; what bounds small outputs (uint8 rows) is the
+// chain of DEPENDENT memory round trips per query, so the kernel is built to have two:
+//   1. one read of a bucket table over positions (one int32 per 1024 bases, L2-resident) gives the first interval
+//      whose running max end exceeds the start of the bin's bucket: everything before it ends at or before the bin
+//      start (exact for any interval-length mix; once per QUERY, not per feature);
+//   2. the warp loads the 32 intervals from there (three coalesced loads in flight together).  Intervals are sorted
+//      by start, so if one of the 32 starts at or after the bin end the candidates are complete — the common case.
+//      A feature that occurs once among the overlapping ones is labelled straight from registers; a feature with
+//      several intervals has its union built by the lowest lane of its group from warp shuffles, in start order;
+//   3. the row is zero-filled with 16-byte streaming stores (issued before the loads, off the chain) and only the
+//      features of overlapping intervals are compared with the host-computed integer thresholds and set (labels
+//      are sparse; thresholds are >= 0, so an untouched feature is always 0).
+// Bins with more than 32 candidates or 2^15 bases and more take a general path over a per-warp union state
+// (coverage and covered_until per feature) in a scratch buffer owned by the handle.
+// Algorithmic traffic per query: F x sizeof(out) written + 12 B per overlapping interval read + the table entry;
+// for int64 / float32 rows the kernel is bound by those output writes.
 #include "sb_common.cuh"
 
 #include <algorithm>
@@ -42,38 +45,22 @@ struct sb_intervals {
     int32_t* tab;        // dev, tab_off[n_chrom] entries
     int64_t* tab_off;    // dev, n_chrom + 1
     int tab_shift;
+    // general-path union state, one slice per resident warp, all-zero between queries (allocated by the first
+    // sb_label_bins; launches that share a handle must be ordered on one stream)
+    int32_t* scratch;
+    size_t scratch_words;
 };
 
 namespace {
 
-constexpr int kWarpsPerBlock = 4;
+constexpr int kWarpsPerBlock = 8;
+constexpr int kBlocksPerSm = 6;
 
 // Per-feature state of one query, one 32-bit word per feature while the bin is shorter than 2^15 bases
 // (bits 0-14 covered_until, bits 15-29 union coverage, bit 30 "some row overlapped"); longer bins take the
 // features in two passes with two words each in the same shared memory.
 constexpr int kPackedMaxLen = 32767;
 constexpr int32_t kAnyRow = 0x40000000;
-
-// first index in [lo, hi) whose running max end exceeds qs, by a 32-ary search the warp does together:
-// ~log32(n) dependent rounds of L2-resident probes instead of log2(n)
-__device__ __forceinline__ long long first_reaching(const int32_t* __restrict__ cmax, long long lo, long long hi, int qs,
-                                                    int lane) {
-    while (hi - lo > 32) {
-        const long long stride = (hi - lo + 31) >> 5;
-        long long p = lo + (long long)(lane + 1) * stride - 1;
-        if (p > hi - 1) p = hi - 1;
-        const unsigned reach = __ballot_sync(0xffffffffu, __ldg(cmax + p) > qs);   // monotone: a suffix of lanes
-        if (reach == 0) return hi;
-        const int first = __ffs(reach) - 1;
-        const long long p_first = __shfl_sync(0xffffffffu, p, first);
-        if (first > 0) lo = __shfl_sync(0xffffffffu, p, first - 1) + 1;
-        hi = p_first;   // cmax[p_first] > qs is known: the answer is in [lo, p_first]
-        if (hi == lo) return lo;
-    }
-    const long long i = lo + lane;
-    const unsigned reach = __ballot_sync(0xffffffffu, i < hi && __ldg(cmax + i) > qs);
-    return reach ? lo + (__ffs(reach) - 1) : hi;
-}
 
 // zero one output row with 16-byte stores (rows are only sizeof(OutT)-aligned: element stores for the ragged ends)
 template <typename OutT>
@@ -97,6 +84,7 @@ struct LabelArgs {
     const int64_t* tab_off;
     int tab_shift, n_features, n_chrom;
     int meta_in_smem;   // chrom_off / tab_off copied to shared memory (n_chrom small)
+    int32_t* scratch;   // general-path state: (resident warps) x words
 };
 
 // clipped [is, ie) of an interval inside the bin, as the reference paints it
@@ -136,32 +124,27 @@ __device__ __forceinline__ void replay(unsigned hit, int fs, int fe, int ff, int
 }
 
 // Labels are sparse (a bin overlaps a handful of the features), so a query costs one vectorised zero fill of its
-// row plus work proportional to the intervals it overlaps: no per-feature loop anywhere.  A feature that occurs
-// once among the overlapping intervals (the common case) is labelled straight from registers; features with
-// several intervals, and bins with more than 32 candidate intervals, go through the per-warp union state in
-// shared memory, which is all-zero between queries (only touched entries are written and then cleared).
+// row plus work proportional to the intervals it overlaps: no per-feature loop anywhere.
 template <typename OutT>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) label_bins_kernel(
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSm) label_bins_kernel(
     const LabelArgs a, const int32_t* __restrict__ q_chrom, const int32_t* __restrict__ q_start,
     const int32_t* __restrict__ q_end, int n_queries, const int32_t* __restrict__ thr_i, OutT* __restrict__ out) {
-    extern __shared__ int32_t smem[];
+    extern __shared__ int64_t meta[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_features = a.n_features;
     const int words = (n_features + 1) & ~1;             // per warp
-    int32_t* st = smem + (size_t)warp * words;
-    for (int i = lane; i < words; i += 32) st[i] = 0;
+    int32_t* st = a.scratch + ((size_t)blockIdx.x * kWarpsPerBlock + warp) * words;
     const int64_t* coff = a.chrom_off;
     const int64_t* toff = a.tab_off;
     if (a.meta_in_smem) {
-        int64_t* m = reinterpret_cast<int64_t*>(smem + (size_t)kWarpsPerBlock * words);
         for (int i = threadIdx.x; i <= a.n_chrom; i += blockDim.x) {
-            m[i] = a.chrom_off[i];
-            m[a.n_chrom + 1 + i] = a.tab_off[i];
+            meta[i] = a.chrom_off[i];
+            meta[a.n_chrom + 1 + i] = a.tab_off[i];
         }
-        coff = m;
-        toff = m + a.n_chrom + 1;
+        coff = meta;
+        toff = meta + a.n_chrom + 1;
+        __syncthreads();
     }
-    __syncthreads();
     const int warps_total = gridDim.x * kWarpsPerBlock;
     int q = blockIdx.x * kWarpsPerBlock + warp;
     int c_n = 0, qs_n = 0, qe_n = 0;
@@ -177,20 +160,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) label_bins_kernel(
         __syncwarp();   // orders the zero fill before the label stores of other lanes
         if (!(c >= 0 && c < a.n_chrom && qlen > 0)) continue;
         const long long lo0 = coff[c], hi0 = coff[c + 1];
-        long long lo, hi;
+        long long lo;
         {
             const long long t0 = toff[c];
             const long long nb = toff[c + 1] - t0;
-            if (qs < 0) { lo = lo0; hi = lo0 + __ldg(a.tab + t0); }
-            else {
-                const long long b = (long long)(qs >> a.tab_shift);
-                if (b >= nb - 1) { lo = hi = hi0; }     // past the last interval end of the chromosome
-                else { lo = lo0 + __ldg(a.tab + t0 + b); hi = lo0 + __ldg(a.tab + t0 + b + 1); }
-            }
+            const long long b = qs < 0 ? 0 : (long long)(qs >> a.tab_shift);
+            if (b >= nb - 1) continue;                   // past the last interval end of the chromosome: no overlap
+            lo = qs < 0 ? lo0 : lo0 + __ldg(a.tab + t0 + b);
         }
-        lo = first_reaching(a.iv_cmax, lo, hi, qs, lane);
         const bool packed = qlen <= kPackedMaxLen;
-        // ---- first 32 candidates
+        // ---- the 32 candidates from the table position
         int fs = 0x7fffffff, fe = 0, ff = 0;
         if (lo + lane < hi0) {
             fs = __ldg(a.iv_start + lo + lane); fe = __ldg(a.iv_end + lo + lane); ff = __ldg(a.iv_feat + lo + lane);
@@ -200,28 +179,34 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) label_bins_kernel(
         const unsigned hitmask = __ballot_sync(0xffffffffu, is_hit);
         if (!more && packed) {
             if (hitmask == 0) continue;
-            bool unique = false;
-            if (is_hit) unique = __match_any_sync(hitmask, ff) == (1u << lane);
-            const unsigned dup = __ballot_sync(0xffffffffu, is_hit && !unique);
-            if (is_hit && unique) {
+            unsigned group = 0;
+            if (is_hit) group = __match_any_sync(hitmask, ff);
+            const bool unique = is_hit && group == (1u << lane);
+            const bool leader = is_hit && (int)(__ffs(group) - 1) == lane;
+            int cov = 0;
+            if (unique) {
                 int is, ie;
                 clip_interval(fs, fe, qs, qlen, is, ie);
+                cov = ie - is;
+            }
+            // features with several intervals: the group's lowest lane merges them in lane (= start) order
+            unsigned rem = __ballot_sync(0xffffffffu, is_hit && !unique);
+            int until = 0;
+            while (rem) {
+                const int l = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const int s = __shfl_sync(0xffffffffu, fs, l);
+                const int e = __shfl_sync(0xffffffffu, fe, l);
+                if (leader && ((group >> l) & 1)) {
+                    int is, ie;
+                    clip_interval(s, e, qs, qlen, is, ie);
+                    if (ie > until) { cov += ie - (is > until ? is : until); until = ie; }
+                }
+            }
+            if (leader) {
                 const int t = __ldg(thr_i + ff);
                 // :39-40 with thresholds; genomic_features.py:406-415 (any overlapping row) when thr < 0
-                if (t < 0 || ie - is > t) o[ff] = (OutT)1;
-            }
-            if (dup) {
-                replay(dup, fs, fe, ff, qs, qlen, true, 0, 0, st, lane);
-                __syncwarp();
-                const bool mine = (dup >> lane) & 1;
-                if (mine) {
-                    const int32_t w = st[ff];
-                    const int t = __ldg(thr_i + ff);
-                    if (t < 0 || ((w >> 15) & 0x7fff) > t) o[ff] = (OutT)1;
-                }
-                __syncwarp();
-                if (mine) st[ff] = 0;
-                __syncwarp();
+                if (t < 0 || cov > t) o[ff] = (OutT)1;
             }
             continue;
         }
@@ -254,6 +239,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) label_bins_kernel(
                     if (live != 0xffffffffu) break;
                 }
                 __syncwarp();
+                __threadfence_block();
             }
         }
     }
@@ -358,6 +344,7 @@ extern "C" int sb_intervals_destroy(sb_intervals* iv) {
     cudaFree(iv->chrom_off);
     cudaFree(iv->tab);
     cudaFree(iv->tab_off);
+    if (iv->scratch) cudaFree(iv->scratch);
     delete iv;
     return SB_OK;
 }
@@ -370,26 +357,28 @@ extern "C" int sb_label_bins(const sb_intervals* iv, const int32_t* chrom, const
     if (n == 0) return SB_OK;
     SB_REQUIRE(chrom && bin_start && bin_end && thr_i && out, "sb_label_bins: null argument");
     const int meta_in_smem = iv->n_chrom <= 512;
-    const size_t smem = (size_t)kWarpsPerBlock * ((iv->n_features + 1) & ~1) * sizeof(int32_t) +
-                        (meta_in_smem ? 2 * (size_t)(iv->n_chrom + 1) * sizeof(int64_t) : 0);
-    SB_REQUIRE(smem <= 200 * 1024, "sb_label_bins: %d features need %zu bytes of shared memory", iv->n_features, smem);
+    const size_t smem = meta_in_smem ? 2 * (size_t)(iv->n_chrom + 1) * sizeof(int64_t) : 0;
     int64_t blocks = ((int64_t)n + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    // persistent grid: as many blocks as are resident at once (shared memory is the limiter)
-    int64_t per_sm = (int64_t)(200 * 1024 / (smem + 1024));
-    if (per_sm > 16) per_sm = 16;
-    if (per_sm < 1) per_sm = 1;
-    const int64_t cap = (int64_t)sb_sm_count(iv->device) * per_sm;
+    const int64_t cap = (int64_t)sb_sm_count(iv->device) * kBlocksPerSm;   // persistent grid: 48 warps per SM
     if (blocks > cap) blocks = cap;
+    // general-path state: one slice of `words` per warp of the largest grid, zeroed once (the kernel leaves it zero)
+    const size_t words = (size_t)((iv->n_features + 1) & ~1);
+    const size_t need = (size_t)cap * kWarpsPerBlock * words;
+    if (iv->scratch == nullptr || iv->scratch_words < need) {
+        sb_intervals* mut = const_cast<sb_intervals*>(iv);
+        if (mut->scratch) SB_CHECK_CUDA(cudaFree(mut->scratch));
+        mut->scratch = nullptr;
+        SB_CHECK_CUDA(cudaMalloc(&mut->scratch, need * sizeof(int32_t)));
+        SB_CHECK_CUDA(cudaMemset(mut->scratch, 0, need * sizeof(int32_t)));
+        mut->scratch_words = need;
+    }
     LabelArgs a;
     a.iv_start = iv->start; a.iv_end = iv->end; a.iv_feat = iv->feat; a.iv_cmax = iv->cmax;
     a.chrom_off = iv->chrom_off; a.tab = iv->tab; a.tab_off = iv->tab_off; a.tab_shift = iv->tab_shift;
-    a.n_features = iv->n_features; a.n_chrom = iv->n_chrom; a.meta_in_smem = meta_in_smem;
+    a.n_features = iv->n_features; a.n_chrom = iv->n_chrom; a.meta_in_smem = meta_in_smem; a.scratch = iv->scratch;
     cudaStream_t s = (cudaStream_t)stream;
 #define SB_LAUNCH_LABEL(T)                                                                                  \
     do {                                                                                                    \
-        if (smem > 48 * 1024)                                                                               \
-            SB_CHECK_CUDA(cudaFuncSetAttribute(label_bins_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                               (int)smem));                                                 \
         label_bins_kernel<T><<<(int)blocks, kWarpsPerBlock * 32, smem, s>>>(a, chrom, bin_start, bin_end, n, thr_i, \
                                                                             (T*)out);                       \
     } while (0)

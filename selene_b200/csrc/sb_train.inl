@@ -507,6 +507,44 @@ extern "C" int sb_net_sgd_step(sb_net* net, const float* grads, float lr, float 
     return SB_OK;
 }
 
+// device (k_f32 x ldw_f32, K index = tap*cin + channel; FC after a conv stack position-major) <-> torch layout
+// (conv (cout, cin, k), fc (cout, cin)); `to_host` selects the direction
+static void layer_layout_copy(const NetLayer& N, std::vector<float>& dev, float* torch_w, bool to_host) {
+    auto xfer = [&](size_t di, size_t ti) {
+        if (to_host) torch_w[ti] = dev[di];
+        else dev[di] = torch_w[ti];
+    };
+    if (N.type == SB_LAYER_CONV) {
+        for (int o = 0; o < N.cout; ++o)
+            for (int c = 0; c < N.cin; ++c)
+                for (int j = 0; j < N.k; ++j)
+                    xfer(((size_t)j * N.cin + c) * N.ldw_f32 + o, ((size_t)o * N.cin + c) * N.k + j);
+    } else {
+        // the FC after the conv stack was packed position-major: K index = t*C + c  <->  torch index c*T + t
+        const int C = N.fc_prev_c, Tn = N.fc_prev_t;
+        for (int o = 0; o < N.cout; ++o)
+            for (int kk = 0; kk < N.cin; ++kk) {
+                size_t torch_idx = (size_t)kk;
+                if (C > 0 && Tn > 1) { const int t = kk / C, c = kk % C; torch_idx = (size_t)c * Tn + t; }
+                xfer((size_t)kk * N.ldw_f32 + o, (size_t)o * N.cin + torch_idx);
+            }
+    }
+}
+
+static int get_layer_tensor(const sb_net* net, int layer, const float* src_w, const float* src_b, float* w_host,
+                            float* b_host) {
+    const NetLayer& N = net->layers[(size_t)layer];
+    SB_CHECK_CUDA(cudaSetDevice(net->device));
+    SB_CHECK_CUDA(cudaDeviceSynchronize());
+    const size_t nw = (size_t)N.k_f32 * N.ldw_f32;
+    std::vector<float> w(nw), b((size_t)N.ldw_f32);
+    SB_CHECK_CUDA(cudaMemcpy(w.data(), src_w, nw * 4, cudaMemcpyDeviceToHost));
+    SB_CHECK_CUDA(cudaMemcpy(b.data(), src_b, (size_t)N.ldw_f32 * 4, cudaMemcpyDeviceToHost));
+    for (int o = 0; o < N.cout; ++o) b_host[o] = b[(size_t)o];
+    layer_layout_copy(N, w, w_host, true);
+    return SB_OK;
+}
+
 // Current fp32 parameters of one layer in torch layout: conv (cout, cin, k), fc (cout, cin); bias (cout).
 // `from_grads` != NULL reads that flat gradient vector instead of the weights (same layout mapping).
 extern "C" int sb_net_get_layer_params(const sb_net* net, int layer, const float* from_grads, float* w_host,
@@ -515,29 +553,32 @@ extern "C" int sb_net_get_layer_params(const sb_net* net, int layer, const float
     const NetLayer& N = net->layers[(size_t)layer];
     SB_REQUIRE(N.type != SB_LAYER_BILSTM, "sb_net_get_layer_params: BiLSTM layers are not exportable yet");
     SB_REQUIRE(!from_grads || net->train, "sb_net_get_layer_params: gradients need sb_net_train_init");
+    return get_layer_tensor(net, layer, from_grads ? from_grads + net->train->goff_w[(size_t)layer] : N.wf,
+                            from_grads ? from_grads + net->train->goff_b[(size_t)layer] : N.biasf, w_host, b_host);
+}
+
+// SGD momentum buffers of one layer in torch layout (the ``momentum_buffer`` entries of torch.optim.SGD's state:
+// what a Selene checkpoint stores under "optimizer", train_model.py:430-437).  All zeros before the first step.
+extern "C" int sb_net_get_layer_momentum(const sb_net* net, int layer, float* w_host, float* b_host) {
+    SB_REQUIRE(net && net->train && layer >= 0 && layer < (int)net->layers.size() && w_host && b_host,
+               "sb_net_get_layer_momentum: bad arguments (sb_net_train_init first)");
+    SB_REQUIRE(net->layers[(size_t)layer].type != SB_LAYER_BILSTM, "sb_net_get_layer_momentum: BiLSTM layers are not trainable");
+    return get_layer_tensor(net, layer, net->train->mom_w[(size_t)layer], net->train->mom_b[(size_t)layer], w_host, b_host);
+}
+
+// Restores the momentum buffers of one layer from torch-layout host arrays (checkpoint resume, train_model.py:296-326).
+extern "C" int sb_net_set_layer_momentum(sb_net* net, int layer, const float* w_host, const float* b_host) {
+    SB_REQUIRE(net && net->train && layer >= 0 && layer < (int)net->layers.size() && w_host && b_host,
+               "sb_net_set_layer_momentum: bad arguments (sb_net_train_init first)");
+    const NetLayer& N = net->layers[(size_t)layer];
+    SB_REQUIRE(N.type != SB_LAYER_BILSTM, "sb_net_set_layer_momentum: BiLSTM layers are not trainable");
     SB_CHECK_CUDA(cudaSetDevice(net->device));
     SB_CHECK_CUDA(cudaDeviceSynchronize());
     const size_t nw = (size_t)N.k_f32 * N.ldw_f32;
-    std::vector<float> w(nw), b((size_t)N.ldw_f32);
-    const float* src_w = from_grads ? from_grads + net->train->goff_w[(size_t)layer] : N.wf;
-    const float* src_b = from_grads ? from_grads + net->train->goff_b[(size_t)layer] : N.biasf;
-    SB_CHECK_CUDA(cudaMemcpy(w.data(), src_w, nw * 4, cudaMemcpyDeviceToHost));
-    SB_CHECK_CUDA(cudaMemcpy(b.data(), src_b, (size_t)N.ldw_f32 * 4, cudaMemcpyDeviceToHost));
-    for (int o = 0; o < N.cout; ++o) b_host[o] = b[(size_t)o];
-    if (N.type == SB_LAYER_CONV) {
-        for (int o = 0; o < N.cout; ++o)
-            for (int c = 0; c < N.cin; ++c)
-                for (int j = 0; j < N.k; ++j)
-                    w_host[((size_t)o * N.cin + c) * N.k + j] = w[((size_t)j * N.cin + c) * N.ldw_f32 + o];
-    } else {
-        // the FC after the conv stack was packed position-major: K index = t*C + c  <->  torch index c*T + t
-        const int C = N.fc_prev_c, Tn = N.fc_prev_t;
-        for (int o = 0; o < N.cout; ++o)
-            for (int kk = 0; kk < N.cin; ++kk) {
-                size_t torch_idx = (size_t)kk;
-                if (C > 0 && Tn > 1) { const int t = kk / C, c = kk % C; torch_idx = (size_t)c * Tn + t; }
-                w_host[(size_t)o * N.cin + torch_idx] = w[(size_t)kk * N.ldw_f32 + o];
-            }
-    }
+    std::vector<float> w(nw, 0.f), b((size_t)N.ldw_f32, 0.f);
+    layer_layout_copy(N, w, const_cast<float*>(w_host), false);
+    for (int o = 0; o < N.cout; ++o) b[(size_t)o] = b_host[o];
+    SB_CHECK_CUDA(cudaMemcpy(net->train->mom_w[(size_t)layer], w.data(), nw * 4, cudaMemcpyHostToDevice));
+    SB_CHECK_CUDA(cudaMemcpy(net->train->mom_b[(size_t)layer], b.data(), (size_t)N.ldw_f32 * 4, cudaMemcpyHostToDevice));
     return SB_OK;
 }

@@ -171,6 +171,7 @@ class B200Net(object):
                                            _lib.perm_arg(self.perm), self.device, C.byref(h)),
                    "sb_net_create")
         self._h = h
+        self.has_recurrence = any(l["type"] == "bilstm" for l in layers)   # outputs depend on row grouping (DanQ)
         self.n_outputs = int(self._lib.sb_net_n_outputs(h))
         self.flops_per_seq = float(self._lib.sb_net_flops_per_seq(h))
         self._ws = None

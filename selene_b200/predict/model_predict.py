@@ -9,10 +9,8 @@ of ``batch_size`` exist only where the reference's behaviour depends on them (th
 the ISM baseline, §9.21 of SURVEY.md).  File outputs keep the reference's names, columns and number
 formats (handler.py:15-114,190-235; write_ref_alt_handler.py:83-108).
 """
-import io
 import math
 import os
-import threading
 import warnings
 
 import numpy as np
@@ -21,7 +19,7 @@ from .. import _lib
 from ..nets import B200Net, layers_from_module
 from ..sequences import Genome, codes_of_string
 from ._in_silico_mutagenesis import ism_mutations_device
-from ._variant_effect_prediction import read_vcf_file, build_ref_alt_strings, _get_ref_idxs
+from ._variant_effect_prediction import VariantTable, read_vcf_file, build_ref_alt_strings, _get_ref_idxs  # noqa: F401
 
 ISM_COLS = ["pos", "ref", "alt"]                                                  # model_predict.py:39
 VARIANTEFFECT_COLS = ["chrom", "pos", "name", "ref", "alt", "strand", "ref_match", "contains_unk"]  # :40
@@ -97,107 +95,24 @@ def format_e2_rows(data, row_prefixes=None):
     return buf.cpu().numpy(), off.cpu().numpy()
 
 
-_TEXT_STAGE = {}   # device index -> (pinned uint8 staging buffer for formatted text)
-_TEXT_CHUNK_BYTES = 96 << 20
+from ._writers import (submit_tsv, write_tsv, write_hdf5, write_row_labels, prefixes_from_ids)  # noqa: E402,F401
 
 
-def _format_rows_device(t, prefixes):
-    """Formats rows of CUDA float32 tensor ``t`` with their byte prefixes; returns (device uint8 buffer, total)."""
-    import torch
-    lib = _lib.load()
-    n, F = int(t.shape[0]), int(t.shape[1])
-    sizes = torch.empty(n, dtype=torch.int64, device=t.device)
-    _lib.check(lib.sb_format_e2_row_bytes(_lib.ptr(t), n, F, _lib.ptr(sizes), _lib.stream_ptr()), "sb_format_e2_row_bytes")
-    lens = np.fromiter((len(p) for p in prefixes), dtype=np.int64, count=n)
-    po = np.zeros(n + 1, dtype=np.int64)
-    np.cumsum(lens, out=po[1:])
-    pre = torch.from_numpy(np.frombuffer(b"".join(prefixes), dtype=np.uint8).copy()).to(t.device)
-    pre_off = torch.from_numpy(po).to(t.device)
-    sizes += pre_off[1:] - pre_off[:-1]
-    off = torch.zeros(n + 1, dtype=torch.int64, device=t.device)
-    torch.cumsum(sizes, 0, out=off[1:])
-    total = int(off[-1].item())
-    buf = torch.empty(total, dtype=torch.uint8, device=t.device)
-    _lib.check(lib.sb_format_e2_rows_prefixed(_lib.ptr(t), n, F, _lib.ptr(off), _lib.ptr(pre), _lib.ptr(pre_off),
-                                              _lib.ptr(buf), _lib.stream_ptr()), "sb_format_e2_rows_prefixed")
-    return buf, total
-
-
-def write_tsv(path, columns_for_ids, features, ids, data, append=False, id_bytes=None):
-    """Rows ``id columns + "{:.2e}" per value`` (handler.py:36-42,99-114).  ``data``: (n, F) numpy array or CUDA
-    tensor.  The file body — id columns and numbers — is assembled by ``sb_format_e2_rows_prefixed`` on the device in
-    chunks of <= 96 MB of text, each read back through a persistent pinned buffer and written with one call."""
-    import torch
-    t = data if isinstance(data, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32))
-    t = t.to(device="cuda", dtype=torch.float32).contiguous()
-    n, F = int(t.shape[0]), int(t.shape[1])
-    dev = t.device.index or 0
-    rows_per_chunk = max(1, _TEXT_CHUNK_BYTES // (F * 10 + 64))
-    with open(path, "ab" if append else "wb") as fh:
-        if not append:
-            fh.write("{0}\n".format("\t".join(list(columns_for_ids) + list(features))).encode())
-        for r0 in range(0, n, rows_per_chunk):
-            r1 = min(n, r0 + rows_per_chunk)
-            prefixes = (id_bytes[r0:r1] if id_bytes is not None else
-                        [("\t".join(str(i) for i in info) + "\t").encode() for info in ids[r0:r1]])
-            buf, total = _format_rows_device(t[r0:r1], prefixes)
-            skey = (dev, threading.get_ident())
-            stage = _TEXT_STAGE.get(skey)
-            if stage is None or stage.numel() < total:
-                stage = _TEXT_STAGE[skey] = torch.empty(max(total, _TEXT_CHUNK_BYTES + (8 << 20)), dtype=torch.uint8,
-                                                       pin_memory=True)
-            stage[:total].copy_(buf, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            fh.write(memoryview(stage.numpy())[:total])
-
-
-def write_hdf5(path, data):
-    """Dataset ``data`` float64 (n_rows, n_features) (handler.py:205-218)."""
-    import h5py
-    if hasattr(data, "is_cuda"):
-        data = data.cpu().numpy()
-    with h5py.File(path, "w") as fh:
-        fh.create_dataset("data", data=np.asarray(data, dtype=np.float64))
-
-
-def write_row_labels(path, columns_for_ids, ids):
-    with open(path, "w") as fh:
-        fh.write("{0}\n".format("\t".join(columns_for_ids)))
-        for info in ids:
-            fh.write("{0}\n".format("\t".join(str(i) for i in info)))
-
-
-_WRITER_POOL = None
-
-
-def _writer_pool():
-    """Two persistent writer threads (persistent so that their pinned text buffers are allocated once)."""
-    global _WRITER_POOL
-    if _WRITER_POOL is None:
-        from concurrent.futures import ThreadPoolExecutor
-        _WRITER_POOL = ThreadPoolExecutor(max_workers=2, thread_name_prefix="sb_writer")
-    return _WRITER_POOL
-
-
-def _write_outputs(results, ids, features, cols, output_path_prefix, output_format, defer=False):
-    """results: ordered list of (handler_filename, prefix_override or None, array).  TSV files of one call are written
-    by the two writer threads side by side (the file writes release the GIL and dominate the time).  With ``defer``
-    the futures are returned instead of awaited, so the caller can score the next input meanwhile."""
+def _write_outputs(results, ids, features, cols, output_path_prefix, output_format, defer=False, prefix=None):
+    """results: ordered list of (handler_filename, prefix_override or None, array).  TSV files are written by the
+    writer pool of ``_writers`` (formatted on the device, chunks written concurrently at their offsets).  ``ids``: list
+    of id tuples (may be None when ``prefix`` = (bytes, offsets) of the id columns is given and the format is TSV).
+    With ``defer`` the ``finish`` callables are returned instead of awaited, so the caller can score the next input
+    meanwhile."""
     labels_written = False
-    # the id columns of a row are the same in every file: encode them once
-    id_bytes = ([("\t".join(str(i) for i in info) + "\t").encode() for info in ids]
-                if output_format == "tsv" and len(results) > 1 else None)
-    futures = []
-    threaded = output_format == "tsv" and (defer or (len(results) > 1 and len(ids) >= 1024))
-    for name, prefix, arr in results:
-        opp = output_path_prefix if prefix is None else prefix
+    if output_format == "tsv" and prefix is None:
+        prefix = prefixes_from_ids(ids)
+    finishers = []
+    for name, prefix_override, arr in results:
+        opp = output_path_prefix if prefix_override is None else prefix_override
         out_dir, fprefix, sp = _scores_filepath(opp, name)
         if output_format == "tsv":
-            if threaded:
-                futures.append(_writer_pool().submit(_write_tsv_job, torch_device_of(arr), sp + ".tsv", cols, features, ids,
-                                                     arr, id_bytes))
-            else:
-                write_tsv(sp + ".tsv", cols, features, ids, arr, id_bytes=id_bytes)
+            finishers.append(submit_tsv(sp + ".tsv", cols, features, arr, prefix[0], prefix[1]))
         else:
             write_hdf5(sp + ".h5", arr)
             if not labels_written:
@@ -209,21 +124,10 @@ def _write_outputs(results, ids, features, cols, output_path_prefix, output_form
                 write_row_labels(os.path.join(out_dir, lf), cols, ids)
                 labels_written = True
     if defer:
-        return futures
-    for f in futures:
-        f.result()      # re-raises a writer's exception
+        return finishers
+    for f in finishers:
+        f()      # waits, closes the file, re-raises a writer's exception
     return []
-
-
-def torch_device_of(arr):
-    return arr.device.index if hasattr(arr, "is_cuda") and arr.is_cuda else None
-
-
-def _write_tsv_job(device_index, path, cols, features, ids, arr, id_bytes):
-    import torch
-    if device_index is not None:
-        torch.cuda.set_device(device_index)
-    write_tsv(path, cols, features, ids, arr, id_bytes=id_bytes)
 
 
 _PINNED = {}   # (name, shape, dtype) -> persistent pinned staging tensor (allocating pinned memory per call is slow)
@@ -298,13 +202,15 @@ class AnalyzeSequences(object):
         else:
             Genome.update_bases_order(['A', 'C', 'G', 'T'])     # :182-183
         self._write_mem_limit = write_mem_limit
+        self.multi_gpu_output = "shards"     # or "gather": see variant_effect_prediction
         # the weights are re-normalised for models that do it on every forward (heartenn.py:73-78)
-        if hasattr(model, "_renorm") or model.__class__.__name__ == "HeartENN":
+        from ..nets import unwrap_non_strand_specific
+        inner = unwrap_non_strand_specific(model)[0]
+        if hasattr(inner, "_renorm") or inner.__class__.__name__ == "HeartENN":
             with torch.no_grad():
-                for m in model.modules():
+                for m in inner.modules():
                     if isinstance(m, (torch.nn.Conv1d, torch.nn.Linear)):
                         m.weight.data.renorm_(2, 0, 0.9)
-        from ..nets import unwrap_non_strand_specific
         self.net = B200Net(layers_from_module(model), sequence_length, perm=Genome.perm(), device=device,
                            strand_mode=unwrap_non_strand_specific(model)[1])
         if self.net.n_outputs != len(self.features):
@@ -340,7 +246,9 @@ class AnalyzeSequences(object):
         ref = np.asarray(ref_codes, dtype=np.uint8)
         alt = np.asarray(alt_codes, dtype=np.uint8)
         rc = np.zeros(n, dtype=np.uint8)
-        if strands is not None:
+        if isinstance(strands, np.ndarray) and strands.dtype != object and strands.dtype.kind in "bui":
+            rc = (strands != 0).astype(np.uint8)            # already a minus-strand mask
+        elif strands is not None:
             rc = np.fromiter(((1 if s in ('-', 1, True) else 0) for s in strands), dtype=np.uint8, count=n)
         # model rows (ref_i, alt_i): code row i with the VCF ref / the alt forced at the variant row;
         # on the minus strand the finished encodings are reverse-complemented (model_predict.py:1102-1110),
@@ -413,20 +321,32 @@ class AnalyzeSequences(object):
         return out
 
     def ism_scores(self, sequence, save_data=("abs_diffs", "logits"), start_position=0, end_position=None,
-                   to_host=True):
-        """ISM of one (already padded/truncated, upper-cased) sequence.  Returns (mutation list as
-        (pos int array, alt code array), dict of arrays, baseline prediction (1, F))."""
+                   to_host=True, mutate_n_bases=1):
+        """ISM of one (already padded/truncated, upper-cased) sequence.  Returns (mutation list, dict of arrays,
+        baseline prediction (1, F)).  The mutation list is (pos int array, alt code array) for single-base ISM —
+        enumerated on the device — and the reference's list of ``[(pos, base), ...]`` for ``mutate_n_bases > 1``
+        (host enumeration in itertools order, _in_silico_mutagenesis.py:91-107; rows are built on the device)."""
         import torch
         want = self._want(save_data)
         if end_position is None:
             end_position = self.sequence_length
-        pos, alt, codes = ism_mutations_device(sequence, start_position, end_position, self.reference_sequence)
         self.net.set_recurrence(self.batch_size, 1)
-        base = self.net.forward_codes(codes, precision=self.precision)          # (1, F) baseline
-        m = int(pos.numel())
         req = [s for s in want if s != "predictions"]
         if "predictions" in want:
             req.append("alt_predictions")
+        if mutate_n_bases == 1:
+            pos, alt, codes = ism_mutations_device(sequence, start_position, end_position, self.reference_sequence)
+            muts, m = (pos, alt), int(pos.numel())
+        else:
+            from ._in_silico_mutagenesis import in_silico_mutagenesis_sequences
+            muts = in_silico_mutagenesis_sequences(sequence, mutate_n_bases, self.reference_sequence,
+                                                   start_position, end_position)
+            m = len(muts)
+            codes = torch.from_numpy(codes_of_string(sequence).copy()).cuda().reshape(1, -1)
+            mpos = torch.from_numpy(np.array([[p for p, _ in mm] for mm in muts], dtype=np.int64).reshape(m, -1)).cuda()
+            malt = torch.from_numpy(np.array([[_CODE[b] for _, b in mm] for mm in muts],
+                                             dtype=np.uint8).reshape(m, -1)).cuda()
+        base = self.net.forward_codes(codes, precision=self.precision)          # (1, F) baseline
         base_pair, base_index = base, None
         if "logits" in want:
             # logit_score_handler.py:118-124 clamps the shared baseline array in place during the first
@@ -435,22 +355,39 @@ class AnalyzeSequences(object):
             clamped = torch.where(clamped >= 1, torch.full_like(base, 0.999999), clamped)
             base_pair = torch.cat([base, clamped], dim=0).contiguous()
             base_index = (torch.arange(m, device=base.device) >= self.batch_size).to(torch.int32)
-        out = self.net.forward_score(codes, torch.zeros(m, dtype=torch.int32, device=codes.device), pos, alt, m,
-                                     _lib.SB_PAIR_BASELINE, precision=self.precision, base_pred=base_pair,
-                                     base_index=base_index, want=tuple(req))
+        if mutate_n_bases == 1:
+            out = self.net.forward_score(codes, torch.zeros(m, dtype=torch.int32, device=codes.device), pos, alt, m,
+                                         _lib.SB_PAIR_BASELINE, precision=self.precision, base_pred=base_pair,
+                                         base_index=base_index, want=tuple(req))
+        else:
+            F = len(self.features)
+            out = {k: torch.empty((m, F), dtype=torch.float32, device=codes.device) for k in req}
+            step = max(self.batch_size, (1 << 16) // self.batch_size * self.batch_size)
+            for a in range(0, m, step):
+                z = min(m, a + step)
+                rows = codes.repeat(z - a, 1)
+                rows.scatter_(1, mpos[a:z], malt[a:z])
+                self.net.forward_score(rows, None, None, None, z - a, _lib.SB_PAIR_BASELINE, precision=self.precision,
+                                       base_pred=base_pair, base_index=None if base_index is None else base_index[a:z],
+                                       want=tuple(req), outs={k: v[a:z] for k, v in out.items()})
         if "logits" in want:
             base = base_pair[1:2]
         if to_host:
             out = _to_host(out)
-            return (pos.cpu().numpy(), alt.cpu().numpy()), out, base.cpu().numpy()
-        return (pos, alt), out, base
+            if mutate_n_bases == 1:
+                muts = (pos.cpu().numpy(), alt.cpu().numpy())
+            return muts, out, base.cpu().numpy()
+        return muts, out, base
 
     # ----------------------------------------------------------------------------------------------
     # reference entry points
     # ----------------------------------------------------------------------------------------------
     def in_silico_mutagenesis(self, sequence, save_data, output_path_prefix="ism", mutate_n_bases=1,
-                              output_format="tsv", start_position=0, end_position=None, _defer_writes=False):
-        """model_predict.py:662-799 (``mutate_n_bases`` is ignored there too: hard-wired to 1, :763-764)."""
+                              output_format="tsv", start_position=0, end_position=None, _defer_writes=False,
+                              _honour_n_bases=False):
+        """model_predict.py:662-799.  The reference checks ``mutate_n_bases`` but then hard-wires single-base ISM
+        (:763-764), and so does this method; ``in_silico_mutagenesis_from_file`` honours it (:907-912) and calls this
+        with ``_honour_n_bases``."""
         if end_position is None:
             end_position = self.sequence_length
         if start_position >= end_position:
@@ -490,9 +427,15 @@ class AnalyzeSequences(object):
         want = self._want(save_data)
         # scores stay in HBM: the writers format them there (only the mutation list comes to the host)
         import torch
-        (pos, alt), out, base = self.ism_scores(sequence, want, start_position, end_position, to_host=False)
-        pos, alt = pos.cpu().numpy(), alt.cpu().numpy()
-        ids = [(str(int(p)), sequence[int(p)], "ACGT"[int(a)]) for p, a in zip(pos, alt)]
+        n_bases = mutate_n_bases if _honour_n_bases else 1
+        muts, out, base = self.ism_scores(sequence, want, start_position, end_position, to_host=False,
+                                          mutate_n_bases=n_bases)
+        if n_bases == 1:
+            pos, alt = muts[0].cpu().numpy(), muts[1].cpu().numpy()
+            ids = [(str(int(p)), sequence[int(p)], "ACGT"[int(a)]) for p, a in zip(pos, alt)]
+        else:
+            from ._in_silico_mutagenesis import _ism_sample_id
+            ids = [_ism_sample_id(sequence, mm) for mm in muts]
         results = []
         for s in want:
             if s == "predictions":
@@ -652,16 +595,21 @@ class AnalyzeSequences(object):
             nxt = self.in_silico_mutagenesis(arr.tobytes().decode("latin-1"), save_data, output_path_prefix=file_prefix,
                                              mutate_n_bases=mutate_n_bases, output_format=output_format,
                                              start_position=start_position, end_position=end_position,
-                                             _defer_writes=True)
-            for f in pending:
-                f.result()
+                                             _defer_writes=True, _honour_n_bases=True)
+            for finish in pending:
+                finish()
             pending = nxt or []
-        for f in pending:
-            f.result()
+        for finish in pending:
+            finish()
 
     def variant_effect_prediction(self, vcf_file, save_data, output_dir=None, output_format="tsv",
                                   strand_index=None, require_strand=False):
-        """model_predict.py:952-1141."""
+        """model_predict.py:952-1141.  The VCF is parsed into a columnar ``VariantTable``; SNVs are scored straight from
+        its arrays, other variants from host-built windows; the id columns of the output files are assembled from the
+        table's field slices.  Under ``torch.distributed`` every rank scores a contiguous shard of the variants and
+        (``self.multi_gpu_output == "shards"``, the default) writes its rows into the shared output files at its byte
+        offset; ``"gather"`` collects the score tiles on rank 0 with one NCCL gather per score type instead."""
+        import torch
         path, filename = os.path.split(vcf_file)
         output_path_prefix = '.'.join(filename.split('.')[:-1])
         if output_dir:
@@ -669,42 +617,61 @@ class AnalyzeSequences(object):
         else:
             output_dir = path
         output_path_prefix = os.path.join(output_dir, output_path_prefix)
-        variants = read_vcf_file(vcf_file, strand_index=strand_index, require_strand=require_strand,
-                                 output_NAs_to_file="{0}.NA".format(output_path_prefix),
-                                 seq_context=(self._start_radius, self._end_radius),
-                                 reference_sequence=self.reference_sequence)
-        want = self._want(save_data)
-        # one process per GPU: every rank scores a contiguous shard of the variant list and rank 0
-        # gathers the score tiles once (selene_b200/sharding.py); single-process runs skip all of it
-        all_variants, rank, world = variants, 0, 1
+        rank, world = 0, 1
         try:
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized():
                 rank, world = dist.get_rank(), dist.get_world_size()
         except ImportError:
-            pass
+            dist = None
+        import time
+        timing = self.last_timing = {}
+        t_stage = time.perf_counter()
+
+        def lap(name):
+            nonlocal t_stage
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            timing[name] = timing.get(name, 0.0) + now - t_stage
+            t_stage = now
+        G = self.reference_sequence
+        table = VariantTable.from_vcf(vcf_file, strand_index=strand_index, require_strand=require_strand,
+                                      output_NAs_to_file="{0}.NA".format(output_path_prefix) if rank == 0 else None,
+                                      seq_context=(self._start_radius, self._end_radius), reference_sequence=G)
+        lap("parse_s")
+        want = self._want(save_data)
+        n_all = len(table)
+        # networks with a batch-axis recurrence (DanQ): the reference's batches are consecutive runs of
+        # ``batch_size`` variants in file order, so shards start on batch boundaries and mixed SNV / indel files are
+        # scored in one pass in file order
+        recurrent = getattr(self.net, "has_recurrence", False)
+        local, lo = table, 0
         if world > 1:
             from ..sharding import shard_range
-            lo, hi = shard_range(len(all_variants), rank, world)
-            variants = all_variants[lo:hi]
-        n = len(variants)
+            if recurrent:
+                b_lo, b_hi = shard_range(-(-n_all // self.batch_size), rank, world)
+                lo, hi = min(n_all, b_lo * self.batch_size), min(n_all, b_hi * self.batch_size)
+            else:
+                lo, hi = shard_range(n_all, rank, world)
+            local = table.rows(lo, hi)
+        n = len(local)
         F = len(self.features)
         names = [s for s in want if s != "predictions"]
         if "predictions" in want:
             names += ["ref_predictions", "alt_predictions"]
-        import torch
         dev = torch.device("cuda", int(self.net.device))
         arrays = {k: torch.zeros((n, F), dtype=torch.float32, device=dev) for k in names}   # scores stay in HBM
         match = np.ones(n, dtype=bool)
         unk = np.zeros(n, dtype=bool)
-        snv = np.fromiter((len(v[3]) == 1 and len(v[4]) == 1 and v[4] not in "*-" for v in variants),
-                          dtype=bool, count=n)
-        idx = np.nonzero(snv)[0]
+        snv = local.is_snv.copy()
+        if recurrent and not snv.all():
+            snv[:] = False
+        idx = np.flatnonzero(snv)
         if len(idx):
-            r = self.score_snvs([variants[i][0] for i in idx], [variants[i][1] for i in idx],
-                                [_CODE.get(variants[i][3], 4) for i in idx],
-                                [_CODE.get(variants[i][4], 4) for i in idx],
-                                strands=[variants[i][5] for i in idx], save_data=want, to_host=False)
+            G._unpicklable_init()
+            to_genome = np.array([G._chrom_index[c] for c in local.chrom_names], dtype=np.int32)
+            r = self.score_snvs(to_genome[local.chrom_id[idx]], local.pos[idx], local.ref_code[idx], local.alt_code[idx],
+                                strands=local.minus[idx], save_data=want, to_host=False)
             if len(idx) == n:
                 for k in names:
                     arrays[k] = r[k]
@@ -713,11 +680,11 @@ class AnalyzeSequences(object):
                 for k in names:
                     arrays[k][didx] = r[k]
             match[idx], unk[idx] = r["ref_match"].cpu().numpy(), r["contains_unk"].cpu().numpy()
-        idx = np.nonzero(~snv)[0]
+        idx = np.flatnonzero(~snv)
         if len(idx):
             refs, alts = [], []
             for i in idx:
-                rs, als, m, u = build_ref_alt_strings(variants[i], self.reference_sequence, self.sequence_length,
+                rs, als, m, u = build_ref_alt_strings(local.variant(i), G, self.sequence_length,
                                                       self._start_radius, self._end_radius)
                 refs.append(codes_of_string(rs)); alts.append(codes_of_string(als))
                 match[i], unk[i] = m, u
@@ -725,19 +692,22 @@ class AnalyzeSequences(object):
             didx = torch.from_numpy(idx).to(dev)
             for k in names:
                 arrays[k][didx] = r[k]
-        for i, v in enumerate(variants):
-            if unk[i]:
-                warnings.warn("For variant ({0}, {1}, {2}, {3}, {4}, {5}), reference sequence contains "
-                              "unknown base(s)--will be marked `True` in the `contains_unk` column of the "
-                              ".tsv or the row_labels .txt file.".format(*v))
-            if not match[i]:
-                warnings.warn("For variant ({0}, {1}, {2}, {3}, {4}, {5}), reference does not match the "
-                              "reference genome. Predictions/scores associated with this variant--where we "
-                              "use '{3}' in the input sequence--will be marked `False` in the `ref_match` "
-                              "column of the .tsv or the row_labels .txt file".format(*v))
-        if world > 1:
+        lap("score_s")
+        for i in np.flatnonzero(unk):
+            warnings.warn("For variant ({0}, {1}, {2}, {3}, {4}, {5}), reference sequence contains "
+                          "unknown base(s)--will be marked `True` in the `contains_unk` column of the "
+                          ".tsv or the row_labels .txt file.".format(*local.variant(i)))
+        for i in np.flatnonzero(~match):
+            warnings.warn("For variant ({0}, {1}, {2}, {3}, {4}, {5}), reference does not match the "
+                          "reference genome. Predictions/scores associated with this variant--where we "
+                          "use '{3}' in the input sequence--will be marked `False` in the `ref_match` "
+                          "column of the .tsv or the row_labels .txt file".format(*local.variant(i)))
+        lap("warnings_s")
+        gather = world > 1 and (self.multi_gpu_output == "gather" or output_format != "tsv")
+        if gather:
             from ..sharding import gather_tiles
-            n_all = len(all_variants)
+            if recurrent:   # batch-aligned shards are not the equal split gather_tiles assumes
+                raise NotImplementedError("multi_gpu_output='gather' is not available for recurrent networks; use 'shards'")
             for k in list(arrays.keys()):
                 arrays[k] = gather_tiles(arrays[k], n_all, dst=0)
             mu = torch.from_numpy(np.stack([match, unk], axis=1).astype(np.float32)).to(dev)
@@ -745,8 +715,7 @@ class AnalyzeSequences(object):
             if rank != 0:
                 return None
             match, unk = g[:, 0].cpu().numpy() > 0.5, g[:, 1].cpu().numpy() > 0.5
-            variants = all_variants
-        ids = [tuple(v) + (bool(match[i]), bool(unk[i])) for i, v in enumerate(variants)]
+            local = table
         results = []
         out_dir, prefix = os.path.split(output_path_prefix)
         for s in want:
@@ -757,5 +726,20 @@ class AnalyzeSequences(object):
                     results.append(("predictions", p, arrays[tag + "_predictions"]))
             else:
                 results.append((s, None, arrays[s]))
-        _write_outputs(results, ids, self.features, VARIANTEFFECT_COLS, output_path_prefix, output_format)
+        lap("gather_s")
+        if output_format == "tsv":
+            pre = local.id_prefix(match, unk)
+            lap("id_columns_s")
+            finishers = [submit_tsv(_scores_filepath(output_path_prefix if p is None else p, name)[2] + ".tsv",
+                                    VARIANTEFFECT_COLS, self.features, arr, pre[0], pre[1],
+                                    dist_group=None if gather else "auto") for name, p, arr in results]
+            lap("submit_s")
+            for finish in finishers:
+                finish()
+            lap("write_s")
+            if world > 1 and not gather:
+                dist.barrier()      # every rank's rows are in the files when any rank returns
+        else:
+            ids = [local.variant(i) + (bool(match[i]), bool(unk[i])) for i in range(len(local))]
+            _write_outputs(results, ids, self.features, VARIANTEFFECT_COLS, output_path_prefix, output_format)
         return None

@@ -18,12 +18,13 @@ def shard_sizes(n, world):
     return [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
 
 
-def gather_tiles(local, n_total, dst=None, group=None):
-    """Gathers per-rank score tiles ``local`` (n_local, F) into the (n_total, F) matrix.
+def gather_tiles(local, n_total, dst=None, group=None, out=None):
+    """Gathers per-rank score tiles ``local`` (n_local, F) into the (n_total, F) matrix with ONE collective.
 
     ``dst=None``: every rank receives the full matrix (all_gather); otherwise only rank ``dst`` does
-    and the others get ``None`` (gather).  Shards may differ by one row; they are padded to the
-    largest shard for the collective and trimmed afterwards."""
+    and the others get ``None`` (gather).  Ranks receive straight into row blocks of one output tensor
+    (``out``, optional, (world * max shard, F), reusable across calls): no staging copies.  Shards may differ
+    by one row; they are padded to the largest shard for the collective and the result is compacted."""
     import torch
     import torch.distributed as dist
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
@@ -39,15 +40,16 @@ def gather_tiles(local, n_total, dst=None, group=None):
         padded = torch.zeros((m, F), dtype=local.dtype, device=local.device)
         padded[:local.shape[0]] = local
     padded = padded.contiguous()
-    if dst is None:
+    receives = dst is None or rank == dst
+    if receives and (out is None or tuple(out.shape) != (world * m, F) or out.dtype != local.dtype):
         out = torch.empty((world * m, F), dtype=local.dtype, device=local.device)
+    if dst is None:
         dist.all_gather_into_tensor(out, padded, group=group)
     else:
-        bufs = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
-        dist.gather(padded, bufs, dst=dst, group=group)
+        blocks = [out[r * m:(r + 1) * m] for r in range(world)] if rank == dst else None
+        dist.gather(padded, blocks, dst=dst, group=group)
         if rank != dst:
             return None
-        out = torch.cat(bufs, dim=0)
     if all(s == m for s in sizes):
         return out
     return torch.cat([out[r * m:r * m + sizes[r]] for r in range(world)], dim=0)

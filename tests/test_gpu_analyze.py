@@ -210,3 +210,62 @@ def test_get_predictions_fasta_bed_and_ism_from_file(tmp_path):
     az.in_silico_mutagenesis_from_file(qfa, ["abs_diffs"], str(tmp_path / "ismi"), use_sequence_name=False,
                                        start_position=0, end_position=2)
     assert sorted(os.listdir(str(tmp_path / "ismi"))) == ["0_abs_diffs.tsv", "1_abs_diffs.tsv", "2_abs_diffs.tsv"]
+
+
+def test_ism_from_file_honours_mutate_n_bases(tmp_path):
+    """model_predict.py:907-912: ``in_silico_mutagenesis_from_file`` passes ``mutate_n_bases`` on; ids are
+    ``pos;pos`` / ``ref;ref`` / ``alt;alt`` (_in_silico_mutagenesis.py:146-170), order = combinations x products."""
+    from selene_b200.predict.model_predict import AnalyzeSequences
+    from selene_b200.sequences import Genome
+    Genome.update_bases_order(['A', 'C', 'G', 'T'])
+    az = AnalyzeSequences(_deepsea(), sequence_length=1000, features=FEATS, reference_sequence=Genome,
+                          precision="fp32", batch_size=64)
+    r = np.random.default_rng(12)
+    seq = "".join(np.array(list("ACGT"))[r.integers(0, 4, 1000)].tolist())
+    fa = str(tmp_path / "two.fa")
+    open(fa, "w").write(">rec1 first token is the name\n%s\n" % seq)
+    out = str(tmp_path / "o")
+    az.in_silico_mutagenesis_from_file(fa, ["abs_diffs", "logits", "predictions"], out, mutate_n_bases=2,
+                                       start_position=497, end_position=503)
+    layers = O.deepsea_layers(1000, 919, seed=0)
+    muts = O.in_silico_mutagenesis_sequences(seq, 2, start_position=497, end_position=503)
+    assert len(muts) == 15 * 9
+    enc = O.sequence_to_encoding(seq)
+    base = O.stack_forward(enc[None], layers)
+    absd, logits = [], []
+    for i in range(0, len(muts), 64):
+        batch = np.stack([O.mutate_sequence(enc, m) for m in muts[i:i + 64]])
+        pred = O.stack_forward(batch, layers)
+        absd.append(O.abs_diff_score(pred, base))
+        logits.append(O.logit_score(pred, base))
+    absd, logits = np.concatenate(absd), np.concatenate(logits)
+    exp_ids = [(";".join(str(p) for p, _ in m), ";".join(seq[p] for p, _ in m), ";".join(b for _, b in m)) for m in muts]
+    for name, exp in (("abs_diffs", absd), ("logits", logits)):
+        header, ids, data = _read_tsv(os.path.join(out, "rec1_%s.tsv" % name), 3)
+        assert ids == exp_ids
+        assert np.abs(data - exp).max() <= 1e-5 + 6e-3 * np.abs(exp).max()
+    header, ids, data = _read_tsv(os.path.join(out, "rec1_predictions.tsv"), 3)
+    assert ids[0] == ("input_sequence", "NA", "NA") and ids[1:] == exp_ids
+
+
+def test_vep_two_processes_write_identical_files(tmp_path):
+    """variants sharded over ranks, every rank writes its rows into the shared files at its byte offset
+    ("shards"), or rank 0 gathers the tiles over NCCL and writes ("gather").  Both must be byte-identical to the
+    single-process files.  Needs >= 2 GPUs (run with gpurun --gpus 2); skipped otherwise."""
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = os.path.join(HERE, "multi_gpu_vep_check.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    single = subprocess.run([sys.executable, script, str(tmp_path), "single"], env=env, capture_output=True, text=True)
+    assert single.returncode == 0, single.stdout[-2000:] + single.stderr[-2000:]
+    for mode in ("shards", "gather"):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                            "--master-addr", "127.0.0.1", "--master-port", "29533", script, str(tmp_path), mode],
+                           env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        for f in sorted(os.listdir(os.path.join(str(tmp_path), "single"))):
+            a = open(os.path.join(str(tmp_path), "single", f), "rb").read()
+            b = open(os.path.join(str(tmp_path), mode, f), "rb").read()
+            assert a == b, "%s differs between the single-process and the 2-rank %s run" % (f, mode)

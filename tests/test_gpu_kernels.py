@@ -69,7 +69,7 @@ def test_encode_small_fasta_goldens(torch, tmp_path):
     assert Genome.encoding_to_sequence(exp) == "ANNNATCA"
 
 
-@pytest.mark.parametrize("L", [1, 7, 200, 1000])
+@pytest.mark.parametrize("L", [1, 7, 15, 17, 200, 511, 513, 1000, 1537])
 def test_encode_windows_vs_oracle(torch, genome_pair, L):
     g, G = genome_pair
     rng = np.random.default_rng(L)
@@ -166,7 +166,7 @@ def test_ism_golden_ATCCG(torch):
 # ------------------------------------------------------------------------------------------------
 # SNV ref/alt pairs
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("L", [1000, 201])
+@pytest.mark.parametrize("L", [1000, 201, 513, 16])
 def test_snv_pairs_vs_oracle(torch, genome_pair, L):
     g, G = genome_pair
     rng = np.random.default_rng(2024 + L)
@@ -189,6 +189,24 @@ def test_snv_pairs_vs_oracle(torch, genome_pair, L):
                       strands=[v[4] for v in variants], want_codes=True)
     ref_o, alt_o = res["ref"].cpu().numpy(), res["alt"].cpu().numpy()
     match, flags = res["ref_match"].cpu().numpy(), res["flags"].cpu().numpy()
+    # the bf16 tensors and the codes-only call (the path bench.py runs) carry the same information
+    res_b = G.snv_pairs([v[0] for v in variants], [v[1] - sr for v in variants],
+                        [code.get(v[2], 4) for v in variants], [code.get(v[3], 4) for v in variants], L, var_row,
+                        strands=[v[4] for v in variants], dtype="bfloat16", want_codes=True)
+    assert np.array_equal(res_b["ref"].float().cpu().numpy(), ref_o) and np.array_equal(res_b["alt"].float().cpu().numpy(), alt_o)
+    res_c = G.snv_pairs([v[0] for v in variants], [v[1] - sr for v in variants],
+                        [code.get(v[2], 4) for v in variants], [code.get(v[3], 4) for v in variants], L, var_row,
+                        strands=[v[4] for v in variants], want_onehot=False, want_codes=True)
+    codes = res_c["codes"].cpu().numpy()
+    assert np.array_equal(codes, res["codes"].cpu().numpy()) and np.array_equal(codes, res_b["codes"].cpu().numpy())
+    assert np.array_equal(res_c["ref_match"].cpu().numpy(), match) and np.array_equal(res_c["flags"].cpu().numpy(), flags)
+    from_onehot = np.where(ref_o.max(axis=2) == 1, ref_o.argmax(axis=2), 4)
+    for i, v in enumerate(variants):
+        o_var = L - 1 - var_row if v[4] == "-" else var_row
+        keep = np.arange(L) != o_var           # codes are the unsubstituted window with the strand applied
+        assert np.array_equal(codes[i][keep], from_onehot[i][keep])
+        if match[i]:
+            assert codes[i][o_var] == from_onehot[i][o_var]
     for i, (c, pos, ref, alt, strand) in enumerate(variants):
         start, end = pos - sr, pos + er
         # the reference queries without pad (model_predict.py:1061-1064); out-of-bounds variants are
@@ -717,14 +735,35 @@ def test_format_e2_matches_python(torch):
 
 
 def test_tsv_writer_uses_device_formatter(torch, tmp_path):
-    """handler.py:15-42,99-114: header, id columns, then "{:.2e}" per value."""
+    """handler.py:15-42,99-114: header, id columns, then "{:.2e}" per value; chunks are written concurrently at their
+    byte offsets (several 32 MB chunks for the large matrix), from a producer stream other than the default one."""
     from selene_b200.predict.model_predict import write_tsv
+    from selene_b200.predict import _writers
     data = np.array([[1.234e-5, 0.5, 0.999999], [1e-24, 123.456, 0.0]], dtype=np.float32)
     path = str(tmp_path / "x.tsv")
     ids = [("1", "A", "C"), ("2", "G", "T")]
     write_tsv(path, ["pos", "ref", "alt"], ["f0", "f1", "f2"], ids, data)
-    write_tsv(path, ["pos", "ref", "alt"], ["f0", "f1", "f2"], ids[:1], torch.from_numpy(data[:1]).cuda(), append=True)
     lines = open(path).read().split("\n")
-    assert lines[0] == "pos\tref\talt\tf0\tf1\tf2" and lines[-1] == "" and len(lines) == 5
-    for line, row, ident in zip(lines[1:4], [data[0], data[1], data[0]], ids + ids[:1]):
+    assert lines[0] == "pos\tref\talt\tf0\tf1\tf2" and lines[-1] == "" and len(lines) == 4
+    for line, row, ident in zip(lines[1:3], [data[0], data[1]], ids):
         assert line == "\t".join(ident) + "\t" + "\t".join("{:.2e}".format(p) for p in list(row))
+    write_tsv(path, ["pos"], ["f0"], [], np.zeros((0, 1), np.float32))          # no rows: header only
+    assert open(path).read() == "pos\tf0\n"
+    # ~100 MB of text -> 4 chunks on the writer pool; produced on a side stream
+    r = np.random.default_rng(1)
+    n, F = 12000, 919
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        big = torch.from_numpy((r.random((n, F)) * 10.0 ** r.integers(-6, 1, (n, F))).astype(np.float32)).cuda()
+        big = big * 1.0
+        ids = [("chr1", i, "rs%d" % i) for i in range(n)]
+        finish = _writers.submit_tsv(path, ["chrom", "pos", "id"], ["f%d" % i for i in range(F)], big,
+                                     *_writers.prefixes_from_ids(ids))
+    finish()
+    host = big.cpu().numpy()
+    with open(path) as fh:
+        assert fh.readline().count("\t") == F + 2
+        for i, line in enumerate(fh):
+            if i % 997 == 0 or i == n - 1:
+                assert line == "chr1\t%d\trs%d\t" % (i, i) + "\t".join("{:.2e}".format(p) for p in list(host[i])) + "\n"
+    assert i == n - 1
