@@ -274,6 +274,11 @@ def hbm_rooflines(G, names, seqs, hbm_gbs):
         gbs = bytes_launch / t / 1e9
         out.append(dict(kernel=kernel, achieved=gbs, peak=hbm_gbs, unit="GB/s", frac=gbs / hbm_gbs, ms=t * 1e3,
                         algorithmic_bytes_per_launch=bytes_launch, **kw))
+    # context: what a plain device fill (write-only stream, torch's vectorised fill kernel) reaches on this GPU
+    fill_buf = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+    t = _timed(lambda: fill_buf.zero_())
+    emit("torch.zero_ (library fill, context only)", float(fill_buf.numel()), t, units="1 GiB", bytes_per_unit=1.0)
+    del fill_buf
     n = 65536
     chrom = torch.from_numpy(rng.integers(0, len(names), n).astype(np.int32)).cuda()
     start = torch.from_numpy(rng.integers(0, per - 1000, n).astype(np.int64)).cuda()

@@ -114,15 +114,11 @@ __global__ void __launch_bounds__(kWinWarps * 32, 5) window_kernel(
     const uint8_t* __restrict__ ref_code, const uint8_t* __restrict__ alt_code, int var_row,
     void* __restrict__ alt_out, uint8_t* __restrict__ codes_out, uint8_t* __restrict__ ref_match) {
     __shared__ __align__(16) uint8_t stage[kWinWarps][kWinChunk];
-    __shared__ __align__(16) float4 lut_f32[5];      // one-hot rows by code, in the caller's channel order
-    __shared__ __align__(16) uint2 lut_bf16[5];
+    __shared__ __align__(16) uint2 lut_bf16[5];      // bf16 one-hot rows by code, in the caller's channel order
     __shared__ int64_t chrom_meta[2 * kWinMaxChromSmem];
     const int lane = threadIdx.x & 31;
     uint8_t* sm = stage[threadIdx.x >> 5];
-    if (threadIdx.x < 5) {
-        lut_f32[threadIdx.x] = onehot_f32(threadIdx.x, perm);
-        lut_bf16[threadIdx.x] = onehot_bf16(threadIdx.x, perm);
-    }
+    if (threadIdx.x < 5) lut_bf16[threadIdx.x] = onehot_bf16(threadIdx.x, perm);
     const bool meta_smem = n_chrom <= kWinMaxChromSmem;
     if (meta_smem)
         for (int i = threadIdx.x; i < n_chrom; i += blockDim.x) {
@@ -270,10 +266,10 @@ __global__ void __launch_bounds__(kWinWarps * 32, 5) window_kernel(
                         const int code = sm[i];
                         if (SNV) {
                             const bool hit = c0 + i == sub_at;
-                            if (out) o4[i] = lut_f32[hit ? sub_ref : code];
-                            if (alt_out) a4[i] = lut_f32[hit ? sub_alt : code];
+                            if (out) o4[i] = onehot_f32(hit ? sub_ref : code, perm);
+                            if (alt_out) a4[i] = onehot_f32(hit ? sub_alt : code, perm);
                         } else {
-                            o4[i] = lut_f32[code];
+                            o4[i] = onehot_f32(code, perm);      // selects: the shared-memory pipe is busy with the codes
                         }
                     }
                 } else {

@@ -25,16 +25,16 @@ SampleIndices = namedtuple("SampleIndices", ["indices", "weights"])
 
 
 def get_indices_and_probabilities(interval_lengths, indices):
-    """selene_sdk/utils/utils.py:34-67."""
-    select_interval_lens = np.array(interval_lengths)[indices]
-    weights = select_interval_lens / float(np.sum(select_interval_lens))
-    keep_indices = []
-    for index, weight in enumerate(weights):
-        if weight > 1e-10:
-            keep_indices.append(indices[index])
-    if len(keep_indices) == len(indices):
-        return indices, weights.tolist()
-    return get_indices_and_probabilities(interval_lengths, keep_indices)
+    """Sampling weights of the intervals ``indices``, proportional to their lengths; intervals whose share is
+    <= 1e-10 are dropped and the weights renormalised until none is (selene_sdk/utils/utils.py:34-67)."""
+    lengths = np.array(interval_lengths)
+    while True:
+        sel = lengths[indices]
+        weights = sel / float(np.sum(sel))
+        keep = [idx for idx, w in zip(indices, weights) if w > 1e-10]
+        if len(keep) == len(indices):
+            return indices, weights.tolist()
+        indices = keep
 
 
 class RandomPositionsSampler(object):
@@ -48,95 +48,78 @@ class RandomPositionsSampler(object):
                  validation_holdout=['chr6', 'chr7'], test_holdout=['chr8', 'chr9'], exclude_chrs=['_'],
                  sequence_length=1000, center_bin_to_predict=200, feature_thresholds=0.5, mode="train",
                  save_datasets=[], output_dir=None):
-        self.modes = list(self.BASE_MODES)
         self._features = features
+        self.n_features = len(features)
         self.seed = seed
-        np.random.seed(self.seed)
-        random.seed(self.seed + 1)
-        if isinstance(center_bin_to_predict, int):
-            if (sequence_length + center_bin_to_predict) % 2 != 0:
-                raise ValueError(
-                    "Sequence length of {0} with a center bin length of {1} "
-                    "is invalid. These 2 inputs should both be odd or both be "
-                    "even.".format(sequence_length, center_bin_to_predict))
-        if test_holdout:
-            self.modes.append("test")
-            if isinstance(validation_holdout, (list,)) and isinstance(test_holdout, (list,)):
-                self.validation_holdout = [str(c) for c in validation_holdout]
-                self.test_holdout = [str(c) for c in test_holdout]
-                self._holdout_type = "chromosome"
-            elif isinstance(validation_holdout, float) and isinstance(test_holdout, float):
-                self.validation_holdout = validation_holdout
-                self.test_holdout = test_holdout
-                self._holdout_type = "proportion"
-            else:
-                raise ValueError(
-                    "Validation holdout and test holdout must have the "
-                    "same type (list or float) but validation was "
-                    "type {0} and test was type {1}".format(type(validation_holdout), type(test_holdout)))
-        else:
-            self.test_holdout = None
-            if isinstance(validation_holdout, (list,)):
-                self.validation_holdout = [str(c) for c in validation_holdout]
-                self._holdout_type = "chromosome"
-            elif isinstance(validation_holdout, float):
-                self.validation_holdout = validation_holdout
-                self._holdout_type = "proportion"
-            else:
-                raise ValueError(
-                    "Validation holdout must be of type list (chromosomal "
-                    "holdout) or float (proportion holdout) but was type "
-                    "{0}.".format(type(validation_holdout)))
+        np.random.seed(seed)           # the two RNG streams of online_sampler.py:136-138, in this order
+        random.seed(seed + 1)
+        self.sequence_length = sequence_length
+        (self._start_window_radius, self._end_window_radius,
+         self._start_radius, self._end_radius) = self._radii(sequence_length, center_bin_to_predict)
+        self._holdout_type, self.validation_holdout, self.test_holdout = self._holdouts(validation_holdout,
+                                                                                        test_holdout)
+        self.modes = list(self.BASE_MODES) + (["test"] if self.test_holdout else [])
         if mode not in self.modes:
             raise ValueError("Mode must be one of {0}. Input was '{1}'.".format(self.modes, mode))
         self.mode = mode
-        self.sequence_length = sequence_length
-        window_radius = int(self.sequence_length / 2)
-        self._start_window_radius = window_radius
-        self._end_window_radius = window_radius
-        if self.sequence_length % 2 != 0:
-            self._end_window_radius += 1
-        if isinstance(center_bin_to_predict, int):
-            bin_radius = int(center_bin_to_predict / 2)
-            self._start_radius = bin_radius
-            self._end_radius = bin_radius
-            if center_bin_to_predict % 2 != 0:
-                self._end_radius += 1
-        else:
-            if not isinstance(center_bin_to_predict, list) or len(center_bin_to_predict) != 2:
-                raise ValueError(
-                    "`center_bin_to_predict` needs to be either an int or a list of "
-                    "two ints, but was type '{0}'".format(type(center_bin_to_predict)))
-            bin_start, bin_end = center_bin_to_predict
-            self._start_radius = self._start_window_radius - bin_start
-            self._end_radius = self._end_window_radius - (self.sequence_length - bin_end)
         self.reference_sequence = reference_sequence
-        self.n_features = len(self._features)
-        if isinstance(target_path, str):
-            self.target = GenomicFeatures(target_path, self._features, feature_thresholds=feature_thresholds)
-        else:
-            self.target = target_path
+        self.target = (GenomicFeatures(target_path, features, feature_thresholds=feature_thresholds)
+                       if isinstance(target_path, str) else target_path)
+        self.exclude_chrs = exclude_chrs
         self._save_datasets = {m: [] for m in save_datasets}
         self._output_dir = output_dir
-        self._sample_from_mode = {}
-        self._randcache = {}
-        for m in self.modes:
-            self._sample_from_mode[m] = None
-            self._randcache[m] = {"cache_indices": None, "sample_next": 0}
+        self._sample_from_mode = dict.fromkeys(self.modes)
+        self._randcache = {m: {"cache_indices": None, "sample_next": 0} for m in self.modes}
         self.sample_from_intervals = []
         self.interval_lengths = []
         self._initialized = False
-        self.exclude_chrs = exclude_chrs
 
-    # -- lazy partitioning, as random_positions_sampler.py:166-262 -----------------------------------
+    @staticmethod
+    def _radii(sequence_length, center_bin):
+        """(window start radius, window end radius, bin start radius, bin end radius) around a sampled position:
+        the odd base goes to the end side; a ``[start, end]`` bin is converted to radii (online_sampler.py:188-216)."""
+        if isinstance(center_bin, int) and (sequence_length + center_bin) % 2 != 0:
+            raise ValueError(
+                "Sequence length of {0} with a center bin length of {1} "
+                "is invalid. These 2 inputs should both be odd or both be "
+                "even.".format(sequence_length, center_bin))
+        w_start = sequence_length // 2
+        w_end = w_start + sequence_length % 2
+        if isinstance(center_bin, int):
+            return w_start, w_end, center_bin // 2, center_bin // 2 + center_bin % 2
+        if not isinstance(center_bin, list) or len(center_bin) != 2:
+            raise ValueError(
+                "`center_bin_to_predict` needs to be either an int or a list of "
+                "two ints, but was type '{0}'".format(type(center_bin)))
+        bin_start, bin_end = center_bin
+        return w_start, w_end, w_start - bin_start, w_end - (sequence_length - bin_end)
+
+    @staticmethod
+    def _holdouts(validation, test):
+        """("chromosome" | "proportion", validation holdout, test holdout or None); lists of names hold out whole
+        chromosomes, floats a share of them, and the two must agree in kind (online_sampler.py:147-186)."""
+        kind = lambda h: "chromosome" if isinstance(h, list) else ("proportion" if isinstance(h, float) else None)
+        norm = lambda h: [str(c) for c in h] if isinstance(h, list) else h
+        if not test:
+            if kind(validation) is None:
+                raise ValueError(
+                    "Validation holdout must be of type list (chromosomal "
+                    "holdout) or float (proportion holdout) but was type "
+                    "{0}.".format(type(validation)))
+            return kind(validation), norm(validation), None
+        if kind(validation) is None or kind(validation) != kind(test):
+            raise ValueError(
+                "Validation holdout and test holdout must have the "
+                "same type (list or float) but validation was "
+                "type {0} and test was type {1}".format(type(validation), type(test)))
+        return kind(validation), norm(validation), norm(test)
+
+    # -- lazy partitioning of the genome into the modes' sampling intervals (random_positions_sampler.py:166-262) --
     def init(func):
         @wraps(func)
         def dfunc(self, *args, **kwargs):
             if not self._initialized:
-                if self._holdout_type == "chromosome":
-                    self._partition_genome_by_chromosome()
-                else:
-                    self._partition_genome_by_proportion()
+                self._partition_genome()
                 for mode in self.modes:
                     self._update_randcache(mode=mode)
                 self._initialized = True
@@ -146,50 +129,38 @@ class RandomPositionsSampler(object):
     def _skip(self, chrom):
         return any(excl in chrom for excl in self.exclude_chrs)
 
-    def _partition_genome_by_proportion(self):
-        for chrom, len_chrom in self.reference_sequence.get_chr_lens():
-            if self._skip(chrom):
-                continue
-            self.sample_from_intervals.append((chrom, self.sequence_length, len_chrom - self.sequence_length))
-            self.interval_lengths.append(len_chrom)
-        n_intervals = len(self.sample_from_intervals)
-        select_indices = list(range(n_intervals))
-        np.random.shuffle(select_indices)
-        n_indices_validate = int(n_intervals * self.validation_holdout)
-        val_indices, val_weights = get_indices_and_probabilities(
-            self.interval_lengths, select_indices[:n_indices_validate])
-        self._sample_from_mode["validate"] = SampleIndices(val_indices, val_weights)
-        if self.test_holdout:
-            n_indices_test = int(n_intervals * self.test_holdout)
-            test_indices_end = n_indices_test + n_indices_validate
-            test_indices, test_weights = get_indices_and_probabilities(
-                self.interval_lengths, select_indices[n_indices_validate:test_indices_end])
-            self._sample_from_mode["test"] = SampleIndices(test_indices, test_weights)
-            tr_indices, tr_weights = get_indices_and_probabilities(
-                self.interval_lengths, select_indices[test_indices_end:])
+    def _partition_genome(self):
+        """One sampling interval ``[L, len - L)`` per kept chromosome, assigned to a mode either by name or by a
+        shuffled split (one ``np.random.shuffle`` call, as upstream); modes draw intervals with probability
+        proportional to ``interval_lengths`` (which upstream fills with ``len - 2L`` for chromosome holdouts and
+        with ``len`` for proportional ones)."""
+        L = self.sequence_length
+        by_name = self._holdout_type == "chromosome"
+        kept = [(c, n) for c, n in self.reference_sequence.get_chr_lens() if not self._skip(c)]
+        self.sample_from_intervals = [(c, L, n - L) for c, n in kept]
+        self.interval_lengths = [n - 2 * L if by_name else n for c, n in kept]
+        members = {m: [] for m in self.modes}
+        if by_name:
+            for i, (c, _n) in enumerate(kept):
+                if c in self.validation_holdout:
+                    members["validate"].append(i)
+                elif self.test_holdout and c in self.test_holdout:
+                    members["test"].append(i)
+                else:
+                    members["train"].append(i)
         else:
-            tr_indices, tr_weights = get_indices_and_probabilities(
-                self.interval_lengths, select_indices[n_indices_validate:])
-        self._sample_from_mode["train"] = SampleIndices(tr_indices, tr_weights)
-
-    def _partition_genome_by_chromosome(self):
-        by_mode = {m: [] for m in self.modes}
-        index = 0
-        for (chrom, len_chrom) in self.reference_sequence.get_chr_lens():
-            if self._skip(chrom):
-                continue
-            if chrom in self.validation_holdout:
-                by_mode["validate"].append(index)
-            elif self.test_holdout and chrom in self.test_holdout:
-                by_mode["test"].append(index)
-            else:
-                by_mode["train"].append(index)
-            self.sample_from_intervals.append((chrom, self.sequence_length, len_chrom - self.sequence_length))
-            self.interval_lengths.append(len_chrom - 2 * self.sequence_length)
-            index += 1
+            order = list(range(len(kept)))
+            np.random.shuffle(order)
+            n_val = int(len(kept) * self.validation_holdout)
+            n_test = int(len(kept) * self.test_holdout) if self.test_holdout else 0
+            members["validate"] = order[:n_val]
+            if self.test_holdout:
+                members["test"] = order[n_val:n_val + n_test]
+            members["train"] = order[n_val + n_test:]
+        # upstream builds validate, then test, then train for proportional holdouts and iterates ``modes`` otherwise;
+        # no RNG is involved, so the order is immaterial
         for m in self.modes:
-            indices, weights = get_indices_and_probabilities(self.interval_lengths, by_mode[m])
-            self._sample_from_mode[m] = SampleIndices(indices, weights)
+            self._sample_from_mode[m] = SampleIndices(*get_indices_and_probabilities(self.interval_lengths, members[m]))
 
     def _update_randcache(self, mode=None):
         if not mode:

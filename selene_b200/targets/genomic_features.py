@@ -29,28 +29,19 @@ def _is_positive_row(start, end, feature_start, feature_end, threshold):
 
 
 def _define_feature_thresholds(feature_thresholds, features):
-    """genomic_features.py:144-193."""
-    feature_thresholds_dict = {}
-    feature_thresholds_vec = np.zeros(len(features))
-    if (isinstance(feature_thresholds, float) or
-            isinstance(feature_thresholds, int)) and feature_thresholds <= 1 \
-            and feature_thresholds > 0:
-        feature_thresholds_dict = dict.fromkeys(features, feature_thresholds)
-        feature_thresholds_vec += feature_thresholds
+    """(dict feature -> threshold, float32 vector in feature order) from the four accepted forms of
+    ``feature_thresholds`` (genomic_features.py:144-193): a number in (0, 1] for every feature; a dict with a
+    ``"default"`` entry and per-feature overrides; a function of the feature name; anything else leaves the
+    thresholds at zero with an empty dict, as upstream."""
+    if isinstance(feature_thresholds, (float, int)) and 0 < feature_thresholds <= 1:
+        per_feature = [feature_thresholds] * len(features)
     elif isinstance(feature_thresholds, dict):
-        feature_thresholds_dict = dict.fromkeys(features, feature_thresholds["default"])
-        feature_thresholds_vec += feature_thresholds["default"]
-        for i, f in enumerate(features):
-            if f in feature_thresholds:
-                feature_thresholds_dict[f] = feature_thresholds[f]
-                feature_thresholds_vec[i] = feature_thresholds[f]
+        per_feature = [feature_thresholds.get(f, feature_thresholds["default"]) for f in features]
     elif isinstance(feature_thresholds, types.FunctionType):
-        for i, f in enumerate(features):
-            threshold = feature_thresholds(f)
-            feature_thresholds_dict[f] = threshold
-            feature_thresholds_vec[i] = threshold
-    feature_thresholds_vec = feature_thresholds_vec.astype(np.float32)
-    return feature_thresholds_dict, feature_thresholds_vec
+        per_feature = [feature_thresholds(f) for f in features]
+    else:
+        return {}, np.zeros(len(features), dtype=np.float32)
+    return dict(zip(features, per_feature)), np.array(per_feature, dtype=np.float64).astype(np.float32)
 
 
 def integer_thresholds(thresholds_vec, query_length):
@@ -124,8 +115,9 @@ class GenomicFeatures(object):
             for ci in np.unique(cidx[~good]):
                 sel = (~good) & (cidx == ci)
                 order = np.argsort(starts[sel], kind="stable")
-                self._bad[int(ci)] = (starts[sel][order], np.maximum.accumulate(ends[sel][order]),
-                                      [r[col] for r, s in zip(rest, sel) if s])
+                bad_names = [r[col] if r else None for r, s in zip(rest, sel) if s]
+                self._bad[int(ci)] = (starts[sel][order], ends[sel][order], np.maximum.accumulate(ends[sel][order]),
+                                      [bad_names[k] for k in order])
         if self.device is None:
             self.device = torch.cuda.current_device()
         lib = _lib.load()
@@ -158,13 +150,15 @@ class GenomicFeatures(object):
             self._handle = None
 
     def _check_bad(self, ci, start, end):
+        """Raises ``KeyError(feature)`` for the first row (in start order, as tabix returns them) that overlaps the
+        query and names a feature outside ``feature_index_dict`` — what ``feature_index_dict[row[3]]`` does upstream
+        (_genomic_features.pyx:34)."""
         if ci in self._bad:
-            s, cmax, names = self._bad[ci]
-            hi = int(np.searchsorted(s, end, side="left"))
+            s, e, cmax, names = self._bad[ci]
+            hi = int(np.searchsorted(s, end, side="left"))         # rows with start < end of the query
             if hi > 0 and cmax[hi - 1] > start:
-                for i in range(hi):
-                    # first offending row in file order of start
-                    raise KeyError(names[i])
+                first = int(np.argmax(e[:hi] > start))             # first of them that ends after the query start
+                raise KeyError(names[first])
 
     def _thr_tensor(self, query_length):
         import torch

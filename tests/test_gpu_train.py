@@ -180,3 +180,90 @@ def test_fused_sgd_repack_equals_separate_passes(monkeypatch):
     assert np.allclose(runs[0][0], runs[1][0], rtol=0, atol=2e-6), (runs[0][0], runs[1][0])
     assert np.abs(runs[0][1] - runs[1][1]).max() <= 2e-6 and np.abs(runs[0][2] - runs[1][2]).max() <= 2e-6
     assert runs[0][0][-1] < runs[0][0][0]
+
+
+class _FixedSampler(object):
+    """A sampler with the reference's interface that cycles through fixed batches (so two runs see the same data)."""
+    modes = ["train", "validate"]
+
+    def __init__(self, n_batches=6, batch=4, seed=0):
+        rng = np.random.default_rng(seed)
+        self.batches = []
+        for _ in range(n_batches):
+            codes = rng.integers(0, 4, (batch, 1000))
+            x = np.eye(4, dtype=np.float32)[codes]
+            y = (rng.random((batch, 919)) < 0.3).astype(np.float32)
+            self.batches.append((x, y))
+        self.i = 0
+
+    def sample_device(self, batch_size, seq_dtype="float32", label_dtype="float32"):
+        import torch
+        x, y = self.batches[self.i % len(self.batches)]
+        self.i += 1
+        return torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+
+    def get_validation_set(self, batch_size, n_samples=None):
+        return self.batches[:2], np.vstack([b[1] for b in self.batches[:2]])
+
+
+def test_trainmodel_checkpoints_resume_and_rejects_unsupported(tmp_path):
+    """train_and_validate must leave checkpoint.pth.tar / best_model.pth.tar in the reference's layout
+    (train_model.py:430-448,638-686), copy the trained weights back into the module, resume from a checkpoint
+    (:296-326: weights, step, min_loss, SGD momentum) and refuse what the kernels do not implement."""
+    import torch
+    import sb_models as M
+    from selene_b200.train_model import TrainModel
+
+    def fresh():
+        torch.manual_seed(11)
+        m = M.DeepSEA(1000, 919)
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0                       # deterministic runs
+        return m
+    kw = dict(loss_criterion=torch.nn.BCELoss(), optimizer_class=torch.optim.SGD,
+              optimizer_kwargs=dict(lr=0.05, momentum=0.9, weight_decay=1e-6), batch_size=4,
+              report_stats_every_n_steps=2, save_checkpoint_every_n_steps=1, use_scheduler=True)
+    # ---- one uninterrupted run of 6 steps
+    m_full = fresh()
+    t_full = TrainModel(m_full, _FixedSampler(), max_steps=6, output_dir=str(tmp_path / "full"), **kw)
+    before = m_full.classifier[2].weight.detach().clone()
+    t_full.train_and_validate()
+    assert not torch.equal(before, m_full.classifier[2].weight)          # the module received the trained weights
+    ck = torch.load(str(tmp_path / "full" / "checkpoint.pth.tar"), weights_only=False)
+    assert sorted(ck.keys()) == ["arch", "min_loss", "optimizer", "state_dict", "step"]
+    assert ck["arch"] == "DeepSEA" and ck["step"] == 5 and np.isfinite(ck["min_loss"])
+    assert list(ck["state_dict"].keys()) == list(m_full.state_dict().keys())
+    assert os.path.exists(str(tmp_path / "full" / "best_model.pth.tar"))
+    # the optimizer entry loads into a real torch SGD over the same module
+    opt = torch.optim.SGD(fresh().parameters(), lr=0.1, momentum=0.9)
+    opt.load_state_dict(ck["optimizer"])
+    assert len(opt.state_dict()["state"]) == 10 and opt.param_groups[0]["lr"] == 0.05
+    # ---- the same 6 steps as 3 + resume + 3
+    m_a = fresh()
+    s = _FixedSampler()
+    t_a = TrainModel(m_a, s, max_steps=3, output_dir=str(tmp_path / "a"), **kw)
+    t_a.train_and_validate()
+    ck_a = torch.load(str(tmp_path / "a" / "checkpoint.pth.tar"), weights_only=False)
+    assert ck_a["step"] == 2
+    # the reference resumes AT the checkpointed step index (it re-runs it); feed the matching batch
+    m_b = fresh()
+    s2 = _FixedSampler()
+    s2.i = 2
+    t_b = TrainModel(m_b, s2, max_steps=6, output_dir=str(tmp_path / "b"),
+                     checkpoint_resume=str(tmp_path / "a" / "checkpoint.pth.tar"), **kw)
+    assert t_b.step == 2 and t_b._min_loss == ck_a["min_loss"]
+    # momentum buffers came back: identical to the checkpoint
+    mw, _mb = t_b.trainer.layer_momentum(4)
+    assert np.array_equal(mw, ck_a["optimizer"]["state"][8]["momentum_buffer"].numpy())
+    w_resumed, _ = t_b.trainer.layer_params(4)
+    assert np.array_equal(w_resumed, ck_a["state_dict"]["classifier.2.weight"].numpy())
+    # ---- unsupported configurations raise instead of silently training something else
+    with pytest.raises(ValueError):
+        TrainModel(fresh(), _FixedSampler(), optimizer_class=torch.optim.Adam, optimizer_kwargs=dict(lr=1e-3), batch_size=4)
+    with pytest.raises(ValueError):
+        TrainModel(fresh(), _FixedSampler(), loss_criterion=torch.nn.MSELoss(), batch_size=4)
+    with pytest.raises(ValueError):
+        TrainModel(fresh(), _FixedSampler(), optimizer_kwargs=dict(lr=0.1, nesterov=True, momentum=0.9), batch_size=4)
+    with pytest.raises(ValueError):
+        TrainModel(M.DeeperDeepSEA(1000, 919), _FixedSampler(), batch_size=4)      # BatchNorm
