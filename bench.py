@@ -17,6 +17,7 @@ is printed by rank 0.  Legs of our arm:
   strong     configs[1] as BASELINE.json states it: a FIXED list of --strong-variants SNVs (default 2^20) split
              into contiguous shards over the ranks, timed (a) with per-rank device->host shard read-back and
              (b) with one NCCL gather of the score tiles to rank 0 + rank 0's device->host read
+  train      configs[2]: the DeepSEA training step, batch 64 per GPU, gradients all-reduced over NCCL (weak scaling)
   cpu_baseline  (N=1) the unmodified reference (baseline/_ref) on a bounded prefix of the first timed block,
              on all host threads; the oracle port's rate on the same prefix is reported beside it
 
@@ -414,6 +415,54 @@ def strong_leg(az, names, seqs, args, rank, world):
                     "device->host read of the whole (variants, 919) x 2 matrix over its one PCIe link"}
 
 
+# --------------------------------------------------------------------------------------------------
+# configs[2]: DeepSEA training step, data parallel (secondary record; weak scaling, batch 64 per GPU)
+# --------------------------------------------------------------------------------------------------
+def train_leg(model_cls, rank, world, batch=64, steps=20, warmup=5):
+    """forward (train mode, dropout) -> BCELoss -> backward on tcgen05 (bf16 operands, fp32 master weights) -> one NCCL
+    all-reduce of the flat fp32 gradient vector (classifier tail overlapped with the conv backward) -> SGD, on a fixed
+    synthetic batch per rank (selene_sdk/train_model.py:483-496, models/deepsea.py:60-74)."""
+    import torch
+    import torch.distributed as dist
+    from selene_b200.train_model import B200Trainer
+    torch.manual_seed(0)
+    model = model_cls()
+    tr = B200Trainer(model, SEQ_LEN, lr=0.01, momentum=0.9, weight_decay=1e-6,
+                     dropout=B200Trainer.dropout_of_module(model), precision="bf16")
+    rng = np.random.default_rng(1 + rank)
+    x = np.eye(4, dtype=np.float32)[rng.integers(0, 4, (batch, SEQ_LEN))]
+    y = (rng.random((batch, N_FEATURES)) < 0.1).astype(np.float32)
+    xs, ys = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    for _ in range(warmup):
+        tr.step(xs, ys)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        tr._enable_overlap()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        tr.forward_backward(xs, ys)
+        tr.allreduce_grads(overlap=True)
+        tr.sgd_step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    out = {"workload": "configs[2]: DeepSEA training step (dropout, BCELoss, SGD momentum 0.9), batch %d per GPU, "
+                       "synthetic fixed batch (no sampler)" % batch,
+           "n_gpus": world, "scaling": "weak", "precision": "bf16 operands / fp32 master weights",
+           "ms_per_step": ms, "samples_per_s": world * batch / ms * 1e3,
+           "allreduce_bytes_per_step": int(tr.grads.numel()) * 4 if world > 1 else 0,
+           "flops_per_sample": 3.0 * 1.0986e9, "loss": float(tr.loss.item())}
+    out["tflops"] = out["samples_per_s"] * out["flops_per_sample"] / 1e12
+    del tr
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -427,6 +476,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample", type=int, default=1024, help="variants timed on the CPU baseline leg")
     ap.add_argument("--strong-variants", type=int, default=1 << 20, help="0 skips the strong-scaling leg")
+    ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-hbm", action="store_true")
     args = ap.parse_args()
@@ -590,6 +640,11 @@ def main():
     if args.strong_variants > 0:
         strong = strong_leg(az, names, seqs, args, rank, world)
 
+    # ---- configs[2]: the training step, data parallel
+    train = None
+    if not args.no_train and args.precision == "bf16":
+        train = train_leg(DeepSEA, rank, world)
+
     # ---- HBM-bound kernels alone (N=1)
     hbm = None
     if rank == 0 and world == 1 and not args.no_hbm:
@@ -625,7 +680,7 @@ def main():
                 "config": config, "clocks": clk, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes},
-                "roofline": roofline, "roofline_hbm": hbm, "strong": strong, "cpu_baseline": cpu,
+                "roofline": roofline, "roofline_hbm": hbm, "strong": strong, "train": train, "cpu_baseline": cpu,
                 "variants_per_sec": value / 2.0}
         print(json.dumps(line))
     if world > 1:

@@ -296,6 +296,22 @@ int sb_net_forward_backward_tc(sb_net* net, const float* x, const float* targets
                                void* workspace, size_t workspace_bytes, float* grads, float* loss, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* packed training samples (samplers/dataloader.py:129-147, scripts/sampler_write_to_h5.py:63-89) */
+/* ------------------------------------------------------------------------------------------ */
+/* sequences: dev uint8 (n, ceil(L_stored/8), 4) = np.packbits(one_hot > 0, axis=1) — bit 7-(p%8) of byte (s, p/8, c);
+ * rows with all four bits set (unknown bases) unpack to 1/4 (unpackbits_sequence).  Writes positions
+ * [seq_start, seq_start + out_len) of every sample as (n, out_len, 4) fp32 / bf16 (the centre crop of
+ * _H5Dataset.__getitem__, dataloader.py:236-246, is seq_start / out_len). */
+int sb_unpack_sequences(const uint8_t* packed, int64_t n, int L_stored, int seq_start, int out_len,
+                        int out_dtype, void* out, void* stream);
+/* targets: dev uint8 (n, ceil(F/8)) = np.packbits(targets > 0, axis=1) -> (n, F) float32 or uint8 (unpackbits_targets) */
+int sb_unpack_targets(const uint8_t* packed, int64_t n, int F, int out_dtype, void* out, void* stream);
+/* the inverse (what sampler_write_to_h5.py --compress stores): dev fp32 (n, L, 4) and / or (n, F) -> packed bits;
+ * either pair of pointers may be NULL */
+int sb_pack_samples(const float* sequences, const float* targets, int64_t n, int L, int F,
+                    uint8_t* packed_sequences, uint8_t* packed_targets, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* score writers (predict_handlers/handler.py:15-42): "{:.2e}" text of a score matrix           */
 /* ------------------------------------------------------------------------------------------ */
 /* Row r of x (dev, n_rows x F float32) as text: "{:.2e}".format(value) per value (correctly rounded, ties to

@@ -474,3 +474,27 @@ class RandomPositionsSamplerOracle(object):
             sequences[n], targets[n] = out
             n += 1
         return sequences, targets
+
+
+# ------------------------------------------------------------------------------------------------
+# packed training samples
+# ------------------------------------------------------------------------------------------------
+def pack_samples(sequences, targets):
+    """scripts/sampler_write_to_h5.py:63-65 (--compress): bits along the position / target axis, MSB first."""
+    return np.packbits(np.asarray(sequences) > 0, axis=1), np.packbits(np.asarray(targets) > 0, axis=1)
+
+
+def unpackbits_sequence(sequence, s_len):
+    """selene_sdk/samplers/dataloader.py:129-138."""
+    sequence = np.unpackbits(sequence.astype(np.uint8), axis=-2)
+    nulls = np.sum(sequence, axis=-1) == sequence.shape[-1]
+    sequence = sequence.astype(float)
+    sequence[nulls, :] = 1.0 / sequence.shape[-1]
+    return sequence[:, :s_len, :] if sequence.ndim == 3 else sequence[:s_len, :]
+
+
+def unpackbits_targets(targets, t_len):
+    """selene_sdk/samplers/dataloader.py:140-146 (its 1-D branch refers to an undefined ``self``; only the 2-D form is
+    reachable from the DataLoader path and the 1-D case is the obvious slice)."""
+    targets = np.unpackbits(targets, axis=-1).astype(float)
+    return targets[:, :t_len] if targets.ndim == 2 else targets[:t_len]

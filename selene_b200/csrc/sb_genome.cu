@@ -96,17 +96,17 @@ __device__ __forceinline__ uint32_t spread_bits4(uint32_t bits4) {    // 4 bits 
     return (m | (m << 7)) & 0x01010101u;
 }
 
-struct WinMeta {          // what is read per window from the caller's arrays (prefetched one window ahead)
+struct WinMeta {          // what is read per window from the caller's arrays
     int c;
     int64_t st;
     int rc, sub_ref, sub_alt;
 };
-struct WinRaw {           // the image words of one lane's 16 positions (prefetched one chunk ahead)
+struct WinRaw {           // the image words of one lane's 16 positions
     uint32_t pw, uw, nw, vm;
 };
 
 template <int MODE, bool SNV>
-__global__ void __launch_bounds__(kWinWarps * 32, 5) window_kernel(
+__global__ void __launch_bounds__(kWinWarps * 32, 6) window_kernel(
     GenomeView g, int64_t n_image, int n_chrom, const int32_t* __restrict__ chrom, const int64_t* __restrict__ start,
     const uint8_t* __restrict__ strand_rc, int n, int L, Perm perm, void* __restrict__ out,
     uint8_t* __restrict__ flags_out,
@@ -173,15 +173,13 @@ __global__ void __launch_bounds__(kWinWarps * 32, 5) window_kernel(
         return r;
     };
 
-    int w = blockIdx.x * kWinWarps + (threadIdx.x >> 5);
-    if (w >= n) return;
-    WinMeta m = load_meta(w);
-    WinMeta m_next = m;
-    if (w + warps_total < n) m_next = load_meta(w + warps_total);
-    int64_t coff, s0, e0, base;
-    geometry(m, coff, s0, e0, base);
-    WinRaw raw = load_raw(coff, s0, e0, base, m.rc, 0);
-    for (; w < n; w += warps_total) {
+    // No software prefetch across windows or chunks: an earlier version that loaded the next chunk's words and the next
+    // window's coordinates ahead needed 48+ registers, and the lost occupancy cost the (store-bound) fp32 path more
+    // than the hidden load latency gained (r02: 0.81 -> 0.75 of the measured copy bandwidth).
+    for (int w = blockIdx.x * kWinWarps + (threadIdx.x >> 5); w < n; w += warps_total) {
+        const WinMeta m = load_meta(w);
+        int64_t coff, s0, e0, base;
+        geometry(m, coff, s0, e0, base);
         const int rc = m.rc;
         int sub_at = -1, sub_ref = m.sub_ref, sub_alt = m.sub_alt;
         if (SNV) {
@@ -193,16 +191,7 @@ __global__ void __launch_bounds__(kWinWarps * 32, 5) window_kernel(
         }
         int flags = 0;
         for (int c0 = 0; c0 < L; c0 += kWinChunk) {
-            // ---------------------------------------------- loads of the NEXT chunk (this window's or the next one's)
-            WinRaw raw_next = raw;
-            int64_t coff_n = coff, s0_n = s0, e0_n = e0, base_n = base;
-            const bool last_chunk = c0 + kWinChunk >= L;
-            if (!last_chunk) {
-                raw_next = load_raw(coff, s0, e0, base, rc, c0 + kWinChunk);
-            } else if (w + warps_total < n) {
-                geometry(m_next, coff_n, s0_n, e0_n, base_n);
-                raw_next = load_raw(coff_n, s0_n, e0_n, base_n, m_next.rc, 0);
-            }
+            const WinRaw raw = load_raw(coff, s0, e0, base, rc, c0);
             // ---------------------------------------------- decode this lane's 16 positions
             const int p0 = c0 + 16 * lane;
             uint4 v;
@@ -301,15 +290,11 @@ __global__ void __launch_bounds__(kWinWarps * 32, 5) window_kernel(
                 }
                 __syncwarp();
             }
-            raw = raw_next;
-            if (last_chunk) { coff = coff_n; s0 = s0_n; e0 = e0_n; base = base_n; }
         }
         if (flags_out != nullptr) {
             flags = __reduce_or_sync(0xffffffffu, flags);
             if (lane == 0) flags_out[w] = (uint8_t)flags;
         }
-        m = m_next;
-        if (w + 2 * warps_total < n) m_next = load_meta(w + 2 * warps_total);
     }
 }
 
@@ -422,7 +407,7 @@ static bool perm_ok(const uint8_t perm[4]) {
 }
 static int window_grid(int n, int device) {
     const long long blocks = ((long long)n + kWinWarps - 1) / kWinWarps;   // one warp per window
-    const long long cap = (long long)sb_sm_count(device) * 5;              // persistent: 5 CTAs of 8 warps per SM
+    const long long cap = (long long)sb_sm_count(device) * 6;              // persistent: 6 CTAs of 8 warps per SM
     return (int)(blocks < cap ? blocks : cap);
 }
 

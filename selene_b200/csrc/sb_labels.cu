@@ -62,20 +62,19 @@ constexpr int kBlocksPerSm = 6;
 constexpr int kPackedMaxLen = 32767;
 constexpr int32_t kAnyRow = 0x40000000;
 
-// zero `n` consecutive output elements with the whole CTA: 16-byte streaming stores over the aligned body (a CTA
-// pass covers 4 KB contiguous), element stores for the ragged ends
+// zero one output row with 16-byte stores (rows are only sizeof(OutT)-aligned: element stores for the ragged ends)
 template <typename OutT>
-__device__ __forceinline__ void zero_flat(OutT* __restrict__ o, long long n, int tid, int nthreads) {
+__device__ __forceinline__ void zero_row(OutT* __restrict__ o, int n, int lane) {
     constexpr int kPer = 16 / (int)sizeof(OutT);
     const int mis = (int)((reinterpret_cast<uintptr_t>(o) & 15) / sizeof(OutT));
-    long long head = mis ? kPer - mis : 0;
+    int head = mis ? kPer - mis : 0;
     if (head > n) head = n;
-    if (tid < head) o[tid] = (OutT)0;
-    const long long body = (n - head) / kPer;
+    if (lane < head) o[lane] = (OutT)0;
+    const int body = (n - head) / kPer;
     uint4* o4 = reinterpret_cast<uint4*>(o + head);
-    for (long long i = tid; i < body; i += nthreads) __stcs(o4 + i, make_uint4(0, 0, 0, 0));   // written once, never re-read here
-    const long long done = head + body * kPer;
-    if (tid < n - done) o[done + tid] = (OutT)0;
+    for (int i = lane; i < body; i += 32) __stcs(o4 + i, make_uint4(0, 0, 0, 0));   // streaming: written once, never re-read here
+    const int done = head + body * kPer;
+    if (lane < n - done) o[done + lane] = (OutT)0;
 }
 
 struct LabelArgs {
@@ -146,40 +145,29 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, kBlocksPerSm) label_bins_
         toff = meta + a.n_chrom + 1;
         __syncthreads();
     }
-    // A CTA iteration owns kWarpsPerBlock CONSECUTIVE queries, one per warp: their rows are one contiguous region that
-    // the CTA zero-fills together (no per-row alignment work), then every warp labels its own query.
-    const int n_batches = (int)(((long long)n_queries + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    const int q_stride = gridDim.x * kWarpsPerBlock;     // the grid is at most SMs x kBlocksPerSm CTAs: no overflow
+    const int warps_total = gridDim.x * kWarpsPerBlock;
     int q = blockIdx.x * kWarpsPerBlock + warp;
-    int c_n = -1, qs_n = 0, qe_n = 0;
+    int c_n = 0, qs_n = 0, qe_n = 0;
     if (q < n_queries) { c_n = q_chrom[q]; qs_n = q_start[q]; qe_n = q_end[q]; }
-    for (int batch = blockIdx.x; batch < n_batches; batch += gridDim.x, q += q_stride) {
+    for (; q < n_queries; q += warps_total) {
         const int c = c_n, qs = qs_n, qe = qe_n;
-        const int q_next = q + q_stride < 0 ? n_queries : q + q_stride;
-        c_n = -1;
-        if (q_next < n_queries) {   // next query's coordinates: off the dependent chain
-            c_n = q_chrom[q_next]; qs_n = q_start[q_next]; qe_n = q_end[q_next];
+        if (q + warps_total < n_queries) {   // next query's coordinates: off the dependent chain
+            c_n = q_chrom[q + warps_total]; qs_n = q_start[q + warps_total]; qe_n = q_end[q + warps_total];
         }
         const int qlen = qe - qs;
-        // the table entry is requested before the fill so that its latency hides behind the stores
-        long long lo = -1, hi0 = 0;
-        if (q < n_queries && c >= 0 && c < a.n_chrom && qlen > 0) {
-            const long long lo0 = coff[c];
-            hi0 = coff[c + 1];
+        OutT* o = out + (long long)q * n_features;
+        zero_row(o, n_features, lane);
+        __syncwarp();   // orders the zero fill before the label stores of other lanes
+        if (!(c >= 0 && c < a.n_chrom && qlen > 0)) continue;
+        const long long lo0 = coff[c], hi0 = coff[c + 1];
+        long long lo;
+        {
             const long long t0 = toff[c];
             const long long nb = toff[c + 1] - t0;
             const long long b = qs < 0 ? 0 : (long long)(qs >> a.tab_shift);
-            if (b < nb - 1)                              // else: past the last interval end of the chromosome
-                lo = qs < 0 ? lo0 : lo0 + __ldg(a.tab + t0 + b);
+            if (b >= nb - 1) continue;                   // past the last interval end of the chromosome: no overlap
+            lo = qs < 0 ? lo0 : lo0 + __ldg(a.tab + t0 + b);
         }
-        {
-            const int q0 = batch * kWarpsPerBlock;
-            const int rows = n_queries - q0 < kWarpsPerBlock ? n_queries - q0 : kWarpsPerBlock;
-            zero_flat(out + (long long)q0 * n_features, (long long)rows * n_features, (int)threadIdx.x, kWarpsPerBlock * 32);
-        }
-        __syncthreads();            // orders the zero fill before the label stores of any thread of the CTA
-        if (lo < 0) continue;
-        OutT* o = out + (long long)q * n_features;
         const bool packed = qlen <= kPackedMaxLen;
         // ---- the 32 candidates from the table position
         int fs = 0x7fffffff, fe = 0, ff = 0;

@@ -21,7 +21,7 @@ from .. import _lib
 
 _CHUNK_BYTES = 32 << 20
 _POOL = None
-_POOL_SIZE = max(2, min(8, int(os.environ.get("SB_WRITER_THREADS", "0")) or (os.cpu_count() or 4) // 2))
+_POOL_SIZE = int(os.environ.get("SB_WRITER_THREADS", "0")) or max(2, min(12, (os.cpu_count() or 4) - 2))
 _TLS = threading.local()
 
 
@@ -157,6 +157,63 @@ def submit_tsv(path, columns_for_ids, features, data, prefix, prefix_off, dist_g
             raise err
         return path
     return finish
+
+
+class TsvFile(object):
+    """A TSV output that is appended to BLOCK BY BLOCK while later blocks are still being scored (single process):
+    ``append`` sizes the block's rows on the device, places it after the text written so far and hands its chunks to the
+    writer pool; ``finish`` waits for them.  The result is byte-identical to one ``submit_tsv`` over all rows."""
+
+    def __init__(self, path, columns_for_ids, features):
+        self.path = path
+        header = "{0}\n".format("\t".join(list(columns_for_ids) + list(features))).encode()
+        self._fd = os.open(path, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o644)
+        os.pwrite(self._fd, header, 0)
+        self._pos = len(header)
+        self._futures = []
+
+    def append(self, data, prefix, prefix_off):
+        import torch
+        lib = _lib.load()
+        t = data.to(dtype=torch.float32).contiguous()
+        n, F = int(t.shape[0]), int(t.shape[1])
+        if n == 0:
+            return
+        dev = t.device
+        prefix_off = np.ascontiguousarray(prefix_off, dtype=np.int64)
+        pre_dev = torch.from_numpy(np.array(prefix, dtype=np.uint8)).to(dev) if len(prefix) else \
+            torch.zeros(1, dtype=torch.uint8, device=dev)
+        pre_off_dev = torch.from_numpy(prefix_off).to(dev)
+        sizes = torch.empty(n, dtype=torch.int64, device=dev)
+        _lib.check(lib.sb_format_e2_row_bytes(_lib.ptr(t), n, F, _lib.ptr(sizes), _lib.stream_ptr()), "sb_format_e2_row_bytes")
+        sizes += pre_off_dev[1:] - pre_off_dev[:-1]
+        row_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(sizes, 0, out=row_off[1:])
+        ready = torch.cuda.Event()
+        ready.record()
+        off_host = row_off.cpu().numpy()                       # waits for this block's scores only
+        pool = writer_pool()
+        r0 = 0
+        while r0 < n:
+            r1 = int(np.searchsorted(off_host, off_host[r0] + _CHUNK_BYTES, side="right")) - 1
+            r1 = min(n, max(r1, r0 + 1))
+            nbytes = int(off_host[r1] - off_host[r0])
+            self._futures.append(pool.submit(_chunk_job, self._fd, self._pos + int(off_host[r0]), t, r0, r1, row_off,
+                                             int(off_host[r0]), nbytes, pre_dev, pre_off_dev, ready))
+            r0 = r1
+        self._pos += int(off_host[-1])
+
+    def finish(self):
+        err = None
+        for f in self._futures:
+            try:
+                f.result()
+            except Exception as e:
+                err = err or e
+        os.close(self._fd)
+        if err is not None:
+            raise err
+        return self.path
 
 
 def write_tsv(path, columns_for_ids, features, ids, data, prefix=None, prefix_off=None):

@@ -203,6 +203,7 @@ class AnalyzeSequences(object):
             Genome.update_bases_order(['A', 'C', 'G', 'T'])     # :182-183
         self._write_mem_limit = write_mem_limit
         self.multi_gpu_output = "shards"     # or "gather": see variant_effect_prediction
+        self.vep_block_variants = 32768      # single-process VEP: variants scored per block while the previous is written
         # the weights are re-normalised for models that do it on every forward (heartenn.py:73-78)
         from ..nets import unwrap_non_strand_specific
         inner = unwrap_non_strand_specific(model)[0]
@@ -660,48 +661,106 @@ class AnalyzeSequences(object):
         if "predictions" in want:
             names += ["ref_predictions", "alt_predictions"]
         dev = torch.device("cuda", int(self.net.device))
-        arrays = {k: torch.zeros((n, F), dtype=torch.float32, device=dev) for k in names}   # scores stay in HBM
-        match = np.ones(n, dtype=bool)
-        unk = np.zeros(n, dtype=bool)
-        snv = local.is_snv.copy()
-        if recurrent and not snv.all():
-            snv[:] = False
-        idx = np.flatnonzero(snv)
-        if len(idx):
-            G._unpicklable_init()
-            to_genome = np.array([G._chrom_index[c] for c in local.chrom_names], dtype=np.int32)
-            r = self.score_snvs(to_genome[local.chrom_id[idx]], local.pos[idx], local.ref_code[idx], local.alt_code[idx],
-                                strands=local.minus[idx], save_data=want, to_host=False)
-            if len(idx) == n:
-                for k in names:
-                    arrays[k] = r[k]
-            else:
-                didx = torch.from_numpy(idx).to(dev)
+        out_dir, prefix = os.path.split(output_path_prefix)
+
+        def output_files():
+            """(score name, path without extension) in the reference's handler order."""
+            files = []
+            for s in want:
+                if s == "predictions":
+                    # write_ref_alt_handler.py:83-108: <prefix>.ref_predictions.* and <prefix>.alt_predictions.*
+                    for tag in ("ref", "alt"):
+                        p = os.path.join(out_dir, "{0}.{1}".format(prefix, tag) if prefix else tag)
+                        files.append((tag + "_predictions", _scores_filepath(p, "predictions")[2], p))
+                else:
+                    files.append((s, _scores_filepath(output_path_prefix, s)[2], None))
+            return files
+
+        def enqueue(tbl):
+            """Enqueues the scoring of ``tbl`` on the current stream.  Returns (dict of CUDA score arrays, resolve) where
+            ``resolve()`` brings ref_match / contains_unk to the host (the only point that waits for the block)."""
+            m = len(tbl)
+            arrays = {k: torch.zeros((m, F), dtype=torch.float32, device=dev) for k in names}   # scores stay in HBM
+            match = np.ones(m, dtype=bool)
+            unk = np.zeros(m, dtype=bool)
+            snv = tbl.is_snv.copy()
+            if recurrent and not snv.all():
+                snv[:] = False
+            idx = np.flatnonzero(snv)
+            r_snv = None
+            if len(idx):
+                G._unpicklable_init()
+                to_genome = np.array([G._chrom_index[c] for c in tbl.chrom_names], dtype=np.int32)
+                r_snv = self.score_snvs(to_genome[tbl.chrom_id[idx]], tbl.pos[idx], tbl.ref_code[idx], tbl.alt_code[idx],
+                                        strands=tbl.minus[idx], save_data=want, to_host=False)
+                if len(idx) == m:
+                    for k in names:
+                        arrays[k] = r_snv[k]
+                else:
+                    didx = torch.from_numpy(idx).to(dev)
+                    for k in names:
+                        arrays[k][didx] = r_snv[k]
+            other = np.flatnonzero(~snv)
+            if len(other):
+                refs, alts = [], []
+                for i in other:
+                    rs, als, mt, u = build_ref_alt_strings(tbl.variant(i), G, self.sequence_length,
+                                                           self._start_radius, self._end_radius)
+                    refs.append(codes_of_string(rs)); alts.append(codes_of_string(als))
+                    match[i], unk[i] = mt, u
+                r = self.score_code_pairs(np.stack(refs), np.stack(alts), save_data=want, to_host=False)
+                didx = torch.from_numpy(other).to(dev)
                 for k in names:
                     arrays[k][didx] = r[k]
-            match[idx], unk[idx] = r["ref_match"].cpu().numpy(), r["contains_unk"].cpu().numpy()
-        idx = np.flatnonzero(~snv)
-        if len(idx):
-            refs, alts = [], []
-            for i in idx:
-                rs, als, m, u = build_ref_alt_strings(local.variant(i), G, self.sequence_length,
-                                                      self._start_radius, self._end_radius)
-                refs.append(codes_of_string(rs)); alts.append(codes_of_string(als))
-                match[i], unk[i] = m, u
-            r = self.score_code_pairs(np.stack(refs), np.stack(alts), save_data=want, to_host=False)
-            didx = torch.from_numpy(idx).to(dev)
-            for k in names:
-                arrays[k][didx] = r[k]
+
+            def resolve():
+                if r_snv is not None:
+                    match[idx], unk[idx] = r_snv["ref_match"].cpu().numpy(), r_snv["contains_unk"].cpu().numpy()
+                return match, unk
+            return arrays, resolve
+
+        def warn(tbl, match, unk):
+            for i in np.flatnonzero(unk):
+                warnings.warn("For variant ({0}, {1}, {2}, {3}, {4}, {5}), reference sequence contains "
+                              "unknown base(s)--will be marked `True` in the `contains_unk` column of the "
+                              ".tsv or the row_labels .txt file.".format(*tbl.variant(i)))
+            for i in np.flatnonzero(~match):
+                warnings.warn("For variant ({0}, {1}, {2}, {3}, {4}, {5}), reference does not match the "
+                              "reference genome. Predictions/scores associated with this variant--where we "
+                              "use '{3}' in the input sequence--will be marked `False` in the `ref_match` "
+                              "column of the .tsv or the row_labels .txt file".format(*tbl.variant(i)))
+
+        if world == 1 and output_format == "tsv":
+            # ---- single process: blocks of variants are scored while the previous block's rows are formatted, read
+            # back and written (the files grow block by block; byte-identical to writing everything at the end)
+            from ._writers import TsvFile
+            files = [(name, TsvFile(path + ".tsv", VARIANTEFFECT_COLS, self.features)) for name, path, _p in output_files()]
+            block = max(self.batch_size, (self.vep_block_variants // self.batch_size) * self.batch_size)
+
+            def finalize(tbl, arrays, resolve):
+                match, unk = resolve()
+                warn(tbl, match, unk)
+                pre = tbl.id_prefix(match, unk)
+                for name, fh in files:
+                    fh.append(arrays[name], pre[0], pre[1])
+            pending = None
+            for b0 in range(0, n, block):
+                tbl = local.rows(b0, min(n, b0 + block))
+                cur = (tbl,) + enqueue(tbl)
+                if pending is not None:
+                    finalize(*pending)
+                pending = cur
+            if pending is not None:
+                finalize(*pending)
+            for _name, fh in files:
+                fh.finish()
+            lap("score_and_write_s")
+            return None
+
+        arrays, resolve = enqueue(local)
+        match, unk = resolve()
         lap("score_s")
-        for i in np.flatnonzero(unk):
-            warnings.warn("For variant ({0}, {1}, {2}, {3}, {4}, {5}), reference sequence contains "
-                          "unknown base(s)--will be marked `True` in the `contains_unk` column of the "
-                          ".tsv or the row_labels .txt file.".format(*local.variant(i)))
-        for i in np.flatnonzero(~match):
-            warnings.warn("For variant ({0}, {1}, {2}, {3}, {4}, {5}), reference does not match the "
-                          "reference genome. Predictions/scores associated with this variant--where we "
-                          "use '{3}' in the input sequence--will be marked `False` in the `ref_match` "
-                          "column of the .tsv or the row_labels .txt file".format(*local.variant(i)))
+        warn(local, match, unk)
         lap("warnings_s")
         gather = world > 1 and (self.multi_gpu_output == "gather" or output_format != "tsv")
         if gather:
@@ -716,16 +775,7 @@ class AnalyzeSequences(object):
                 return None
             match, unk = g[:, 0].cpu().numpy() > 0.5, g[:, 1].cpu().numpy() > 0.5
             local = table
-        results = []
-        out_dir, prefix = os.path.split(output_path_prefix)
-        for s in want:
-            if s == "predictions":
-                # write_ref_alt_handler.py:83-108: <prefix>.ref_predictions.* and <prefix>.alt_predictions.*
-                for tag in ("ref", "alt"):
-                    p = os.path.join(out_dir, "{0}.{1}".format(prefix, tag) if prefix else tag)
-                    results.append(("predictions", p, arrays[tag + "_predictions"]))
-            else:
-                results.append((s, None, arrays[s]))
+        results = [("predictions" if p is not None else name, p, arrays[name]) for name, _path, p in output_files()]
         lap("gather_s")
         if output_format == "tsv":
             pre = local.id_prefix(match, unk)
