@@ -136,6 +136,19 @@ __device__ __forceinline__ void sb_tma_load_2d(void* smem_dst, const void* tmap,
         : "memory");
 }
 
+// 3-D im2col TMA load (channels, position, sequence): `pixelsPerColumn` window starts from (w, n) on, each read at
+// position + w_off; completion signalled on `bar`.
+__device__ __forceinline__ void sb_tma_load_im2col_3d(void* smem_dst, const void* tmap, uint64_t* bar, int32_t c,
+                                                      int32_t w, int32_t n, uint16_t w_off) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2], {%6};"
+        :
+        : "r"(sb_smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(sb_smem_u32(bar)), "r"(c), "r"(w), "r"(n),
+          "h"(w_off)
+        : "memory");
+}
+
 // --- tcgen05 / TMEM -------------------------------------------------------------------------
 __device__ __forceinline__ void sb_tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {  // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(

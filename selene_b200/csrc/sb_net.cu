@@ -41,6 +41,8 @@ struct NetLayer {
     uint16_t* w1_packed;  // dev, tcgen05 core-matrix layout (sb_conv1.cu); null if unsupported
     uint16_t* w1l_packed; // dev, the same for sb_conv1l.cu (many taps, wide pool); null if unsupported
     float* bias1_padded;  // dev, n_pass*64
+    uint32_t* w1m_packed; // dev, mma.sync B fragments (sb_conv1m.cu: pool-4 first conv on register accumulators); null if unsupported
+    float* bias1m;        // dev, groups of 80 channels
     // first layer too long / pooled too wide for sb_conv1.cu (DanQ: 26 taps, pool 13): generic layer kernel
     // on a (n, L, 8) bf16 one-hot (4 zero channels), K index = tap*8 + canonical base
     __nv_bfloat16* w0_b;
@@ -84,6 +86,7 @@ struct sb_net {
     uint8_t perm[4];
     double flops_per_seq;
     bool force_per_tap;
+    bool no_im2col;                  // SB_TC_IM2COL=0, or the driver refused an im2col tensor map
     int rec_group, rec_interleave;   // row grouping of BiLSTM recurrences (sb_net_set_recurrence)
     int strand_mode;                 // 0: plain; 1 / 2: NonStrandSpecific mean / max (sb_net_set_strand_mode)
     bool has_lstm;
@@ -94,6 +97,9 @@ struct sb_net {
     bool timing;
     std::vector<std::vector<cudaEvent_t>> ev;  // per layer: start0, stop0, start1, stop1, ...
     std::vector<size_t> ev_used;
+    // first conv one chunk ahead (forward_impl): side stream + ordering events, created on first use
+    cudaStream_t side;
+    cudaEvent_t ev_fork, ev_c1[2], ev_done[2];
 };
 
 // sb_lstm.cu
@@ -106,6 +112,14 @@ int sb_lstm_perm_row(int n, int H);
 size_t sb_conv1_pack_weights(const float* w, int cout, int taps, const uint8_t perm[4], uint16_t* out,
                              uint16_t (*to_bf16)(float));
 int sb_conv1_tc_supported(int taps, int pool, int cout);
+// sb_conv1m.cu: pool-4 first conv on mma.sync (accumulators in registers)
+int sb_conv1_mma_supported(int taps, int pool, int cout, int out_ld);
+size_t sb_conv1_mma_pack_weights(const float* w, int cout, int taps, const uint8_t perm[4], uint32_t* out,
+                                 uint16_t (*to_bf16)(float));
+int sb_conv1_mma_launch(const uint8_t* codes, const int32_t* src, const int32_t* sub_pos, const uint8_t* sub_code,
+                        long long row0, long long n_rows, int L, int taps, int pool, int t_pool, int out_pitch, int cout,
+                        int out_ld, int relu, const void* bfrag, const float* bias_padded, void* out, int device,
+                        cudaStream_t stream, int ctas_per_sm);
 // sb_conv1l.cu: many taps + wide pool (DanQ)
 int sb_conv1_long_supported(int taps, int pool, int cout);
 size_t sb_conv1_long_pack_weights(const float* w, int cout, int taps, const uint8_t perm[4], uint16_t* out,
@@ -500,6 +514,7 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
     sb_net* net = new sb_net();
     net->train = nullptr;
     net->capture_stream = nullptr;
+    net->side = nullptr;
     net->train_tc = nullptr;
     net->zero_bias_tc = nullptr;
     net->inference_weights_stale = false;
@@ -508,8 +523,13 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
     net->n_layers = n_layers;
     memcpy(net->perm, perm, 4);
     net->flops_per_seq = 0.0;
+    {
+        const char* e2 = getenv("SB_TC_IM2COL");
+        net->no_im2col = e2 && e2[0] == '0';
+    }
     const char* env = getenv("SB_TC_PER_TAP");
     net->force_per_tap = env && env[0] == '1';
+    if (net->force_per_tap) net->no_im2col = true;
     net->timing = false;
     net->rec_group = 64;
     net->strand_mode = 0;
@@ -623,6 +643,16 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
                 std::vector<float> bp((size_t)n_pass * 64, 0.f);
                 for (int o = 0; o < S.cout; ++o) bp[o] = S.bias[o];
                 rc = upload(&N.bias1_padded, bp); if (rc) return rc;
+                // pool-4 first conv: register-accumulator kernel (SB_CONV1_MMA=0 keeps the tcgen05 one)
+                const char* use_mma = getenv("SB_CONV1_MMA");
+                if (sb_conv1_mma_supported(S.k, N.pool, S.cout, round_up(S.cout, 8)) && !(use_mma && use_mma[0] == '0')) {
+                    std::vector<uint32_t> wm(sb_conv1_mma_pack_weights(S.weight, S.cout, S.k, perm, nullptr, f32_to_bf16_bits), 0);
+                    sb_conv1_mma_pack_weights(S.weight, S.cout, S.k, perm, wm.data(), f32_to_bf16_bits);
+                    rc = upload(&N.w1m_packed, wm); if (rc) return rc;
+                    std::vector<float> bm((size_t)((S.cout + 79) / 80) * 80, 0.f);
+                    for (int o = 0; o < S.cout; ++o) bm[o] = S.bias[o];
+                    rc = upload(&N.bias1m, bm); if (rc) return rc;
+                }
             } else if (sb_conv1_long_supported(S.k, N.pool, S.cout) && !(force_lut && force_lut[0] == '1') &&
                        !(getenv("SB_CONV1_LONG") && getenv("SB_CONV1_LONG")[0] == '0')) {
                 const int n_pass = (S.cout + 63) / 64;
@@ -763,9 +793,14 @@ extern "C" int sb_net_destroy(sb_net* net) {
     for (auto& g : net->lstm_graphs) cudaGraphExecDestroy(g.exec);
     if (net->capture_stream) cudaStreamDestroy(net->capture_stream);
     for (auto& N : net->layers) {
-        cudaFree(N.wf); cudaFree(N.biasf); cudaFree(N.wb); cudaFree(N.wb_tap); cudaFree(N.biasb); cudaFree(N.lut); cudaFree(N.w1_packed); cudaFree(N.w1l_packed); cudaFree(N.bias1_padded); cudaFree(N.w0_b); cudaFree(N.w0_bias);
+        cudaFree(N.wf); cudaFree(N.biasf); cudaFree(N.wb); cudaFree(N.wb_tap); cudaFree(N.biasb); cudaFree(N.lut); cudaFree(N.w1_packed); cudaFree(N.w1l_packed); cudaFree(N.bias1_padded); cudaFree(N.w1m_packed); cudaFree(N.bias1m); cudaFree(N.w0_b); cudaFree(N.w0_bias);
         cudaFree(N.whh_f[0]); cudaFree(N.whh_f[1]); cudaFree(N.whh_b[0]); cudaFree(N.whh_b[1]); cudaFree(N.zero_bias);
         cudaFree(N.wb_perm); cudaFree(N.biasb_perm); cudaFree(N.whh_perm[0]); cudaFree(N.whh_perm[1]);
+    }
+    if (net->side) {
+        cudaStreamDestroy(net->side);
+        cudaEventDestroy(net->ev_fork);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(net->ev_c1[i]); cudaEventDestroy(net->ev_done[i]); }
     }
     delete net;
     return SB_OK;
@@ -825,10 +860,15 @@ extern "C" double sb_net_flops_per_seq(const sb_net* net) { return net ? net->fl
 
 namespace {
 
-int chunk_rows(int precision) { return precision == SB_PREC_BF16 ? 8192 : 256; }
+int chunk_rows(int precision) {
+    if (precision != SB_PREC_BF16) return 256;
+    const char* e = getenv("SB_CHUNK");       // tuning knob: rows per chunk of the bf16 path
+    const int v = e ? atoi(e) : 0;
+    return v >= 256 ? (v & ~1) : 8192;
+}
 
 // bytes of the two ping-pong activation buffers, the fp32 "full" buffer and the logits buffer
-struct WsPlan { size_t act, full, logits, lstm, strand, total; long long n_units; };
+struct WsPlan { size_t act, full, logits, lstm, strand, c1, total; long long n_units; };
 
 // the one-launch recurrence (sb_lstm.cu) runs this layer at this precision
 bool lstm_persistent(const NetLayer& N, int precision) {
@@ -838,6 +878,10 @@ bool lstm_persistent(const NetLayer& N, int precision) {
 
 long long chunk_for(const sb_net* net, int precision, bool generic) {
     long long c = generic ? 256 : chunk_rows(precision);
+    // first conv one chunk ahead (conv1_ahead): smaller chunks leave less of it exposed at the start of a call
+    if (!generic && precision == SB_PREC_BF16 && net->layers[0].w1m_packed && !net->strand_mode && !net->has_lstm &&
+        !getenv("SB_CHUNK"))
+        c = 4096;
     if (net->has_lstm) {  // chunks must hold whole recurrence blocks
         const long long blk = (long long)net->rec_group * net->rec_interleave;
         long long cap = 2048;
@@ -854,6 +898,15 @@ long long chunk_for(const sb_net* net, int precision, bool generic) {
         if (c < blk) c = blk;
     }
     return c;
+}
+
+// The register-accumulator first conv (sb_conv1m.cu) needs neither tensor memory nor much shared memory, so its CTAs
+// fit on an SM next to a tc_layer_kernel CTA: with several chunks to do, the first conv of chunk k+1 runs on a side
+// stream while the tcgen05 layers of chunk k run, into one of two extra buffers (SB_CONV1_AHEAD=0 disables it).
+bool conv1_ahead(const sb_net* net, long long n, int precision, bool generic) {
+    const char* e = getenv("SB_CONV1_AHEAD");
+    return precision == SB_PREC_BF16 && !generic && net->layers[0].w1m_packed && !net->strand_mode && !net->has_lstm &&
+           n > chunk_for(net, precision, generic) && !(e && e[0] == '0');
 }
 
 WsPlan plan_ws(const sb_net* net, long long n, int precision, bool generic) {
@@ -904,7 +957,12 @@ WsPlan plan_ws(const sb_net* net, long long n, int precision, bool generic) {
     p.logits = al((size_t)ch * round_up(net->n_out, 4) * 4);
     // NonStrandSpecific: probabilities of both strands + the reverse-complemented rows of the chunk
     p.strand = net->strand_mode ? al(2 * (size_t)ch * net->n_out * 4) + al((size_t)ch * net->L * (generic ? 16 : 1)) : 0;
-    p.total = 2 * p.act + p.full + p.logits + p.lstm + p.strand + 4096;
+    p.c1 = 0;
+    if (conv1_ahead(net, n, precision, generic)) {
+        const NetLayer& N0 = net->layers[0];
+        p.c1 = al((size_t)ch * N0.pitch_out * N0.out_ld_b * 2);
+    }
+    p.total = 2 * p.act + p.full + p.logits + p.lstm + p.strand + 2 * p.c1 + 4096;
     return p;
 }
 
@@ -1083,7 +1141,8 @@ int run_lstm(sb_net* net, const NetLayer& N, const void* act_in, void* act_out, 
 // Runs rows [r0, r0+m) through the network; leaves fp32 logits (row stride ldl) in ws logits buffer.
 int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int precision, uint8_t* ws,
               const WsPlan& plan, float** logits_out, int* ldl_out, cudaStream_t stream,
-              const SbScoreEpilogue* fused = nullptr) {
+              const SbScoreEpilogue* fused = nullptr, int phase = 0, void* l0_buf = nullptr) {
+    // phase 0: the whole network; 1: the first conv only, into l0_buf; 2: every other layer, reading l0_buf
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023);
     void* act[2] = {base, base + plan.act};
     float* full = reinterpret_cast<float*>(base + 2 * plan.act);
@@ -1094,6 +1153,7 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
     int cur = 0;
 
     // ---- layer 0
+    if (phase != 2) {
     time_begin(net, 0, stream);
     {
         const NetLayer& N = net->layers[0];
@@ -1102,7 +1162,12 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
             const size_t smem = (size_t)N.k * 5 * N.cout * sizeof(float) + (size_t)round_up(net->L, 16);
             SB_REQUIRE(smem <= 220 * 1024, "first-layer lookup table (%zu B) does not fit shared memory", smem);
             int threads = round_up(out_ld < 512 ? out_ld : 512, 32);
-            if (bf && N.w1_packed) {
+            if (bf && N.w1m_packed) {
+                int rc = sb_conv1_mma_launch(in.codes, in.src, in.sub_pos, in.sub_code, r0, m, net->L, N.k, N.pool,
+                                             N.t_pool, N.pitch_out, N.cout, out_ld, N.relu, N.w1m_packed, N.bias1m,
+                                             phase == 1 ? l0_buf : act[cur], dev, stream, phase == 1 && r0 > 0 ? 1 : 2);
+                if (rc) return rc;
+            } else if (bf && N.w1_packed) {
                 int rc = sb_conv1_tc_launch(in.codes, in.src, in.sub_pos, in.sub_code, r0, m, net->L, N.k, N.pool,
                                             N.t_pool, N.pitch_out, N.cout, out_ld, N.relu, N.w1_packed,
                                             N.bias1_padded, act[cur], dev, stream);
@@ -1175,6 +1240,8 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
     }
 
     time_end(net, 0, stream);
+    }
+    if (phase == 1) return SB_OK;
 
     // ---- remaining layers
     for (size_t li = 1; li < net->layers.size(); ++li) {
@@ -1192,7 +1259,7 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
         if (bf) {
             SbTcLayer T;
             memset(&T, 0, sizeof(T));
-            T.a = act[cur];
+            T.a = (phase == 2 && li == 1) ? l0_buf : act[cur];
             T.rows_a = m * (long long)N.pitch_in;
             T.a_ld = N.a_ld;
             T.bias = N.biasb; T.block_n = N.block_n; T.n_tiles_n = N.n_tiles_n;
@@ -1202,16 +1269,24 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
             T.out_f32 = last ? (fused ? 2 : 1) : 0;
             T.out = last ? (void*)logits : act[cur ^ 1];
             T.out_ld = last ? ldl : N.out_ld_b;
+            // conv layers: im2col tensor map (valid window starts only) -> overlapping-stride view -> per-tap boxes,
+            // each the fallback of the one before if the driver refuses the tensor map
             bool per_tap = net->force_per_tap && N.type == SB_LAYER_CONV;
+            bool im2col = N.type == SB_LAYER_CONV && N.k > 1 && N.wb_tap && !net->no_im2col;
             int rc = SB_OK;
-            for (int attempt = 0; attempt < 2; ++attempt) {
-                if (per_tap) {
+            for (int attempt = 0; attempt < 3; ++attempt) {
+                T.im2col = 0;
+                if (im2col) {
+                    T.per_tap = 1; T.im2col = 1; T.taps = N.k; T.w = N.wb_tap; T.w_ld = N.w_ld_tap; T.k_full = N.k_full_tap;
+                } else if (per_tap) {
                     T.per_tap = 1; T.taps = N.k; T.w = N.wb_tap; T.w_ld = N.w_ld_tap; T.k_full = N.k_full_tap;
                 } else {
                     T.per_tap = 0; T.taps = N.k; T.w = N.wb; T.w_ld = N.w_ld; T.k_full = N.k_full;
                 }
                 rc = sb_tc_launch(T, dev, stream, last ? fused : nullptr);
-                if (rc == SB_OK || per_tap || N.type != SB_LAYER_CONV) break;
+                if (rc == SB_OK || N.type != SB_LAYER_CONV) break;
+                if (im2col) { im2col = false; net->no_im2col = true; continue; }
+                if (per_tap) break;
                 per_tap = true;            // overlapping-stride tensor map refused: fall back to per-tap boxes
                 net->force_per_tap = true;
             }
@@ -1285,10 +1360,65 @@ static int forward_impl(sb_net* net, const RowSource& in, int64_t n, int precisi
         SB_REQUIRE(n % 2 == 0, "interleaved ref/alt rows need an even row count, got %lld", (long long)n);
         chunk &= ~1ll;
     }
-    for (long long r0 = 0; r0 < n; r0 += chunk) {
+    const bool ahead = conv1_ahead(net, n, precision, generic) && plan.c1 > 0;
+    void* c1_buf[2] = {nullptr, nullptr};
+    if (ahead) {
+        if (!net->side) {
+            SB_CHECK_CUDA(cudaStreamCreateWithFlags(&net->side, cudaStreamNonBlocking));
+            SB_CHECK_CUDA(cudaEventCreateWithFlags(&net->ev_fork, cudaEventDisableTiming));
+            for (int i = 0; i < 2; ++i) {
+                SB_CHECK_CUDA(cudaEventCreateWithFlags(&net->ev_c1[i], cudaEventDisableTiming));
+                SB_CHECK_CUDA(cudaEventCreateWithFlags(&net->ev_done[i], cudaEventDisableTiming));
+            }
+        }
+        uint8_t* b0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023) + 2 * plan.act +
+                      plan.full + plan.logits + plan.lstm + plan.strand;
+        c1_buf[0] = b0;
+        c1_buf[1] = b0 + plan.c1;
+        // the side stream starts after everything already queued on the caller's stream (the inputs)
+        SB_CHECK_CUDA(cudaEventRecord(net->ev_fork, s));
+        SB_CHECK_CUDA(cudaStreamWaitEvent(net->side, net->ev_fork, 0));
+        float* lg0 = nullptr;
+        int ldl0 = 0;
+        const long long m0 = n < chunk ? n : chunk;
+        rc = run_chunk(net, in, 0, m0, precision, reinterpret_cast<uint8_t*>(ws), plan, &lg0, &ldl0, net->side, nullptr, 1, c1_buf[0]);
+        if (rc) return rc;
+        SB_CHECK_CUDA(cudaEventRecord(net->ev_c1[0], net->side));
+    }
+    long long k_chunk = 0;
+    for (long long r0 = 0; r0 < n; r0 += chunk, ++k_chunk) {
         const long long m = (n - r0) < chunk ? (n - r0) : chunk;
         float* lg = nullptr;
         int ldl = 0;
+        if (ahead) {
+            // first conv of chunk k+1 (side stream; its buffer was last read by chunk k-1), then layers 1.. of chunk k
+            const long long r1 = r0 + chunk;
+            if (r1 < n) {
+                const long long m1 = (n - r1) < chunk ? (n - r1) : chunk;
+                if (k_chunk >= 1) SB_CHECK_CUDA(cudaStreamWaitEvent(net->side, net->ev_done[(k_chunk - 1) & 1], 0));
+                rc = run_chunk(net, in, r1, m1, precision, reinterpret_cast<uint8_t*>(ws), plan, &lg, &ldl, net->side, nullptr, 1,
+                               c1_buf[(k_chunk + 1) & 1]);
+                if (rc) return rc;
+                SB_CHECK_CUDA(cudaEventRecord(net->ev_c1[(k_chunk + 1) & 1], net->side));
+            }
+            SB_CHECK_CUDA(cudaStreamWaitEvent(s, net->ev_c1[k_chunk & 1], 0));
+            SbScoreEpilogue E;
+            memset(&E, 0, sizeof(E));
+            E.F = F;
+            E.row0 = r0;
+            if (!scoring) { E.mode = 0; E.pred = pred; }
+            else {
+                E.mode = pair_mode == SB_PAIR_INTERLEAVED ? 1 : 2;
+                E.base_pred = base_pred; E.base_index = base_index;
+                E.abs_diff = abs_diff; E.diff = diff; E.logit = logit;
+                E.pred_ref = pair_mode == SB_PAIR_INTERLEAVED ? pred_ref : nullptr;
+                E.pred_alt = pred_alt;
+            }
+            rc = run_chunk(net, in, r0, m, precision, reinterpret_cast<uint8_t*>(ws), plan, &lg, &ldl, s, &E, 2, c1_buf[k_chunk & 1]);
+            if (rc) return rc;
+            SB_CHECK_CUDA(cudaEventRecord(net->ev_done[k_chunk & 1], s));
+            continue;
+        }
         if (net->strand_mode) {
             // both strands through the network, combined probabilities, then the handlers' math on those
             uint8_t* sbase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023) +

@@ -45,6 +45,9 @@ struct TcParams {
     int out_ld, relu, out_f32;
     int block_n, n_tiles_n, n_tiles_m, num_k_blocks;
     int chunks_per_tap;  // 0: overlapping-stride A view; >0: per-tap boxes
+    int im2col;          // per-tap boxes through an im2col tensor map: tiles enumerate valid window starts only
+    int v_pix;           // im2col: valid window starts per sequence (= pool * t_pool); the epilogue's rows per sequence
+    int last_k16;        // K = 16 slices multiplied in a tap's last 64-channel chunk (4 unless SB_TC_SKIPK=1, see the MMA loop)
     int stages, stage_bytes;   // smem ring: stage = A tile (16 KB) + B tile (block_n x 128 B)
     // narrow layers (block_n <= 128) run TWO CTAs per SM: half the ring, 256 TMEM columns (2 x 128) each.  One
     // issuing thread needs ~600 cycles per k-block (wait, descriptors, 4 MMAs, commit) but a 128 x 64 x 64 k-block
@@ -130,7 +133,13 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     uint8_t* sa = smem + stage * p.stage_bytes;
                     uint8_t* sb = sa + kABytes;
                     sb_mbar_expect_tx(&full_bar[stage], tx_bytes);
-                    if (p.chunks_per_tap > 0) {
+                    if (p.im2col) {
+                        // 128 window starts from (position w, sequence n) on, read at position + tap
+                        const int tap = kb / p.chunks_per_tap;
+                        const int n = m0 / p.v_pix;
+                        sb_tma_load_im2col_3d(sa, &tmap_a, &full_bar[stage], (kb - tap * p.chunks_per_tap) * kBlockK,
+                                              m0 - n * p.v_pix, n, (uint16_t)tap);
+                    } else if (p.chunks_per_tap > 0) {
                         const int tap = kb / p.chunks_per_tap;
                         sb_tma_load_2d(sa, &tmap_a, &full_bar[stage],
                                        (kb - tap * p.chunks_per_tap) * kBlockK, m0 + tap);
@@ -160,10 +169,17 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     const uint32_t sa = sb_smem_u32(smem + stage * p.stage_bytes);
                     const uint64_t da = sb_umma_desc_sw128(sa);
                     const uint64_t db = sb_umma_desc_sw128(sa + kABytes);
+                    // im2col: the last chunk of a tap may hold fewer than 64 real channels (480 = 7 x 64 + 32; TMA zero-fills
+                    // the rest and the per-tap weights are zero-padded).  Its empty K slices are multiplied all the same
+                    // unless SB_TC_SKIPK=1: skipping them halves that k-block's tensor time but not its 46 KB of loads, and
+                    // the ring then starves (r02, conv3: 11.0 ms with the slices, 12.5 ms without them, 11.6 ms before im2col)
+                    int nk = kBlockK / 16;
+                    if (p.last_k16 < nk && (kb + 1) % p.chunks_per_tap == 0) nk = p.last_k16;
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k)
-                        sb_umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                     (kb | k) != 0 ? 1u : 0u);
+                        if (k < nk)
+                            sb_umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                         (kb | k) != 0 ? 1u : 0u);
                     sb_umma_commit(&empty_bar[stage]);  // frees the smem stage when the MMAs finish
                     if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -190,8 +206,9 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             // window start is a mask and the only division left is the one by t_in)
             const uint32_t r = (uint32_t)m0 + (uint32_t)row_in_tile;
             const uint32_t rg = r & ~(uint32_t)(p.pool - 1);  // first row of the pool window
-            const uint32_t seq = rg / (uint32_t)p.t_in;
-            const int t = (int)(rg - seq * (uint32_t)p.t_in);
+            const uint32_t rps = (uint32_t)(p.im2col ? p.v_pix : p.t_in);   // rows of the M axis per sequence
+            const uint32_t seq = rg / rps;
+            const int t = (int)(rg - seq * rps);
             const int tp = p.pool == 4 ? t >> 2 : (p.pool == 2 ? t >> 1 : t);
             const bool valid = ((long long)rg < p.rows_a) && (tp < p.t_pool);
             const long long out_row = (long long)seq * p.out_pitch + tp;
@@ -342,6 +359,53 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+EncodeIm2colFn get_encode_im2col_fn() {
+    static EncodeIm2colFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) return nullptr;
+    fn = reinterpret_cast<EncodeIm2colFn>(p);
+    return fn;
+}
+
+// Channel-last bf16 activations (sequence, position, channel) as an im2col tensor: dims {channels, t_in, n_seq}; the
+// window starts ("base pixels") are positions [0, v_pix) of every sequence (upper corner = v_pix - t_in), a load
+// fetches 64 channels of 128 consecutive window starts, continuing in the next sequence, at position + tap.
+int make_tmap_im2col(CUtensorMap* tm, const void* base, uint64_t channels, uint64_t ld, uint64_t t_in, uint64_t n_seq,
+                     int v_pix) {
+    EncodeIm2colFn fn = get_encode_im2col_fn();
+    if (!fn) {
+        sb_set_error("cuTensorMapEncodeIm2col is not available from the driver");
+        return SB_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {channels, t_in, n_seq};
+    cuuint64_t strides[2] = {ld * 2, t_in * ld * 2};
+    int lower[1] = {0};
+    int upper[1] = {v_pix - (int)t_in};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, lower, upper,
+                    (cuuint32_t)kBlockK, (cuuint32_t)kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        sb_set_error("cuTensorMapEncodeIm2col failed with CUresult %d (channels=%llu t_in=%llu n_seq=%llu v_pix=%d)", (int)r,
+                     (unsigned long long)channels, (unsigned long long)t_in, (unsigned long long)n_seq, v_pix);
+        return SB_ERR_CUDA;
+    }
+    // Drivers up to CUDA 13.1 encode im2col maps of tensors below 128 KB with a flag that makes the load fault; CUTLASS
+    // (cute/atom/copy_traits_sm90_im2col.hpp) clears bit 21 of the second descriptor word for them, and so do we.
+    int drv = 0;
+    if (cudaDriverGetVersion(&drv) == cudaSuccess && drv <= 13010 && n_seq * t_in * ld * 2 < 131072)
+        reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+    return SB_OK;
+}
+
 // 2-D bf16 tensor: dim0 (contiguous) = inner elements, dim1 = rows with stride row_stride_elems.
 int make_tmap(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems,
               uint32_t box_inner, uint32_t box_rows) {
@@ -386,7 +450,17 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbSc
     CUtensorMap tm_a, tm_b;
     int rc;
     int chunks_per_tap = 0;
-    if (L.per_tap) {
+    const int v_pix = (L.t_conv / L.pool) * L.pool;      // window starts that feed a pooled output
+    long long rows_m = L.rows_a;                         // rows of the M axis
+    if (L.per_tap && L.im2col) {
+        chunks_per_tap = (L.a_ld + kBlockK - 1) / kBlockK;
+        SB_REQUIRE(L.k_full == L.taps * chunks_per_tap * kBlockK, "sb_tc_launch: per-tap k_full mismatch");
+        SB_REQUIRE(L.rows_a % L.t_in == 0 && v_pix > 0 && L.t_in - v_pix < 32768 && L.taps <= 65535,
+                   "sb_tc_launch: im2col needs whole sequences (rows %lld, t_in %d)", (long long)L.rows_a, L.t_in);
+        const long long n_seq = L.rows_a / L.t_in;
+        rc = make_tmap_im2col(&tm_a, L.a, (uint64_t)L.a_ld, (uint64_t)L.a_ld, (uint64_t)L.t_in, (uint64_t)n_seq, v_pix);
+        rows_m = n_seq * v_pix;
+    } else if (L.per_tap) {
         chunks_per_tap = (L.a_ld + kBlockK - 1) / kBlockK;
         SB_REQUIRE(L.k_full == L.taps * chunks_per_tap * kBlockK, "sb_tc_launch: per-tap k_full mismatch");
         rc = make_tmap(&tm_a, L.a, (uint64_t)L.a_ld, (uint64_t)L.rows_a, (uint64_t)L.a_ld, kBlockK, kBlockM);
@@ -402,7 +476,14 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbSc
     if (rc != SB_OK) return rc;
 
     TcParams p;
-    p.rows_a = L.rows_a;
+    p.rows_a = rows_m;
+    p.im2col = L.per_tap && L.im2col;
+    p.v_pix = v_pix;
+    p.last_k16 = kBlockK / 16;
+    {
+        const char* e = getenv("SB_TC_SKIPK");
+        if (e && e[0] == '1' && p.im2col) p.last_k16 = (L.a_ld - (chunks_per_tap - 1) * kBlockK + 15) / 16;
+    }
     p.t_in = L.t_in;
     p.t_conv = L.t_conv;
     p.pool = L.pool;
@@ -413,7 +494,7 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbSc
     p.out_f32 = L.out_f32;
     p.block_n = L.block_n;
     p.n_tiles_n = L.n_tiles_n;
-    p.n_tiles_m = (int)((L.rows_a + kBlockM - 1) / kBlockM);
+    p.n_tiles_m = (int)((rows_m + kBlockM - 1) / kBlockM);
     p.num_k_blocks = (L.k_full + kBlockK - 1) / kBlockK;
     p.chunks_per_tap = chunks_per_tap;
     const char* narrow_env = getenv("SB_TC_NARROW");

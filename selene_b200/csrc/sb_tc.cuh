@@ -20,6 +20,10 @@ struct SbTcLayer {
                          // 1: one 2-D box per (tap, 64-channel chunk); the weight K axis is then
                          //    taps x (chunks_per_tap*64) with zero padding, k_full = that product
     int taps;            // only used when per_tap
+    int im2col;          // with per_tap: A is fetched through an IM2COL tensor map (channels, position, sequence) whose
+                         // pixel bounding box holds only the pool * t_pool valid window starts of every sequence, so an
+                         // M tile is 128 VALID rows (it walks across sequence boundaries) and no MMA row is wasted on
+                         // windows that straddle two sequences
     const float* bias;   // dev fp32, padded to n_tiles_n * block_n entries
     int block_n;         // UMMA N (multiple of 16, <= 256)
     int n_tiles_n;
