@@ -47,6 +47,7 @@ struct TcParams {
     int chunks_per_tap;  // 0: overlapping-stride A view; >0: per-tap boxes
     int im2col;          // per-tap boxes through an im2col tensor map: tiles enumerate valid window starts only
     int v_pix;           // im2col: valid window starts per sequence (= pool * t_pool); the epilogue's rows per sequence
+    int k_splits, kb_per_split;   // split-K (out_f32 == 3): tile = (range, m, n)
     int last_k16;        // K = 16 slices multiplied in a tap's last 64-channel chunk (4 unless SB_TC_SKIPK=1, see the MMA loop)
     int stages, stage_bytes;   // smem ring: stage = A tile (16 KB) + B tile (block_n x 128 B)
     // narrow layers (block_n <= 128) run TWO CTAs per SM: half the ring, 256 TMEM columns (2 x 128) each.  One
@@ -97,7 +98,8 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.n_tiles_m * p.n_tiles_n;
+    const int tiles_mn = p.n_tiles_m * p.n_tiles_n;
+    const int num_tiles = tiles_mn * p.k_splits;
 
     if (warp == 0 && lane == 0) {
         sb_prefetch_tmap(&tmap_a);
@@ -126,9 +128,12 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             uint32_t stage = 0, phase = 0;
             const uint32_t tx_bytes = kABytes + (uint32_t)p.block_n * kBlockK * 2;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int m0 = (tile / p.n_tiles_n) * kBlockM;
-                const int n0 = (tile % p.n_tiles_n) * p.block_n;
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                const int mn = tile % tiles_mn;
+                const int m0 = (mn / p.n_tiles_n) * kBlockM;
+                const int n0 = (mn % p.n_tiles_n) * p.block_n;
+                const int kb0 = (tile / tiles_mn) * p.kb_per_split;
+                const int kb1 = kb0 + p.kb_per_split < p.num_k_blocks ? kb0 + p.kb_per_split : p.num_k_blocks;
+                for (int kb = kb0; kb < kb1; ++kb) {
                     sb_mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * p.stage_bytes;
                     uint8_t* sb = sa + kABytes;
@@ -163,7 +168,9 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 sb_mbar_wait(&tempty_bar[as], aphase ^ 1);
                 sb_tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * p.acc_stride;
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                const int kb0 = (tile / tiles_mn) * p.kb_per_split;
+                const int kb1 = kb0 + p.kb_per_split < p.num_k_blocks ? kb0 + p.kb_per_split : p.num_k_blocks;
+                for (int kb = kb0; kb < kb1; ++kb) {
                     sb_mbar_wait(&full_bar[stage], phase);
                     sb_tc_fence_after();
                     const uint32_t sa = sb_smem_u32(smem + stage * p.stage_bytes);
@@ -179,7 +186,7 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     for (int k = 0; k < kBlockK / 16; ++k)
                         if (k < nk)
                             sb_umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                         (kb | k) != 0 ? 1u : 0u);
+                                         (kb > kb0 || k > 0) ? 1u : 0u);
                     sb_umma_commit(&empty_bar[stage]);  // frees the smem stage when the MMAs finish
                     if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -195,8 +202,9 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-            const int m0 = (tile / p.n_tiles_n) * kBlockM;
-            const int n0 = (tile % p.n_tiles_n) * p.block_n;
+            const int mn = tile % tiles_mn;
+            const int m0 = (mn / p.n_tiles_n) * kBlockM;
+            const int n0 = (mn % p.n_tiles_n) * p.block_n;
             float* bs = bias_s + as * kMaxN;
             for (int i = et; i < p.block_n; i += 128) bs[i] = __ldg(p.bias + n0 + i);
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -285,6 +293,13 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                                 tc_store_scores(sc, grow * sc.F + nb + j, __ldg(sc.base_pred + bi * sc.F + nb + j), v[j],
                                                 false);
                     }
+                } else if (p.out_f32 == 3) {
+                    // split-K partial sums (bias is zero, no ReLU / pool): lanes are rows, so each red covers one float
+                    float* o = reinterpret_cast<float*>(p.out) + out_row * p.out_ld + nb;
+                    if (valid)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (nb + j < p.out_ld) atomicAdd(o + j, v[j]);
                 } else if (p.out_f32) {
                     float* o = reinterpret_cast<float*>(p.out) + out_row * p.out_ld + nb;
 #pragma unroll
@@ -441,6 +456,8 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbSc
     SB_REQUIRE(L.out_f32 == 2 ? score != nullptr : (L.out_f32 ? (L.out_ld % 4 == 0) : (L.out_ld % 8 == 0)),
                "sb_tc_launch: bad out_ld %d / missing score epilogue", L.out_ld);
     SB_REQUIRE(!(L.out_f32 && L.pool != 1), "sb_tc_launch: fp32 output cannot pool");
+    SB_REQUIRE(L.out_f32 == 3 || L.k_splits <= 1, "sb_tc_launch: split-K needs the accumulating fp32 output mode");
+    SB_REQUIRE(!(L.out_f32 == 3 && (L.relu || L.per_tap)), "sb_tc_launch: split-K tiles cannot apply ReLU / per-tap boxes");
     if (L.rows_a <= 0) return SB_OK;
     SB_REQUIRE(L.rows_a < (1ll << 31) - 256, "sb_tc_launch: %lld rows exceed the 32-bit row arithmetic of the epilogue",
                (long long)L.rows_a);
@@ -497,6 +514,9 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbSc
     p.n_tiles_m = (int)((rows_m + kBlockM - 1) / kBlockM);
     p.num_k_blocks = (L.k_full + kBlockK - 1) / kBlockK;
     p.chunks_per_tap = chunks_per_tap;
+    p.k_splits = (L.out_f32 == 3 && L.k_splits > 1) ? (L.k_splits < p.num_k_blocks ? L.k_splits : p.num_k_blocks) : 1;
+    p.kb_per_split = (p.num_k_blocks + p.k_splits - 1) / p.k_splits;
+    p.k_splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;     // no empty range
     const char* narrow_env = getenv("SB_TC_NARROW");
     const bool narrow = L.block_n <= 128 && !(narrow_env && narrow_env[0] == '0');
     p.ring_bytes = narrow ? kRingBytes / 2 : kRingBytes;
@@ -519,7 +539,7 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbSc
                                            cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
-    const int64_t tiles = (int64_t)p.n_tiles_m * p.n_tiles_n;
+    const int64_t tiles = (int64_t)p.n_tiles_m * p.n_tiles_n * p.k_splits;
     const int sms = sb_sm_count(device);
     const int ctas = narrow ? 2 * sms : sms;
     const int grid = (int)(tiles < ctas ? tiles : ctas);

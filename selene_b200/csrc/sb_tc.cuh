@@ -31,7 +31,10 @@ struct SbTcLayer {
     int t_conv;          // valid conv outputs per sequence: t_in - taps + 1
     int pool;            // 1, 2 or 4 (requires t_in % pool == 0)
     int relu;
-    int out_f32;         // 0: bf16 output, 1: fp32 output, 2: fused sigmoid + score epilogue (`score`)
+    int out_f32;         // 0: bf16 output, 1: fp32 output, 2: fused sigmoid + score epilogue (`score`),
+                         // 3: split-K partial sums ADDED to a zeroed fp32 output (no bias / ReLU / pool: the caller finishes)
+    int k_splits;        // out_f32 == 3: the K axis is cut into this many ranges, one tile per (m, n, range), so that a
+                         // GEMM with few output tiles and a long K (FC over a small batch) still fills every SM
     void* out;           // dev, (sequences * t_pool) x out_ld
     int out_ld;          // bf16: multiple of 8; fp32: multiple of 4
     int out_pitch;       // rows per sequence in `out` (>= t_pool; the consumer's padded t_in); 0 = t_pool

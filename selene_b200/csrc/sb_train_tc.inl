@@ -118,59 +118,117 @@ __global__ void __launch_bounds__(256) pack_dgrad_kernel(const float* __restrict
     }
 }
 
-// pooled[s][tp][c] = max_q full[s][tp*pool+q][c]  (bf16 in / out), optional dropout (mask fp32, per element)
+// 8 bf16 channels <-> 8 floats (16-byte vectors: every leading dimension here is a multiple of 8)
+__device__ __forceinline__ void bf16x8_to_f32(const uint4 v, float (&f)[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        f[2 * k] = __uint_as_float(w[k] << 16);
+        f[2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+    }
+}
+__device__ __forceinline__ uint4 f32_to_bf16x8(const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+        w[k] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// pooled[s][tp][c] = max_q full[s][tp*pool+q][c]  (bf16 in / out), optional dropout (mask fp32, per element).
+// A thread owns 8 channels of one pooled position: `pool` 16-byte loads, one 16-byte store.
 __global__ void __launch_bounds__(256) pool_fwd_bf16_kernel(const bf16* __restrict__ full, int t_full, int pool, int t_pool,
                                                             int ld, long long n_seq, bf16* __restrict__ out,
                                                             const float* __restrict__ mask_in, float* __restrict__ mask_out,
                                                             float p, unsigned long long seed) {
-    const long long total = n_seq * t_pool * ld;
+    const int ld8 = ld >> 3;
+    const long long total = n_seq * t_pool * ld8;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int c = (int)(i % ld);
-        const long long rt = i / ld;
+    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += stride) {
+        const int c8 = (int)(u % ld8);
+        const long long rt = u / ld8;
         const int tp = (int)(rt % t_pool);
         const long long s = rt / t_pool;
-        float m = -INFINITY;
-        for (int q = 0; q < pool; ++q)
-            m = fmaxf(m, __bfloat162float(full[(s * t_full + (long long)tp * pool + q) * ld + c]));
-        if (mask_in) m *= mask_in[i];
-        else if (p > 0.f) { const float k = hash_uniform(seed, (unsigned long long)i) >= p ? scale : 0.f; mask_out[i] = k; m *= k; }
-        out[i] = __float2bfloat16_rn(m);
+        float m[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+        const uint4* src = reinterpret_cast<const uint4*>(full + (s * t_full + (long long)tp * pool) * ld) + c8;
+        for (int q = 0; q < pool; ++q) {
+            float f[8];
+            bf16x8_to_f32(__ldg(src + (long long)q * ld8), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], f[k]);
+        }
+        const long long i0 = rt * ld + 8 * c8;       // element index of channel 8*c8 in the pooled tensor
+        if (mask_in) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(mask_in + i0)), b = __ldg(reinterpret_cast<const float4*>(mask_in + i0) + 1);
+            m[0] *= a.x; m[1] *= a.y; m[2] *= a.z; m[3] *= a.w; m[4] *= b.x; m[5] *= b.y; m[6] *= b.z; m[7] *= b.w;
+        } else if (p > 0.f) {
+            float kk[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                kk[k] = hash_uniform(seed, (unsigned long long)(i0 + k)) >= p ? scale : 0.f;
+                m[k] *= kk[k];
+            }
+            reinterpret_cast<float4*>(mask_out + i0)[0] = make_float4(kk[0], kk[1], kk[2], kk[3]);
+            reinterpret_cast<float4*>(mask_out + i0)[1] = make_float4(kk[4], kk[5], kk[6], kk[7]);
+        }
+        reinterpret_cast<uint4*>(out + i0)[0] = f32_to_bf16x8(m);
     }
 }
 
 // dfull[s][t][c] (t < t_in rows per sequence) from gout[s][t/pool][c]: first maximum of the window and > 0, times the
-// dropout mask; rows t >= t_pool*pool are zero.
+// dropout mask; rows t >= t_pool*pool are zero.  A thread owns 8 channels of one pooling window (or of one tail row).
 __global__ void __launch_bounds__(256) pool_relu_bwd_bf16_kernel(const bf16* __restrict__ full, int t_full, const bf16* __restrict__ gout,
                                                                  const float* __restrict__ mask, int t_in, int pool, int t_pool,
                                                                  int ld, long long n_seq, bf16* __restrict__ dfull) {
-    const long long total = n_seq * t_in * ld;
+    const int ld8 = ld >> 3;
+    const int tail = t_in - t_pool * pool;                  // zero rows at the end of every sequence
+    const int units_seq = t_pool + tail;                    // windows + tail rows
+    const long long total = n_seq * units_seq * ld8;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int c = (int)(i % ld);
-        const long long rt = i / ld;
-        const int t = (int)(rt % t_in);
-        const long long s = rt / t_in;
-        float g = 0.f;
-        const int tp = t / pool;
-        if (tp < t_pool) {
-            const float v = __bfloat162float(full[(s * t_full + t) * ld + c]);
-            if (v > 0.f) {
-                bool first_max = true;
-                for (int q = 0; q < pool; ++q) {
-                    const int tq = tp * pool + q;
-                    const float u = __bfloat162float(full[(s * t_full + tq) * ld + c]);
-                    if (u > v || (u == v && tq < t)) first_max = false;
-                }
-                if (first_max) {
-                    const long long oi = (s * t_pool + tp) * ld + c;
-                    g = __bfloat162float(gout[oi]);
-                    if (mask) g *= mask[oi];
-                }
-            }
+    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += stride) {
+        const int c8 = (int)(u % ld8);
+        const long long ru = u / ld8;
+        const int w = (int)(ru % units_seq);
+        const long long s = ru / units_seq;
+        if (w >= t_pool) {                                  // tail row
+            const long long t = (long long)t_pool * pool + (w - t_pool);
+            reinterpret_cast<uint4*>(dfull + (s * t_in + t) * ld)[c8] = make_uint4(0u, 0u, 0u, 0u);
+            continue;
         }
-        dfull[i] = __float2bfloat16_rn(g);
+        const uint4* src = reinterpret_cast<const uint4*>(full + (s * t_full + (long long)w * pool) * ld) + c8;
+        float best[8];
+        int arg[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; arg[k] = 0; }
+        for (int q = 0; q < pool; ++q) {
+            float f[8];
+            bf16x8_to_f32(__ldg(src + (long long)q * ld8), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (f[k] > best[k]) { best[k] = f[k]; arg[k] = q; }      // strict: the FIRST maximum keeps the gradient
+        }
+        const long long oi = (s * t_pool + w) * ld + 8 * c8;
+        float g[8];
+        bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(gout + oi)), g);
+        if (mask) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(mask + oi)), b = __ldg(reinterpret_cast<const float4*>(mask + oi) + 1);
+            g[0] *= a.x; g[1] *= a.y; g[2] *= a.z; g[3] *= a.w; g[4] *= b.x; g[5] *= b.y; g[6] *= b.z; g[7] *= b.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (!(best[k] > 0.f)) g[k] = 0.f;                // ReLU
+        uint4* dst = reinterpret_cast<uint4*>(dfull + (s * t_in + (long long)w * pool) * ld) + c8;
+        for (int q = 0; q < pool; ++q) {
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = arg[k] == q ? g[k] : 0.f;
+            dst[(long long)q * ld8] = f32_to_bf16x8(o);
+        }
     }
 }
 
@@ -183,6 +241,21 @@ __global__ void __launch_bounds__(256) fc_bwd_bf16_kernel(bf16* __restrict__ g, 
         if (mask) v *= mask[i];
         if (relu && !(__bfloat162float(y[i]) > 0.f)) v = 0.f;
         g[i] = __float2bfloat16_rn(v);
+    }
+}
+
+// y[r][c] = act(acc[r][c] + bias[c]) as bf16 (c < ld; columns >= cout are zero): finishes a split-K FC forward
+__global__ void __launch_bounds__(256) bias_act_bf16_kernel(const float* __restrict__ acc, const float* __restrict__ bias,
+                                                            long long rows, int cout, int ld, int relu, bf16* __restrict__ y) {
+    const long long total = rows * ld;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % ld);
+        float v = 0.f;
+        if (c < cout) {
+            v = acc[i] + bias[c];
+            if (relu) v = fmaxf(v, 0.f);
+        }
+        y[i] = __float2bfloat16(v);
     }
 }
 
@@ -288,6 +361,47 @@ __global__ void __launch_bounds__(128) conv1_wgrad_kernel(const float* __restric
     }
 }
 
+// first conv on tcgen05: the (n, L, 4) fp32 input as bf16 rows of 8 channels (4 real + 4 zero), `pad` zero rows appended
+__global__ void __launch_bounds__(256) x_to_bf16x8_kernel(const float4* __restrict__ x, long long rows, long long rows_alloc,
+                                                          uint4* __restrict__ out) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows_alloc; r += (long long)gridDim.x * blockDim.x) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (r < rows) {
+            const float4 f = __ldg(x + r);
+            __nv_bfloat162 a = __floats2bfloat162_rn(f.x, f.y), b = __floats2bfloat162_rn(f.z, f.w);
+            v.x = *reinterpret_cast<uint32_t*>(&a);
+            v.y = *reinterpret_cast<uint32_t*>(&b);
+        }
+        out[r] = v;
+    }
+}
+
+// first conv B operand + padded bias from the fp32 master: w0[o][tap*8 + c] = W[tap*4 + c][o] (c < 4, else 0)
+__global__ void __launch_bounds__(256) pack_w0_kernel(const float* __restrict__ wf, int ldw, int taps, int cout, int rows_w,
+                                                      int w_ld, bf16* __restrict__ w0, const float* __restrict__ bias,
+                                                      float* __restrict__ bias_pad, int n_bias) {
+    const int total = rows_w * w_ld;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int o = i / w_ld, k = i - o * w_ld;
+        const int tap = k >> 3, c = k & 7;
+        float v = 0.f;
+        if (o < cout && tap < taps && c < 4) v = wf[(size_t)(tap * 4 + c) * ldw + o];
+        w0[i] = __float2bfloat16_rn(v);
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_bias; i += gridDim.x * blockDim.x)
+        bias_pad[i] = i < cout ? bias[i] : 0.f;
+}
+
+// gw[(tap*4 + c)][o] += g8[(tap*8 + c)][o]  (c < 4): the 8-channel rows of the tcgen05 weight gradient back to the 4-channel layout
+__global__ void __launch_bounds__(256) w0_grad_unpad_kernel(const float* __restrict__ g8, int ld8, int taps, int cout,
+                                                            float* __restrict__ gw, int ldw) {
+    const int total = taps * 4 * cout;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int kk = i / cout, o = i - kk * cout;
+        gw[(size_t)kk * ldw + o] += g8[(size_t)((kk >> 2) * 8 + (kk & 3)) * ld8 + o];
+    }
+}
+
 struct TcTrainLayer {
     bf16* wb;      // forward B operand (cout x w_ld)
     bf16* wt;      // dgrad B operand (cin x wt_ld)
@@ -301,6 +415,11 @@ struct TcTrainLayer {
 struct sb_train_tc_state {
     std::vector<TcTrainLayer> L;
     bool packed_fresh;   // the bf16 operands match the fp32 master weights (sb_net_sgd_step repacks while it updates)
+    // first conv on tcgen05 (SB_TRAIN_L0_TC=0 keeps it on CUDA cores): bf16 weights (rows x taps*8), padded bias, tiling
+    bool l0_tc;
+    bf16* w0b;
+    float* bias0;
+    int w0_ld, w0_block_n, w0_n_tiles_n;
 };
 
 namespace {
@@ -319,7 +438,7 @@ bool tc_trainable(const sb_net* net, const char** why) {
 
 struct TcPlan {
     std::vector<size_t> full, pooled, mask;   // per layer byte offsets (layer 0: fp32 full / fp32 pooled / mask, + bf16 pooled)
-    size_t x1b, g_a, g_b, g32, logits, total;
+    size_t x1b, g_a, g_b, g32, logits, fc32, x8, g8, total;
 };
 
 TcPlan plan_train_tc(const sb_net* net, long long n) {
@@ -346,15 +465,24 @@ TcPlan plan_train_tc(const sb_net* net, long long n) {
     // fp32 scratch for the first conv's backward: dfull over all input rows with (taps-1) leading rows
     P.g32 = off; off += align256(((size_t)n * net->layers[0].t_in + 8) * net->layers[0].cout * 4 * 2);
     P.logits = off; off += align256((size_t)n * round_up(net->n_out, 4) * 4);
+    // fp32 accumulator of split-K FC forwards (small batches: see the forward pass)
+    size_t fc32 = 0;
+    for (size_t li = 1; li < net->layers.size(); ++li)
+        if (net->layers[li].type == SB_LAYER_FC) fc32 = std::max(fc32, (size_t)n * round_up(net->layers[li].cout, 8) * 4);
+    P.fc32 = off; off += align256(fc32);
+    // first conv on tcgen05: input as 8-channel bf16 rows (+ taps zero rows), fp32 weight gradient over 8-channel rows
+    P.x8 = off; off += align256(((size_t)n * net->layers[0].t_in + net->layers[0].k + 8) * 16);
+    P.g8 = off; off += align256((size_t)net->layers[0].k * 8 * net->layers[0].ldw_f32 * 4);
     P.total = off + 1024;
     return P;
 }
 
 int launch_tc_plain(const void* a, long long rows_a, int a_ld, int k_full, const void* w, int n_rows_w, int w_ld,
                     const float* bias, int block_n, int n_tiles_n, int t_in, int t_conv, int relu, int out_f32, void* out,
-                    int out_ld, int out_pitch, int dev, cudaStream_t s) {
+                    int out_ld, int out_pitch, int dev, cudaStream_t s, int k_splits = 1) {
     SbTcLayer T;
     memset(&T, 0, sizeof(T));
+    T.k_splits = k_splits;
     T.a = a; T.rows_a = rows_a; T.a_ld = a_ld; T.k_full = k_full;
     T.w = w; T.n_rows_w = n_rows_w; T.w_ld = w_ld;
     T.bias = bias; T.block_n = block_n; T.n_tiles_n = n_tiles_n;
@@ -373,6 +501,19 @@ extern "C" int sb_net_train_init_tc(sb_net* net) {
     SB_REQUIRE(tc_trainable(net, &why), "sb_net_train_init_tc: unsupported on the tcgen05 training path (%s); use fp32", why);
     sb_train_tc_state* S = new sb_train_tc_state();
     S->packed_fresh = false;
+    {
+        const NetLayer& N0 = net->layers[0];
+        const char* e = getenv("SB_TRAIN_L0_TC");
+        S->l0_tc = !(e && e[0] == '0');
+        S->w0_ld = N0.k * 8;
+        S->w0_n_tiles_n = (N0.cout + 255) / 256;
+        S->w0_block_n = round_up((N0.cout + S->w0_n_tiles_n - 1) / S->w0_n_tiles_n, 16);
+        const size_t rows_w = (size_t)S->w0_n_tiles_n * S->w0_block_n;
+        S->w0b = nullptr;
+        S->bias0 = nullptr;
+        SB_CHECK_CUDA(cudaMalloc(&S->w0b, rows_w * S->w0_ld * 2));
+        SB_CHECK_CUDA(cudaMalloc(&S->bias0, rows_w * 4));
+    }
     S->L.resize(net->layers.size());
     size_t max_cols = 256;
     for (size_t li = 1; li < net->layers.size(); ++li) {
@@ -439,13 +580,34 @@ extern "C" int sb_net_forward_backward_tc(sb_net* net, const float* x, const flo
     }
 
     // ------------------------------------------------------------------ forward
-    // layer 0 on CUDA cores (fp32), output converted to bf16
+    // layer 0: tcgen05 over the input as 8-channel bf16 rows (one 64-wide k-block for 8 taps), or CUDA cores (fp32)
     const NetLayer& N0 = net->layers[0];
     float* full0 = reinterpret_cast<float*>(base + P.full[0]);
     float* pooled0 = reinterpret_cast<float*>(base + P.pooled[0]);
     bf16* x1b = reinterpret_cast<bf16*>(base + P.x1b);
     const int ld0b = round_up(N0.cout, 8);
-    {
+    bf16* x8 = reinterpret_cast<bf16*>(base + P.x8);
+    bf16* full0b = reinterpret_cast<bf16*>(base + P.full[0]);
+    if (S->l0_tc) {
+        const long long rows = (long long)n * N0.t_in;
+        const long long rows_alloc = rows + N0.k;
+        x_to_bf16x8_kernel<<<grid_for(rows_alloc, dev), 256, 0, s>>>(reinterpret_cast<const float4*>(x), rows, rows_alloc,
+                                                                     reinterpret_cast<uint4*>(x8));
+        SB_COUNT_LAUNCH();
+        const int rows_w = S->w0_n_tiles_n * S->w0_block_n;
+        pack_w0_kernel<<<grid_for((long long)rows_w * S->w0_ld, dev), 256, 0, s>>>(N0.wf, N0.ldw_f32, N0.k, N0.cout, rows_w,
+                                                                                  S->w0_ld, S->w0b, N0.biasf, S->bias0, rows_w);
+        SB_COUNT_LAUNCH();
+        SB_CHECK_LAUNCH();
+        int rc = launch_tc_plain(x8, rows, 8, N0.k * 8, S->w0b, N0.cout, S->w0_ld, S->bias0, S->w0_block_n, S->w0_n_tiles_n,
+                                 N0.t_in, N0.t_conv, N0.relu, 0, full0b, ld0b, N0.t_conv, dev, s);
+        if (rc) return rc;
+        const long long pe = (long long)n * N0.t_pool * ld0b;
+        pool_fwd_bf16_kernel<<<grid_for(pe, dev), 256, 0, s>>>(full0b, N0.t_conv, N0.pool, N0.t_pool, ld0b, n, x1b, ext_mask(0),
+                                                               mask_of(0), T->dropout_p[0], seed_of(0));
+        SB_COUNT_LAUNCH();
+        SB_CHECK_LAUNCH();
+    } else {
         const long long rows = (long long)n * N0.t_in;
         int rc = launch_gemm_gen(x, rows * 4, 4, 1, N0.wf, N0.ldw_f32, 1, rows, N0.cout, N0.k_f32, N0.biasf, N0.relu, full0,
                                  N0.cout, s);
@@ -484,9 +646,27 @@ extern "C" int sb_net_forward_backward_tc(sb_net* net, const float* x, const flo
             SB_CHECK_LAUNCH();
             if (!last) xin[li + 1] = pooled;
         } else {
-            rc = launch_tc_plain(xin[li], n, N.a_ld, N.k_full, N.wb, N.cout, N.w_ld, N.biasb, N.block_n, N.n_tiles_n, 1, 1,
-                                 N.relu, last ? 1 : 0, last ? (void*)logits : (void*)full, last ? ldl : ldo, 1, dev, s);
-            if (rc) return rc;
+            // A small batch gives an FC layer a handful of output tiles (batch 64 x 925 outputs: 4) over a very long K
+            // (50 880): split K over the SMs, partial sums added into an fp32 buffer, bias + ReLU in a finishing pass
+            const long long out_tiles = ((n + 127) / 128) * N.n_tiles_n;
+            const int kbs = (N.k_full + 63) / 64;
+            const int sms = sb_sm_count(dev);
+            int splits = 1;
+            if (!last && out_tiles * 2 <= sms && kbs >= 32) splits = (int)std::min<long long>(kbs / 4, sms / out_tiles);
+            if (splits > 1) {
+                float* acc = reinterpret_cast<float*>(base + P.fc32);
+                SB_CHECK_CUDA(cudaMemsetAsync(acc, 0, (size_t)n * ldo * 4, s));
+                rc = launch_tc_plain(xin[li], n, N.a_ld, N.k_full, N.wb, N.cout, N.w_ld, net->zero_bias_tc, N.block_n,
+                                     N.n_tiles_n, 1, 1, 0, 3, acc, ldo, 1, dev, s, splits);
+                if (rc) return rc;
+                bias_act_bf16_kernel<<<grid_for((long long)n * ldo, dev), 256, 0, s>>>(acc, N.biasb, n, N.cout, ldo, N.relu, full);
+                SB_COUNT_LAUNCH();
+                SB_CHECK_LAUNCH();
+            } else {
+                rc = launch_tc_plain(xin[li], n, N.a_ld, N.k_full, N.wb, N.cout, N.w_ld, N.biasb, N.block_n, N.n_tiles_n, 1, 1,
+                                     N.relu, last ? 1 : 0, last ? (void*)logits : (void*)full, last ? ldl : ldo, 1, dev, s);
+                if (rc) return rc;
+            }
             if (!last && (T->dropout_p[li] > 0.f || ext_mask(li))) {
                 dropout_bf16_kernel<<<grid_for((long long)n * ldo, dev), 256, 0, s>>>(full, (long long)n * ldo, ext_mask(li),
                                                                                       mask_of(li), T->dropout_p[li], seed_of(li));
@@ -561,8 +741,29 @@ extern "C" int sb_net_forward_backward_tc(sb_net* net, const float* x, const flo
         if (li == 1) break;
     }
 
-    // ------------------------------------------------------------------ layer 0 backward on CUDA cores
-    {
+    // ------------------------------------------------------------------ layer 0 backward
+    if (S->l0_tc) {
+        // dfull over all t_in rows of every sequence (rows >= t_conv are zero, so the input windows that run into the next
+        // sequence contribute nothing), weight gradient on tcgen05 over the 8-channel rows, bias gradient as a column sum
+        const long long rows = (long long)n * N0.t_in;
+        const bool dropped0 = T->dropout_p[0] > 0.f || ext_mask(0);
+        const float* mk0 = dropped0 ? (ext_mask(0) ? ext_mask(0) : mask_of(0)) : nullptr;
+        bf16* dfull0 = g_oth;
+        pool_relu_bwd_bf16_kernel<<<grid_for(rows * ld0b, dev), 256, 0, s>>>(full0b, N0.t_conv, g_cur, mk0, N0.t_in, N0.pool,
+                                                                            N0.t_pool, ld0b, n, dfull0);
+        SB_COUNT_LAUNCH();
+        float* g8 = reinterpret_cast<float*>(base + P.g8);
+        SB_CHECK_CUDA(cudaMemsetAsync(g8, 0, (size_t)N0.k * 8 * N0.ldw_f32 * 4, s));
+        int rc = sb_tc_wgrad_launch(dfull0, ld0b, x8, 8, rows + N0.k, rows, N0.cout, N0.k * 8, g8, N0.ldw_f32, dev, s);
+        if (rc) return rc;
+        w0_grad_unpad_kernel<<<grid_for((long long)N0.k * 4 * N0.cout, dev), 256, 0, s>>>(g8, N0.ldw_f32, N0.k, N0.cout,
+                                                                                         grads + T->goff_w[0], N0.ldw_f32);
+        SB_COUNT_LAUNCH();
+        colsum_bf16_kernel<<<dim3((N0.cout + 31) / 32, (unsigned)((rows + kColsumRows - 1) / kColsumRows)), 256, 0, s>>>(
+            dfull0, rows, ld0b, N0.cout, grads + T->goff_b[0]);
+        SB_COUNT_LAUNCH();
+        SB_CHECK_LAUNCH();
+    } else {
         const long long pe = (long long)n * N0.t_pool * N0.cout;
         float* g32 = reinterpret_cast<float*>(base + P.g32);
         float* dpool32 = g32;                                     // (n, t_pool, cout) fp32
@@ -618,6 +819,8 @@ static void free_train_states(sb_net* net) {
     }
     if (net->train_tc) {
         for (auto& T : net->train_tc->L) cudaFree(T.wt);
+        cudaFree(net->train_tc->w0b);
+        cudaFree(net->train_tc->bias0);
         delete net->train_tc;
         net->train_tc = nullptr;
     }
