@@ -295,6 +295,11 @@ int sb_net_forward_backward_tc(sb_net* net, const float* x, const float* targets
                                const float* const* dropout_masks, unsigned long long dropout_seed,
                                void* workspace, size_t workspace_bytes, float* grads, float* loss, void* stream);
 
+/* fp32 <-> bf16 casts of a flat device vector: data-parallel training sends its gradients as bf16 (half the bytes
+ * of the all-reduce the reference's DataParallel / DDP would do in fp32, train_model.py:469-508). */
+int sb_cast_f32_to_bf16(const float* in, int64_t n, void* out_bf16, void* stream);
+int sb_cast_bf16_to_f32(const void* in_bf16, int64_t n, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* packed training samples (samplers/dataloader.py:129-147, scripts/sampler_write_to_h5.py:63-89) */
 /* ------------------------------------------------------------------------------------------ */

@@ -80,6 +80,8 @@ SIGNATURES = {
     "sb_net_get_layer_momentum": (_I, [_P, _I, _P, _P]),
     "sb_net_set_layer_momentum": (_I, [_P, _I, _P, _P]),
     "sb_score_pairs": (_I, [_P, _P, _P, _L, _L, _I, _P, _P, _P, _I, _P]),
+    "sb_cast_f32_to_bf16": (_I, [_P, _L, _P, _P]),
+    "sb_cast_bf16_to_f32": (_I, [_P, _L, _P, _P]),
     "sb_unpack_sequences": (_I, [_P, _L, _I, _I, _I, _I, _P, _P]),
     "sb_unpack_targets": (_I, [_P, _L, _I, _I, _P, _P]),
     "sb_pack_samples": (_I, [_P, _P, _L, _I, _I, _P, _P, _P]),

@@ -1572,3 +1572,57 @@ extern "C" int sb_score_pairs(const float* ref, const float* alt, const int32_t*
 
 #include "sb_train.inl"
 #include "sb_train_tc.inl"
+
+// ---------------------------------------------------------------------------------------------
+// fp32 <-> bf16 casts of a flat vector (data-parallel training: gradients travel as bf16, train_model.py)
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, long long n, __nv_bfloat16* __restrict__ out) {
+    const long long n4 = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(in) + i);
+        __nv_bfloat162 a = __floats2bfloat162_rn(f.x, f.y), b = __floats2bfloat162_rn(f.z, f.w);
+        reinterpret_cast<uint2*>(out)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, long long n, float* __restrict__ out) {
+    const long long n4 = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(in) + i);
+        reinterpret_cast<float4*>(out)[i] = make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xFFFF0000u),
+                                                        __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xFFFF0000u));
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __bfloat162float(in[i]);
+}
+}  // namespace
+
+extern "C" int sb_cast_f32_to_bf16(const float* in, int64_t n, void* out, void* stream) {
+    SB_REQUIRE(n >= 0, "sb_cast_f32_to_bf16: bad n");
+    if (n == 0) return SB_OK;
+    SB_REQUIRE(in && out, "sb_cast_f32_to_bf16: null argument");
+    SB_REQUIRE((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0,
+               "sb_cast_f32_to_bf16: buffers must be 16-byte (fp32) / 8-byte (bf16) aligned");
+    int dev = 0;
+    SB_CHECK_CUDA(cudaGetDevice(&dev));
+    cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, dev), 256, 0, (cudaStream_t)stream>>>(in, n, reinterpret_cast<__nv_bfloat16*>(out));
+    SB_COUNT_LAUNCH();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}
+
+extern "C" int sb_cast_bf16_to_f32(const void* in, int64_t n, float* out, void* stream) {
+    SB_REQUIRE(n >= 0, "sb_cast_bf16_to_f32: bad n");
+    if (n == 0) return SB_OK;
+    SB_REQUIRE(in && out, "sb_cast_bf16_to_f32: null argument");
+    SB_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0,
+               "sb_cast_bf16_to_f32: buffers must be 16-byte (fp32) / 8-byte (bf16) aligned");
+    int dev = 0;
+    SB_CHECK_CUDA(cudaGetDevice(&dev));
+    cast_bf16_f32_kernel<<<grid_for(n / 4 + 1, dev), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), n, out);
+    SB_COUNT_LAUNCH();
+    SB_CHECK_LAUNCH();
+    return SB_OK;
+}

@@ -22,8 +22,14 @@ logger = logging.getLogger("selene")
 
 class B200Trainer(object):
     def __init__(self, model_or_layers, sequence_length, lr=0.01, momentum=0.9, weight_decay=1e-6,
-                 dropout=None, perm=(0, 1, 2, 3), device=None, seed=0, precision="fp32"):
+                 dropout=None, perm=(0, 1, 2, 3), device=None, seed=0, precision="fp32", grad_comm_dtype=None):
         import torch
+        # data-parallel gradient exchange: fp32 (exact mean of the ranks' gradients) or bf16 (half the bytes; default of
+        # the bf16 training path, whose operands are rounded to bf16 anyway)
+        self.grad_comm_dtype = grad_comm_dtype or ("bf16" if precision == "bf16" else "fp32")
+        if self.grad_comm_dtype not in ("fp32", "bf16"):
+            raise ValueError("grad_comm_dtype must be 'fp32' or 'bf16', got %r" % (grad_comm_dtype,))
+        self._grads16 = None
         layers = model_or_layers if isinstance(model_or_layers, list) else layers_from_module(model_or_layers)
         self.net = B200Net(layers, sequence_length, perm=perm, device=device)
         self._lib = self.net._lib
@@ -114,16 +120,38 @@ class B200Trainer(object):
             return
         avg = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else dist.ReduceOp.SUM
         div = None if avg == dist.ReduceOp.AVG else dist.get_world_size()
-        if overlap and self._tail_event is not None:
+        half = self.grad_comm_dtype == "bf16"
+        if half and self._grads16 is None:
+            self._grads16 = torch.empty((self.n_params,), dtype=torch.bfloat16, device=self.device)
+
+        def reduce(lo, hi, **kw):
+            """all-reduce of grads[lo:hi] on the current stream, through the bf16 copy if configured"""
+            if not half:
+                return dist.all_reduce(self.grads[lo:hi], op=avg, **kw)
+            # slices start at multiples of 4 elements or at a cudaMalloc'd base: the casts' alignment holds
+            _lib.check(self._lib.sb_cast_f32_to_bf16(_lib.ptr(self.grads[lo:hi]), hi - lo, _lib.ptr(self._grads16[lo:hi]),
+                                                     _lib.stream_ptr()), "sb_cast_f32_to_bf16")
+            return dist.all_reduce(self._grads16[lo:hi], op=avg, **kw)
+
+        def widen(lo, hi):
+            if half:
+                _lib.check(self._lib.sb_cast_bf16_to_f32(_lib.ptr(self._grads16[lo:hi]), hi - lo, _lib.ptr(self.grads[lo:hi]),
+                                                         _lib.stream_ptr()), "sb_cast_bf16_to_f32")
+
+        n = self.n_params
+        if overlap and self._tail_event is not None and self._tail_off % 4 == 0:
             cur = torch.cuda.current_stream()
             self._comm_stream.wait_event(self._tail_event)
             with torch.cuda.stream(self._comm_stream):
-                tail = dist.all_reduce(self.grads[self._tail_off:], op=avg, async_op=True)
-            dist.all_reduce(self.grads[:self._tail_off], op=avg)
-            tail.wait()                                   # the current stream waits for the side-stream reduction
-            cur.wait_stream(self._comm_stream)
+                tail = reduce(self._tail_off, n, async_op=True)
+                tail.wait()
+                widen(self._tail_off, n)
+            reduce(0, self._tail_off)
+            widen(0, self._tail_off)
+            cur.wait_stream(self._comm_stream)            # the current stream waits for the side-stream reduction
         else:
-            dist.all_reduce(self.grads, op=avg)
+            reduce(0, n)
+            widen(0, n)
         if div:
             self.grads.div_(div)
 
