@@ -51,7 +51,8 @@ static inline int sb_ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) /
 
 // Global launch counter (bench.py reports gpu_launches from it).
 extern unsigned long long g_sb_launches;
-#define SB_COUNT_LAUNCH() (++g_sb_launches)
+// writer threads launch format kernels concurrently with the caller's thread: the count is atomic
+#define SB_COUNT_LAUNCH() ((void)__atomic_fetch_add(&g_sb_launches, 1ull, __ATOMIC_RELAXED))
 
 // Cached device properties.
 int sb_sm_count(int device);

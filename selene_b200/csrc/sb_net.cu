@@ -1104,7 +1104,7 @@ int run_lstm(sb_net* net, const NetLayer& N, const void* act_in, void* act_out, 
     for (auto& e : net->lstm_graphs)
         if (memcmp(&e.key, &key, sizeof(key)) == 0) {
             SB_CHECK_CUDA(cudaGraphLaunch(e.exec, stream));
-            g_sb_launches += e.n_launches;
+            (void)__atomic_fetch_add(&g_sb_launches, (unsigned long long)e.n_launches, __ATOMIC_RELAXED);
             return SB_OK;
         }
     // warm the lazily initialised pieces (function attributes, driver entry point) outside the capture
