@@ -59,10 +59,13 @@ struct TcParams {
     SbScoreEpilogue sc;
 };
 
-__device__ __forceinline__ float tc_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+// The fused epilogue belongs to the bf16 path (gate 2e-2 on sigmoid outputs): exp / log / divide are the hardware
+// approximations (ex2 / lg2 / rcp, relative error ~1e-7), a third of the instructions of the library routines that the
+// fp32 path's score_kernel keeps (the epilogue of fc2 is instruction-bound: 4 warps finish 128 x 240 values per tile)
+__device__ __forceinline__ float tc_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 // logit_score_handler.py:118-124: clamp, then scipy.special.logit in float32
 __device__ __forceinline__ float tc_clamp(float p) { return p == 0.f ? 1e-24f : (p >= 1.f ? 0.999999f : p); }
-__device__ __forceinline__ float tc_logit(float p) { return logf(p / (1.f - p)); }
+__device__ __forceinline__ float tc_logit(float p) { return __logf(__fdividef(p, 1.f - p)); }
 
 // one (ref, alt) probability pair -> the requested score arrays at flat index `idx`
 __device__ __forceinline__ void tc_store_scores(const SbScoreEpilogue& sc, long long idx, float ref, float alt,
