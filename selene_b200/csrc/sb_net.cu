@@ -1272,7 +1272,15 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
             // conv layers: im2col tensor map (valid window starts only) -> overlapping-stride view -> per-tap boxes,
             // each the fallback of the one before if the driver refuses the tensor map
             bool per_tap = net->force_per_tap && N.type == SB_LAYER_CONV;
+            // im2col pays when the rows it drops outweigh the K padding of per-tap chunks (channels rounded up to 64 per
+            // tap): DeepSEA conv2 240/248 rows, conv3 53/60 rows x 512/480 K.  Long narrow layers (HeartENN 60 channels,
+            // 986/993 rows) lose 4 % with it and keep the overlapping view (r02 sweep, same GPU back to back)
             bool im2col = N.type == SB_LAYER_CONV && N.k > 1 && N.wb_tap && !net->no_im2col;
+            if (im2col) {
+                const double rows_ratio = (double)((N.t_conv / N.pool) * N.pool) / (double)N.pitch_in;
+                const double k_ratio = (double)N.k_full_tap / (double)round_up(N.k_full, 64);
+                im2col = rows_ratio * k_ratio <= 0.975;
+            }
             int rc = SB_OK;
             for (int attempt = 0; attempt < 3; ++attempt) {
                 T.im2col = 0;
