@@ -880,8 +880,22 @@ long long chunk_for(const sb_net* net, int precision, bool generic) {
     long long c = generic ? 256 : chunk_rows(precision);
     // first conv one chunk ahead (conv1_ahead): smaller chunks leave less of it exposed at the start of a call
     if (!generic && precision == SB_PREC_BF16 && net->layers[0].w1m_packed && !net->strand_mode && !net->has_lstm &&
-        !getenv("SB_CHUNK"))
+        !getenv("SB_CHUNK")) {
+        // ... and sized so that the first FC layer (few, long-K tiles) fills the SMs exactly: 128 rows x (SMs / its N tiles),
+        // DeepSEA on 148 SMs: 37 x 128 = 4736 rows = 148 fc1 tiles, 120 conv2 and 53 conv3 tiles per SM
         c = 4096;
+        for (const NetLayer& N : net->layers)
+            if (N.type == SB_LAYER_FC && N.n_tiles_n > 0) {
+                const long long per = sb_sm_count(net->device) / N.n_tiles_n;
+                if (per > 0) {
+                    long long cc = per * 128;
+                    while (cc < 3072) cc *= 2;
+                    while (cc > 6144 && cc % 256 == 0) cc /= 2;
+                    c = cc;
+                }
+                break;
+            }
+    }
     if (net->has_lstm) {  // chunks must hold whole recurrence blocks
         const long long blk = (long long)net->rec_group * net->rec_interleave;
         long long cap = 2048;
