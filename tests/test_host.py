@@ -225,3 +225,21 @@ def test_count_unknown_host_prefix():
         inner = seq[max(s, 0):min(e, len(seq))]
         exp = sum(ch not in "ACGTacgt" for ch in inner) + max(0, -s) + max(0, e - len(seq))
         assert G.count_unknown("chr1", s, e) == exp
+
+
+def test_hdf5_writer_or_clear_import_error(tmp_path):
+    """handler.py:205-218: dataset ``data`` float64 (n, F).  With h5py the file is written and read back; without it
+    (this image) ``output_format='hdf5'`` must fail with an ImportError that names the package, not crash later."""
+    from selene_b200.predict._writers import write_hdf5
+    data = np.arange(12, dtype=np.float32).reshape(3, 4) / 7
+    path = str(tmp_path / "scores.h5")
+    try:
+        import h5py
+    except ImportError:
+        with pytest.raises(ImportError, match="h5py"):
+            write_hdf5(path, data)
+        return
+    write_hdf5(path, data)
+    with h5py.File(path, "r") as fh:
+        got = fh["data"][()]
+    assert got.dtype == np.float64 and np.array_equal(got, data.astype(np.float64))
