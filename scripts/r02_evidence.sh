@@ -9,7 +9,7 @@ SMALL="python bench.py --steps 2 --warmup 1 --no-cpu --no-hbm --no-train --stron
 $SMALL > gpurun_out/ncu_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $SMALL > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches exit $?"
-ncu --set full --clock-control none --import-source on -k regex:'tc_layer|conv1_mma' -s 5 -c 10 -o gpurun_out/prof_tc -f $SMALL > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'tc_layer|conv1_mma' -s 5 -c 12 -o gpurun_out/prof_tc -f $SMALL > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit $?"
 python scripts/prof_hbm.py --ncu > gpurun_out/prof_hbm_plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:'window_kernel|label_bins|ism_expand' -c 16 -o gpurun_out/prof_hbm -f python scripts/prof_hbm.py --ncu > gpurun_out/ncu_hbm.log 2>&1

@@ -552,6 +552,69 @@ def test_long_first_conv_wide_pool_vs_torch(torch, taps, pool, cout, L):
 
 
 # ------------------------------------------------------------------------------------------------
+# first conv with <= 8 taps and pool 4 on register accumulators (sb_conv1m.cu), odd shapes; and the same net over
+# several chunks, where the first conv of chunk k+1 runs on a side stream next to the tcgen05 layers of chunk k
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("taps,cout,L", [(8, 320, 1000), (5, 100, 997), (3, 8, 64), (8, 81, 203), (1, 160, 40), (7, 640, 131)])
+def test_pool4_first_conv_register_accumulators_vs_torch(torch, taps, cout, L):
+    import torch.nn as nn
+    from selene_b200.nets import B200Net, layers_from_module
+    torch.manual_seed(taps * 1000 + cout)
+    t_pool = (L - taps + 1) // 4
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv_net = nn.Sequential(nn.Conv1d(4, cout, taps), nn.ReLU(inplace=True), nn.MaxPool1d(4, 4))
+            self.classifier = nn.Sequential(nn.Linear(cout * t_pool, 24), nn.Sigmoid())
+
+        def forward(self, x):
+            o = self.conv_net(x)
+            return self.classifier(o.reshape(o.size(0), -1))
+    model = Net().eval()
+    with torch.no_grad():
+        model.classifier[0].weight.mul_(0.2)
+    codes = _rand_codes(11, L, taps + cout, p_unk=0.05)
+    with torch.no_grad():
+        exp = model(torch.tensor(_onehot(codes)).transpose(1, 2)).numpy()
+    net = B200Net(layers_from_module(model), L)
+    dev_codes = torch.from_numpy(codes).cuda()
+    got = net.forward_codes(dev_codes, precision="bf16").cpu().numpy()
+    assert np.abs(got - exp).max() <= 2e-2, np.abs(got - exp).max()
+    assert np.corrcoef(got.ravel(), exp.ravel())[0, 1] > 0.999
+    # substituted rows (first / last / unknown base) through a row map
+    src = torch.tensor([0, 1, 2, 3, 3], dtype=torch.int32).cuda()
+    pos = torch.tensor([0, L - 1, L // 2, min(taps, L - 1), 7 % L], dtype=torch.int32).cuda()
+    sub = torch.tensor([3, 0, 4, 1, 2], dtype=torch.uint8).cuda()
+    rows = codes[[0, 1, 2, 3, 3]].copy()
+    rows[np.arange(5), pos.cpu().numpy()] = sub.cpu().numpy()
+    with torch.no_grad():
+        exp_rows = model(torch.tensor(_onehot(rows)).transpose(1, 2)).numpy()
+    got = net.forward_codes(dev_codes, src, pos, sub, n=5, precision="bf16").cpu().numpy()
+    assert np.abs(got - exp_rows).max() <= 2e-2
+
+
+def test_first_conv_one_chunk_ahead_equals_single_stream(torch, deepsea, monkeypatch):
+    """More rows than one chunk: the side-stream pipeline (first conv of chunk k+1 during the other layers of chunk k,
+    two extra buffers) must give bit-identical predictions to the same kernels run chunk by chunk on one stream."""
+    from selene_b200.nets import B200Net
+    monkeypatch.setenv("SB_CHUNK", "512")
+    layers, _ = deepsea
+    net = B200Net(layers, 1000)
+    n = 512 * 3 + 77
+    codes = torch.from_numpy(_rand_codes(64, 1000, 5)).cuda()
+    src = torch.from_numpy(np.random.default_rng(1).integers(0, 64, n).astype(np.int32)).cuda()
+    pos = torch.from_numpy(np.random.default_rng(2).integers(0, 1000, n).astype(np.int32)).cuda()
+    sub = torch.from_numpy(np.random.default_rng(3).integers(0, 5, n).astype(np.uint8)).cuda()
+    ahead = net.forward_codes(codes, src, pos, sub, n=n, precision="bf16").cpu().numpy()
+    again = net.forward_codes(codes, src, pos, sub, n=n, precision="bf16").cpu().numpy()
+    monkeypatch.setenv("SB_CONV1_AHEAD", "0")
+    plain = net.forward_codes(codes, src, pos, sub, n=n, precision="bf16").cpu().numpy()
+    assert np.array_equal(ahead, again)
+    assert np.array_equal(ahead, plain)
+
+
+# ------------------------------------------------------------------------------------------------
 # NonStrandSpecific wrapper (SURVEY §8 f3): both strands through the network, mean / max of the outputs
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("mode", ["mean", "max"])
