@@ -87,6 +87,7 @@ struct sb_net {
     double flops_per_seq;
     bool force_per_tap;
     bool no_im2col;                  // SB_TC_IM2COL=0, or the driver refused an im2col tensor map
+    bool no_im2col_run;              // SB_TC_IM2COL=1 (per-tap maps only), or the driver refused the run-view map
     int rec_group, rec_interleave;   // row grouping of BiLSTM recurrences (sb_net_set_recurrence)
     int strand_mode;                 // 0: plain; 1 / 2: NonStrandSpecific mean / max (sb_net_set_strand_mode)
     bool has_lstm;
@@ -526,6 +527,7 @@ extern "C" int sb_net_create(const sb_layer* layers, int n_layers, int L, const 
     {
         const char* e2 = getenv("SB_TC_IM2COL");
         net->no_im2col = e2 && e2[0] == '0';
+        net->no_im2col_run = e2 && e2[0] == '1';
     }
     const char* env = getenv("SB_TC_PER_TAP");
     net->force_per_tap = env && env[0] == '1';
@@ -1283,22 +1285,27 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
             T.out_f32 = last ? (fused ? 2 : 1) : 0;
             T.out = last ? (void*)logits : act[cur ^ 1];
             T.out_ld = last ? ldl : N.out_ld_b;
-            // conv layers: im2col tensor map (valid window starts only) -> overlapping-stride view -> per-tap boxes,
-            // each the fallback of the one before if the driver refuses the tensor map
+            // conv layers: im2col tensor map over the run view (valid window starts only, no K padding) -> per-tap im2col
+            // map -> overlapping-stride view -> per-tap boxes, each the fallback of the one before if the driver refuses
+            // the tensor map.  The run view pays whenever rows are dropped (DeepSEA conv2 240 / 248, conv3 53 / 60); the
+            // per-tap map pads the channels to 64 per tap (conv3: 512 / 480), so it is only used where rows x K still
+            // shrinks; long narrow layers (HeartENN: 986 / 993 rows) keep the overlapping view (r02 sweep, same GPU)
             bool per_tap = net->force_per_tap && N.type == SB_LAYER_CONV;
-            // im2col pays when the rows it drops outweigh the K padding of per-tap chunks (channels rounded up to 64 per
-            // tap): DeepSEA conv2 240/248 rows, conv3 53/60 rows x 512/480 K.  Long narrow layers (HeartENN 60 channels,
-            // 986/993 rows) lose 4 % with it and keep the overlapping view (r02 sweep, same GPU back to back)
-            bool im2col = N.type == SB_LAYER_CONV && N.k > 1 && N.wb_tap && !net->no_im2col;
-            if (im2col) {
+            int im2col = 0;
+            if (N.type == SB_LAYER_CONV && N.k > 1 && !net->no_im2col) {
                 const double rows_ratio = (double)((N.t_conv / N.pool) * N.pool) / (double)N.pitch_in;
-                const double k_ratio = (double)N.k_full_tap / (double)round_up(N.k_full, 64);
-                im2col = rows_ratio * k_ratio <= 0.975;
+                if (!net->no_im2col_run && rows_ratio <= 0.985) im2col = 2;
+                else if (N.wb_tap) {
+                    const double k_ratio = (double)N.k_full_tap / (double)round_up(N.k_full, 64);
+                    if (rows_ratio * k_ratio <= 0.975) im2col = 1;
+                }
             }
             int rc = SB_OK;
-            for (int attempt = 0; attempt < 3; ++attempt) {
+            for (int attempt = 0; attempt < 4; ++attempt) {
                 T.im2col = 0;
-                if (im2col) {
+                if (im2col == 2) {
+                    T.per_tap = 0; T.im2col = 2; T.taps = N.k; T.w = N.wb; T.w_ld = N.w_ld; T.k_full = N.k_full;
+                } else if (im2col == 1) {
                     T.per_tap = 1; T.im2col = 1; T.taps = N.k; T.w = N.wb_tap; T.w_ld = N.w_ld_tap; T.k_full = N.k_full_tap;
                 } else if (per_tap) {
                     T.per_tap = 1; T.taps = N.k; T.w = N.wb_tap; T.w_ld = N.w_ld_tap; T.k_full = N.k_full_tap;
@@ -1307,7 +1314,8 @@ int run_chunk(sb_net* net, const RowSource& in, long long r0, long long m, int p
                 }
                 rc = sb_tc_launch(T, dev, stream, last ? fused : nullptr);
                 if (rc == SB_OK || N.type != SB_LAYER_CONV) break;
-                if (im2col) { im2col = false; net->no_im2col = true; continue; }
+                if (im2col == 2) { net->no_im2col_run = true; im2col = N.wb_tap ? 1 : 0; continue; }
+                if (im2col == 1) { im2col = 0; net->no_im2col = true; continue; }
                 if (per_tap) break;
                 per_tap = true;            // overlapping-stride tensor map refused: fall back to per-tap boxes
                 net->force_per_tap = true;

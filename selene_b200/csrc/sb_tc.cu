@@ -141,7 +141,12 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     uint8_t* sa = smem + stage * p.stage_bytes;
                     uint8_t* sb = sa + kABytes;
                     sb_mbar_expect_tx(&full_bar[stage], tx_bytes);
-                    if (p.im2col) {
+                    if (p.im2col == 2) {
+                        // im2col over the RUN view: a window start's "channels" are its whole taps x C run (the next
+                        // positions' rows follow contiguously), so a k-block is 64 elements of that run: no per-tap padding
+                        const int n = m0 / p.v_pix;
+                        sb_tma_load_im2col_3d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0 - n * p.v_pix, n, (uint16_t)0);
+                    } else if (p.im2col) {
                         // 128 window starts from (position w, sequence n) on, read at position + tap
                         const int tap = kb / p.chunks_per_tap;
                         const int n = m0 / p.v_pix;
@@ -472,7 +477,14 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbSc
     int chunks_per_tap = 0;
     const int v_pix = (L.t_conv / L.pool) * L.pool;      // window starts that feed a pooled output
     long long rows_m = L.rows_a;                         // rows of the M axis
-    if (L.per_tap && L.im2col) {
+    if (!L.per_tap && L.im2col == 2) {
+        // run view: every window start owns k_full "channels" (its taps x C run, overlapping the next positions' rows)
+        SB_REQUIRE(L.rows_a % L.t_in == 0 && v_pix > 0 && L.t_in - v_pix < 32768,
+                   "sb_tc_launch: im2col needs whole sequences (rows %lld, t_in %d)", (long long)L.rows_a, L.t_in);
+        const long long n_seq = L.rows_a / L.t_in;
+        rc = make_tmap_im2col(&tm_a, L.a, (uint64_t)L.k_full, (uint64_t)L.a_ld, (uint64_t)L.t_in, (uint64_t)n_seq, v_pix);
+        rows_m = n_seq * v_pix;
+    } else if (L.per_tap && L.im2col) {
         chunks_per_tap = (L.a_ld + kBlockK - 1) / kBlockK;
         SB_REQUIRE(L.k_full == L.taps * chunks_per_tap * kBlockK, "sb_tc_launch: per-tap k_full mismatch");
         SB_REQUIRE(L.rows_a % L.t_in == 0 && v_pix > 0 && L.t_in - v_pix < 32768 && L.taps <= 65535,
@@ -497,12 +509,12 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbSc
 
     TcParams p;
     p.rows_a = rows_m;
-    p.im2col = L.per_tap && L.im2col;
+    p.im2col = (L.per_tap && L.im2col) ? 1 : ((!L.per_tap && L.im2col == 2) ? 2 : 0);
     p.v_pix = v_pix;
     p.last_k16 = kBlockK / 16;
     {
         const char* e = getenv("SB_TC_SKIPK");
-        if (e && e[0] == '1' && p.im2col) p.last_k16 = (L.a_ld - (chunks_per_tap - 1) * kBlockK + 15) / 16;
+        if (e && e[0] == '1' && p.im2col == 1) p.last_k16 = (L.a_ld - (chunks_per_tap - 1) * kBlockK + 15) / 16;
     }
     p.t_in = L.t_in;
     p.t_conv = L.t_conv;

@@ -20,7 +20,9 @@ struct SbTcLayer {
                          // 1: one 2-D box per (tap, 64-channel chunk); the weight K axis is then
                          //    taps x (chunks_per_tap*64) with zero padding, k_full = that product
     int taps;            // only used when per_tap
-    int im2col;          // with per_tap: A is fetched through an IM2COL tensor map (channels, position, sequence) whose
+    int im2col;          // 2 (without per_tap): the same map over the RUN view — a window start's channel axis is its whole
+                         // taps x C run, k-blocks are 64 elements of it (no per-tap channel padding).
+                         // 1 with per_tap: A is fetched through an IM2COL tensor map (channels, position, sequence) whose
                          // pixel bounding box holds only the pool * t_pool valid window starts of every sequence, so an
                          // M tile is 128 VALID rows (it walks across sequence boundaries) and no MMA row is wasted on
                          // windows that straddle two sequences
