@@ -150,6 +150,57 @@ __device__ __forceinline__ void sb_tma_load_im2col_3d(void* smem_dst, const void
         : "memory");
 }
 
+// ---- CTA pairs (cta_group::2): the variants CUTLASS uses in cute/arch/copy_sm100_tma.hpp, mma_sm100_umma.hpp,
+// tmem_allocator_sm100.hpp and cutlass/arch/barrier.h.  A shared::cta address of CTA 1 with bit 24 cleared names the same
+// location in CTA 0 (the leader), which owns the "full" barriers of the pair.
+constexpr uint32_t kSbPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void sb_tma_load_2d_pair(void* smem_dst, const void* tmap, uint64_t* leader_bar, int32_t c0, int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        :
+        : "r"(sb_smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(sb_smem_u32(leader_bar) & kSbPeerBitMask),
+          "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void sb_tma_load_im2col_3d_pair(void* smem_dst, const void* tmap, uint64_t* leader_bar, int32_t c,
+                                                           int32_t w, int32_t n, uint16_t w_off) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2], {%6};"
+        :
+        : "r"(sb_smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(sb_smem_u32(leader_bar) & kSbPeerBitMask),
+          "r"(c), "r"(w), "r"(n), "h"(w_off)
+        : "memory");
+}
+__device__ __forceinline__ void sb_tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {  // one warp of EACH CTA of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sb_smem_u32(smem_dst)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void sb_tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs, 128 rows each] (+)= [A of CTA 0; A of CTA 1] * [B half of CTA 0 | B half of CTA 1]; leader thread only
+__device__ __forceinline__ void sb_umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+// arrive on `bar` (same offset) in BOTH CTAs once all previously issued MMAs of the pair have completed
+__device__ __forceinline__ void sb_umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     sb_smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
 // --- tcgen05 / TMEM -------------------------------------------------------------------------
 __device__ __forceinline__ void sb_tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {  // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(

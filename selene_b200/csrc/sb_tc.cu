@@ -86,6 +86,10 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// PAIR: two CTAs of a cluster (one TPC) work on one 256-row M tile with cta_group::2 MMAs: each CTA loads its own 128
+// rows of A and HALF of the B tile, the leader (cluster rank 0) issues the MMAs for both, every CTA drains its own 128
+// accumulator lanes.  Per k-block a CTA then pulls 16 KB + N x 64 B instead of 16 KB + N x 128 B from L2.
+template <bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                 const TcParams p) {
@@ -101,8 +105,14 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int tiles_mn = p.n_tiles_m * p.n_tiles_n;
+    const int tiles_mn = p.n_tiles_m * p.n_tiles_n;      // PAIR: n_tiles_m counts 256-row tiles
     const int num_tiles = tiles_mn * p.k_splits;
+    const uint32_t rank = PAIR ? sb_cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int m_rows_tile = PAIR ? 2 * kBlockM : kBlockM;
+    const int b_rows = PAIR ? p.block_n / 2 : p.block_n;       // B rows this CTA loads
 
     if (warp == 0 && lane == 0) {
         sb_prefetch_tmap(&tmap_a);
@@ -115,13 +125,17 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         }
         for (int i = 0; i < 2; ++i) {
             sb_mbar_init(&tfull_bar[i], 1);
-            sb_mbar_init(&tempty_bar[i], 128);
+            sb_mbar_init(&tempty_bar[i], PAIR ? 256 : 128);    // PAIR: the epilogue threads of both CTAs arrive at the leader's
         }
         sb_fence_mbar_init();
     }
-    if (warp == 2) sb_tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (warp == 2) {
+        if (PAIR) sb_tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols);
+        else sb_tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    }
     sb_tc_fence_before();
-    __syncthreads();
+    if (PAIR) sb_cluster_sync();
+    else __syncthreads();
     sb_tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -129,37 +143,47 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            const uint32_t tx_bytes = kABytes + (uint32_t)p.block_n * kBlockK * 2;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const uint32_t tx_bytes = (kABytes + (uint32_t)b_rows * kBlockK * 2) * (PAIR ? 2u : 1u);   // PAIR: both CTAs' bytes
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 const int mn = tile % tiles_mn;
-                const int m0 = (mn / p.n_tiles_n) * kBlockM;
-                const int n0 = (mn % p.n_tiles_n) * p.block_n;
+                const int m0 = (mn / p.n_tiles_n) * m_rows_tile + (int)rank * kBlockM;
+                const int n0 = (mn % p.n_tiles_n) * p.block_n + (int)rank * b_rows;
+                // PAIR: the second half of the last 256-row tile may lie wholly past the rows; it then loads tile 0 (its
+                // accumulators are never stored)
+                const int m0_real = m0;
+                const int m0_ld = (PAIR && (long long)m0_real >= p.rows_a) ? 0 : m0_real;
                 const int kb0 = (tile / tiles_mn) * p.kb_per_split;
                 const int kb1 = kb0 + p.kb_per_split < p.num_k_blocks ? kb0 + p.kb_per_split : p.num_k_blocks;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     sb_mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * p.stage_bytes;
                     uint8_t* sb = sa + kABytes;
-                    sb_mbar_expect_tx(&full_bar[stage], tx_bytes);
+                    // PAIR: every load of either CTA completes on the LEADER's barrier, which expects both CTAs' bytes
+                    if (leader) sb_mbar_expect_tx(&full_bar[stage], tx_bytes);
                     if (p.im2col == 2) {
                         // im2col over the RUN view: a window start's "channels" are its whole taps x C run (the next
                         // positions' rows follow contiguously), so a k-block is 64 elements of that run: no per-tap padding
-                        const int n = m0 / p.v_pix;
-                        sb_tma_load_im2col_3d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0 - n * p.v_pix, n, (uint16_t)0);
+                        const int n = m0_ld / p.v_pix;
+                        if (PAIR) sb_tma_load_im2col_3d_pair(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0_ld - n * p.v_pix, n, (uint16_t)0);
+                        else sb_tma_load_im2col_3d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0_ld - n * p.v_pix, n, (uint16_t)0);
                     } else if (p.im2col) {
                         // 128 window starts from (position w, sequence n) on, read at position + tap
                         const int tap = kb / p.chunks_per_tap;
-                        const int n = m0 / p.v_pix;
-                        sb_tma_load_im2col_3d(sa, &tmap_a, &full_bar[stage], (kb - tap * p.chunks_per_tap) * kBlockK,
-                                              m0 - n * p.v_pix, n, (uint16_t)tap);
+                        const int n = m0_ld / p.v_pix;
+                        if (PAIR) sb_tma_load_im2col_3d_pair(sa, &tmap_a, &full_bar[stage], (kb - tap * p.chunks_per_tap) * kBlockK,
+                                                             m0_ld - n * p.v_pix, n, (uint16_t)tap);
+                        else sb_tma_load_im2col_3d(sa, &tmap_a, &full_bar[stage], (kb - tap * p.chunks_per_tap) * kBlockK,
+                                                   m0_ld - n * p.v_pix, n, (uint16_t)tap);
                     } else if (p.chunks_per_tap > 0) {
                         const int tap = kb / p.chunks_per_tap;
-                        sb_tma_load_2d(sa, &tmap_a, &full_bar[stage],
-                                       (kb - tap * p.chunks_per_tap) * kBlockK, m0 + tap);
+                        if (PAIR) sb_tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], (kb - tap * p.chunks_per_tap) * kBlockK, m0_ld + tap);
+                        else sb_tma_load_2d(sa, &tmap_a, &full_bar[stage], (kb - tap * p.chunks_per_tap) * kBlockK, m0_ld + tap);
                     } else {
-                        sb_tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0);
+                        if (PAIR) sb_tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0_ld);
+                        else sb_tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0_ld);
                     }
-                    sb_tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBlockK, n0);
+                    if (PAIR) sb_tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], kb * kBlockK, n0);
+                    else sb_tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * kBlockK, n0);
                     if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -167,13 +191,14 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = sb_umma_idesc_bf16(kBlockM, (uint32_t)p.block_n);
+        if (lane == 0 && leader) {
+            const uint32_t idesc = sb_umma_idesc_bf16((uint32_t)m_rows_tile, (uint32_t)p.block_n);
             uint32_t stage = 0, phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
                 const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-                sb_mbar_wait(&tempty_bar[as], aphase ^ 1);
+                if (PAIR) sb_mbar_wait_cluster(&tempty_bar[as], aphase ^ 1);     // arrivals come from both CTAs
+                else sb_mbar_wait(&tempty_bar[as], aphase ^ 1);
                 sb_tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * p.acc_stride;
                 const int kb0 = (tile / tiles_mn) * p.kb_per_split;
@@ -192,13 +217,20 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     if (p.last_k16 < nk && (kb + 1) % p.chunks_per_tap == 0) nk = p.last_k16;
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k)
-                        if (k < nk)
-                            sb_umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                         (kb > kb0 || k > 0) ? 1u : 0u);
-                    sb_umma_commit(&empty_bar[stage]);  // frees the smem stage when the MMAs finish
+                        if (k < nk) {
+                            if (PAIR) sb_umma_bf16_pair(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                                        (kb > kb0 || k > 0) ? 1u : 0u);
+                            else sb_umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                              (kb > kb0 || k > 0) ? 1u : 0u);
+                        }
+                    // frees the smem stage (of both CTAs) when the MMAs finish
+                    if (PAIR) sb_umma_commit_pair(&empty_bar[stage]);
+                    else sb_umma_commit(&empty_bar[stage]);
                     if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                 }
-                sb_umma_commit(&tfull_bar[as]);  // accumulator complete
+                // accumulator complete (in both CTAs)
+                if (PAIR) sb_umma_commit_pair(&tfull_bar[as]);
+                else sb_umma_commit(&tfull_bar[as]);
             }
         }
         __syncwarp();
@@ -208,10 +240,10 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         const int row_in_tile = quad * 32 + lane;
         const int et = threadIdx.x - 64;            // 0..127
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = tile0; tile < num_tiles; tile += tile_step, ++it) {
             const uint32_t as = it & 1, aphase = (it >> 1) & 1;
             const int mn = tile % tiles_mn;
-            const int m0 = (mn / p.n_tiles_n) * kBlockM;
+            const int m0 = (mn / p.n_tiles_n) * m_rows_tile + (int)rank * kBlockM;
             const int n0 = (mn % p.n_tiles_n) * p.block_n;
             float* bs = bias_s + as * kMaxN;
             for (int i = et; i < p.block_n; i += 128) bs[i] = __ldg(p.bias + n0 + i);
@@ -351,15 +383,19 @@ tc_layer_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 }
             }
             sb_tc_fence_before();
-            sb_mbar_arrive(&tempty_bar[as]);  // 128 arrivals hand the accumulator back to the MMA warp
+            // 128 arrivals (PAIR: 256, at the leader's barrier) hand the accumulator back to the MMA warp
+            if (PAIR) sb_mbar_arrive_cluster(sb_mapa(sb_smem_u32(&tempty_bar[as]), 0u));
+            else sb_mbar_arrive(&tempty_bar[as]);
         }
     }
 
     sb_tc_fence_before();
-    __syncthreads();
+    if (PAIR) sb_cluster_sync();
+    else __syncthreads();
     if (warp == 2) {
         sb_tc_fence_after();
-        sb_tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+        if (PAIR) sb_tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
+        else sb_tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
 }
 
@@ -503,8 +539,14 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbSc
         rc = make_tmap(&tm_a, L.a, (uint64_t)L.k_full, (uint64_t)rows_tma, (uint64_t)L.a_ld, kBlockK, kBlockM);
     }
     if (rc != SB_OK) return rc;
+    // CTA pairs (SB_TC_PAIR=0 switches them off): 256-row tiles, each CTA loads half of the B tile
+    const char* narrow_env = getenv("SB_TC_NARROW");
+    const bool narrow = L.block_n <= 128 && !(narrow_env && narrow_env[0] == '0');
+    const char* pair_env = getenv("SB_TC_PAIR");
+    const bool pair = !(pair_env && pair_env[0] == '0') && !narrow && L.block_n % 32 == 0 && L.out_f32 != 3 &&
+                      sb_sm_count(device) % 2 == 0;
     rc = make_tmap(&tm_b, L.w, (uint64_t)L.k_full, (uint64_t)L.n_rows_w, (uint64_t)L.w_ld, kBlockK,
-                   (uint32_t)L.block_n);
+                   (uint32_t)(pair ? L.block_n / 2 : L.block_n));
     if (rc != SB_OK) return rc;
 
     TcParams p;
@@ -526,18 +568,16 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbSc
     p.out_f32 = L.out_f32;
     p.block_n = L.block_n;
     p.n_tiles_n = L.n_tiles_n;
-    p.n_tiles_m = (int)((rows_m + kBlockM - 1) / kBlockM);
+    p.n_tiles_m = pair ? (int)((rows_m + 2 * kBlockM - 1) / (2 * kBlockM)) : (int)((rows_m + kBlockM - 1) / kBlockM);
     p.num_k_blocks = (L.k_full + kBlockK - 1) / kBlockK;
     p.chunks_per_tap = chunks_per_tap;
     p.k_splits = (L.out_f32 == 3 && L.k_splits > 1) ? (L.k_splits < p.num_k_blocks ? L.k_splits : p.num_k_blocks) : 1;
     p.kb_per_split = (p.num_k_blocks + p.k_splits - 1) / p.k_splits;
     p.k_splits = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;     // no empty range
-    const char* narrow_env = getenv("SB_TC_NARROW");
-    const bool narrow = L.block_n <= 128 && !(narrow_env && narrow_env[0] == '0');
     p.ring_bytes = narrow ? kRingBytes / 2 : kRingBytes;
     p.tmem_cols = narrow ? 256 : kTmemCols;
     p.acc_stride = narrow ? 128 : kMaxN;
-    p.stage_bytes = kABytes + L.block_n * kBlockK * 2;
+    p.stage_bytes = kABytes + (pair ? L.block_n / 2 : L.block_n) * kBlockK * 2;
     p.stages = p.ring_bytes / p.stage_bytes;
     if (p.stages > kMaxStages) p.stages = kMaxStages;
     p.bias = L.bias;
@@ -547,19 +587,36 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbSc
 
     static bool attr_set = false;
     if (!attr_set) {
-        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kSmemBytes));
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         // narrow layers put two CTAs of ~103 KB on an SM: ask for the largest shared-memory carve-out
-        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+        SB_CHECK_CUDA(cudaFuncSetAttribute(tc_layer_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                            cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     const int64_t tiles = (int64_t)p.n_tiles_m * p.n_tiles_n * p.k_splits;
     const int sms = sb_sm_count(device);
-    const int ctas = narrow ? 2 * sms : sms;
-    const int grid = (int)(tiles < ctas ? tiles : ctas);
     const int smem_bytes = p.ring_bytes + kAuxBytes + 1024;
-    tc_layer_kernel<<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, p);
+    if (pair) {
+        int grid = (int)(2 * tiles < sms ? 2 * tiles : sms) & ~1;      // whole clusters of two CTAs
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = (size_t)smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attrs[1];
+        attrs[0].id = cudaLaunchAttributeClusterDimension;
+        attrs[0].val.clusterDim.x = 2;
+        attrs[0].val.clusterDim.y = 1;
+        attrs[0].val.clusterDim.z = 1;
+        cfg.attrs = attrs;
+        cfg.numAttrs = 1;
+        SB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, tc_layer_kernel<true>, tm_a, tm_b, p));
+    } else {
+        const int ctas = narrow ? 2 * sms : sms;
+        const int grid = (int)(tiles < ctas ? tiles : ctas);
+        tc_layer_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(tm_a, tm_b, p);
+    }
     SB_COUNT_LAUNCH();
     SB_CHECK_LAUNCH();
     return SB_OK;
