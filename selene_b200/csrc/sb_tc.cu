@@ -543,8 +543,17 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbSc
     const char* narrow_env = getenv("SB_TC_NARROW");
     const bool narrow = L.block_n <= 128 && !(narrow_env && narrow_env[0] == '0');
     const char* pair_env = getenv("SB_TC_PAIR");
-    const bool pair = !(pair_env && pair_env[0] == '0') && !narrow && L.block_n % 32 == 0 && L.out_f32 != 3 &&
-                      sb_sm_count(device) % 2 == 0;
+    bool pair = !(pair_env && pair_env[0] == '0') && !narrow && L.block_n % 16 == 0 && L.out_f32 != 3 &&
+                sb_sm_count(device) % 2 == 0;
+    if (pair && !(pair_env && pair_env[0] == '2')) {
+        // a pair does the work of two CTAs in the time of one tile, so what decides is the number of waves: a layer whose
+        // 128-row tiles fill the SMs exactly (DeepSEA fc1: 148 tiles) would need two half-empty waves of 256-row tiles
+        const long long sms = sb_sm_count(device);
+        const long long t1 = ((rows_m + kBlockM - 1) / kBlockM) * L.n_tiles_n;
+        const long long t2 = ((rows_m + 2 * kBlockM - 1) / (2 * kBlockM)) * L.n_tiles_n;
+        const long long w1 = (t1 + sms - 1) / sms, w2 = (t2 + sms / 2 - 1) / (sms / 2);
+        pair = w2 * 100 <= w1 * 103;
+    }
     rc = make_tmap(&tm_b, L.w, (uint64_t)L.k_full, (uint64_t)L.n_rows_w, (uint64_t)L.w_ld, kBlockK,
                    (uint32_t)(pair ? L.block_n / 2 : L.block_n));
     if (rc != SB_OK) return rc;
