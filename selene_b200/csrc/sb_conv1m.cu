@@ -36,7 +36,7 @@ struct Conv1mParams {
     const int32_t* sub_pos;
     const uint8_t* sub_code;
     long long row0, n_rows;
-    int L, t_pool, out_pitch, out_ld, relu, n_cg, units_per_seq, rows_async, row_bytes;
+    int L, t_pool, out_pitch, out_ld, relu, n_cg, units_per_seq, rows_async, row_bytes, dense_only;
     const uint32_t* bfrag;   // [n_cg][kNT][2 k-steps][2][32 lanes]
     const float* bias;       // [n_cg * 80]
     __nv_bfloat16* out;
@@ -48,6 +48,20 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t a0,
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
                  : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
+}
+
+// 2:4 structured-sparse A (one-hot input: exactly one of the four bases of a tap is set): A holds two values per group of
+// four K (here (1, 0) or (0, 1)), the metadata nibble of the group names their positions ((0,1) or (2,3)); K = 32 in ONE
+// instruction.  Layouts measured with scripts/probes/probe_mma_sp.cu: a0 / a1 = rows g / g+8 of group t, a2 / a3 of group
+// t + 4; metadata (selector 0) comes from lanes 4g and 4g+1: nibbles 0-3 = row g, groups 4s .. 4s+3, nibbles 4-7 = row g+8.
+__device__ __forceinline__ void mma_sp_bf16_16832(float (&d)[4], const uint32_t a0, const uint32_t a1, const uint32_t a2,
+                                                  const uint32_t a3, const uint32_t b0, const uint32_t b1, const uint32_t b2,
+                                                  const uint32_t b3, const uint32_t meta) {
+    asm volatile(
+        "mma.sp::ordered_metadata.sync.aligned.m16n8k32.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+        "{%8,%9,%10,%11}, {%12,%12,%12,%12}, %13, 0x0;"
+        : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3), "f"(0.f), "r"(meta));
 }
 
 // bf16 pair (base 2h, base 2h + 1) of the one-hot row of `code`; 4 (and anything above) is the unknown base
@@ -107,6 +121,10 @@ __global__ void __launch_bounds__(kWarps * 32, 2) conv1_mma_kernel(const Conv1mP
     extern __shared__ __align__(16) uint8_t rows_s[];
     uint8_t* rbuf0 = rows_s + (size_t)(2 * warp) * p.row_bytes;      // two buffers of row_bytes, back to back
     for (int i = lane * 4; i < 2 * p.row_bytes; i += 128) *reinterpret_cast<uint32_t*>(rbuf0 + i) = 0x04040404u;
+    // sparse-metadata nibble of every position of the current row (0x4: bases 0 / 1 -> slots (0,1); 0xE: bases 2 / 3 ->
+    // slots (2,3)), eight per word: a unit's metadata registers are then two shifts of one 32-bit window of this stream
+    const int mwords = p.row_bytes / 8 + 2;
+    uint32_t* mstream = reinterpret_cast<uint32_t*>(rows_s + (size_t)2 * kWarps * p.row_bytes) + (size_t)warp * mwords;
     __syncwarp();
 
     struct RowMeta { long long srow; int sp; uint32_t sc; };
@@ -149,52 +167,24 @@ __global__ void __launch_bounds__(kWarps * 32, 2) conv1_mma_kernel(const Conv1mP
         __syncwarp();
         if (lane == 0 && m0.sp >= 0 && m0.sp < p.L) cur[m0.sp] = (uint8_t)m0.sc;
         __syncwarp();
+        for (int wi = lane; wi < mwords - 2; wi += 32) {
+            const uint32_t c_lo = reinterpret_cast<const uint32_t*>(cur)[2 * wi], c_hi = reinterpret_cast<const uint32_t*>(cur)[2 * wi + 1];
+            const uint32_t z = ((c_lo >> 1) & 0x1u) | ((c_lo >> 5) & 0x10u) | ((c_lo >> 9) & 0x100u) | ((c_lo >> 13) & 0x1000u) |
+                               ((c_hi << 15) & 0x10000u) | ((c_hi << 11) & 0x100000u) | ((c_hi << 7) & 0x1000000u) |
+                               ((c_hi << 3) & 0x10000000u);
+            mstream[wi] = 0x44444444u + 10u * z;
+        }
+        __syncwarp();
         const uint32_t* cw = reinterpret_cast<const uint32_t*>(cur) + g;
         __nv_bfloat16* orow = p.out + (seq * p.out_pitch + g) * (long long)p.out_ld + ch0;
 #pragma unroll 1
         for (int u = 0; u < p.units_per_seq; ++u, cw += 8, orow += (long long)kUnitPooled * p.out_ld) {
         // this thread's ten codes: bytes 4g + th ... + 9 of the unit
         const uint32_t w0 = cw[0], w1 = cw[1], w2 = cw[2];
-        const uint32_t x0 = th ? __funnelshift_r(w0, w1, 8) : w0;    // bytes th .. th+3
-        const uint32_t x1 = th ? __funnelshift_r(w1, w2, 8) : w1;    // bytes th+4 .. th+7
-        const uint32_t x2 = th ? (w2 >> 8) : w2;                     // bytes th+8, th+9
-        uint32_t P[10];
-        if (__any_sync(0xffffffffu, ((w0 | w1 | w2) & 0xFCFCFCFCu) != 0u)) {
-            // an unknown base somewhere in the unit (rare): the general pattern
-#pragma unroll
-            for (int d = 0; d < 4; ++d) {
-                P[d] = pair_pattern((x0 >> (8 * d)) & 0xFFu, h);
-                P[4 + d] = pair_pattern((x1 >> (8 * d)) & 0xFFu, h);
-            }
-            P[8] = pair_pattern(x2 & 0xFFu, h);
-            P[9] = pair_pattern((x2 >> 8) & 0xFFu, h);
-        } else {
-            // codes 0..3: c' = code ^ 2h is 0 / 1 for this thread's base pair.  The bf16 pair is a byte permutation of
-            // 0x3F800000 (bytes 00 00 80 3F) with the selector 0x32 << 8 c': c' = 0 puts 1.0 in the low half, c' = 1 in the
-            // high half, c' >= 2 shifts the selector out of the 16 bits prmt reads (all bytes = byte 0 = zero)
-            const uint32_t hx = h * 0x02020202u;
-            const uint32_t y0 = ((x0 ^ hx) << 3) & 0x18181818u, y1 = ((x1 ^ hx) << 3) & 0x18181818u,
-                           y2 = ((x2 ^ hx) << 3) & 0x18181818u;
-#pragma unroll
-            for (int d = 0; d < 4; ++d) {
-                P[d] = prmt_sel(0x32u << ((y0 >> (8 * d)) & 31u));
-                P[4 + d] = prmt_sel(0x32u << ((y1 >> (8 * d)) & 31u));
-            }
-            P[8] = prmt_sel(0x32u << (y2 & 31u));
-            P[9] = prmt_sel(0x32u << ((y2 >> 8) & 31u));
-        }
-
         uint32_t o_lo[kNT / 2], o_hi[kNT / 2];
         float keep_lo = 0.f, keep_hi = 0.f;
-#pragma unroll
-        for (int j = 0; j < kNT; ++j) {
-            float X[4], Y[4];
-            // tile X: rows = positions 4g, 4g+1; tile Y: positions 4g+2, 4g+3.  k-step 0 = taps th, th+2; 1 = th+4, th+6
-            mma_bf16_16816(X, P[0], P[1], P[2], P[3], bw[j][0][0], bw[j][0][1], 0.f, 0.f, 0.f, 0.f);
-            mma_bf16_16816(Y, P[2], P[3], P[4], P[5], bw[j][0][0], bw[j][0][1], 0.f, 0.f, 0.f, 0.f);
-            mma_bf16_16816(X, P[4], P[5], P[6], P[7], bw[j][1][0], bw[j][1][1], X[0], X[1], X[2], X[3]);
-            mma_bf16_16816(Y, P[6], P[7], P[8], P[9], bw[j][1][0], bw[j][1][1], Y[0], Y[1], Y[2], Y[3]);
-            // max over the pool window, then bias + ReLU as max(m, -bias) + bias
+        // max over the pool window (tile X: positions 4g, 4g+1; tile Y: 4g+2, 4g+3), then bias + ReLU as max(m, -bias) + bias
+        auto finish = [&](int j, const float (&X)[4], const float (&Y)[4]) {
             const float bl = bias_lo[j], bh = bias_hi[j];
             const float lo = max3f(max3f(X[0], X[2], Y[0]), Y[2], RELU ? -bl : -INFINITY) + bl;     // column 2t
             const float hi = max3f(max3f(X[1], X[3], Y[1]), Y[3], RELU ? -bh : -INFINITY) + bh;     // column 2t + 1
@@ -204,6 +194,52 @@ __global__ void __launch_bounds__(kWarps * 32, 2) conv1_mma_kernel(const Conv1mP
             } else {
                 keep_lo = lo;
                 keep_hi = hi;
+            }
+        };
+        if (p.dense_only || __any_sync(0xffffffffu, ((w0 | w1 | w2) & 0xFCFCFCFCu) != 0u)) {
+            // an unknown base somewhere in the unit (rare): dense MMAs, general one-hot patterns (0.25 x 4 for the unknown)
+            const uint32_t x0 = th ? __funnelshift_r(w0, w1, 8) : w0;    // bytes th .. th+3
+            const uint32_t x1 = th ? __funnelshift_r(w1, w2, 8) : w1;    // bytes th+4 .. th+7
+            const uint32_t x2 = th ? (w2 >> 8) : w2;                     // bytes th+8, th+9
+            uint32_t P[10];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                P[d] = pair_pattern((x0 >> (8 * d)) & 0xFFu, h);
+                P[4 + d] = pair_pattern((x1 >> (8 * d)) & 0xFFu, h);
+            }
+            P[8] = pair_pattern(x2 & 0xFFu, h);
+            P[9] = pair_pattern((x2 >> 8) & 0xFFu, h);
+#pragma unroll
+            for (int j = 0; j < kNT; ++j) {
+                float X[4], Y[4];
+                // k-step 0 = taps th, th+2; 1 = th+4, th+6
+                mma_bf16_16816(X, P[0], P[1], P[2], P[3], bw[j][0][0], bw[j][0][1], 0.f, 0.f, 0.f, 0.f);
+                mma_bf16_16816(Y, P[2], P[3], P[4], P[5], bw[j][0][0], bw[j][0][1], 0.f, 0.f, 0.f, 0.f);
+                mma_bf16_16816(X, P[4], P[5], P[6], P[7], bw[j][1][0], bw[j][1][1], X[0], X[1], X[2], X[3]);
+                mma_bf16_16816(Y, P[6], P[7], P[8], P[9], bw[j][1][0], bw[j][1][1], Y[0], Y[1], Y[2], Y[3]);
+                finish(j, X, Y);
+            }
+        } else {
+            // codes 0..3: ONE sparse MMA per (tile, n-tile).  Value pairs of this thread's taps t and t + 4 at the tile rows:
+            // the codes at bytes 4g + t ... + 7 of the unit; the slot is the low bit of the code
+            const uint32_t x0 = __funnelshift_r(w0, w1, 8 * t), x1 = __funnelshift_r(w1, w2, 8 * t);
+            uint32_t V[8];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                V[d] = 0x3F80u << ((d == 0 ? (x0 << 4) : (x0 >> (8 * d - 4))) & 16u);
+                V[4 + d] = 0x3F80u << ((d == 0 ? (x1 << 4) : (x1 >> (8 * d - 4))) & 16u);
+            }
+            // metadata: nibbles of positions 4g + 4s ... of the unit (s = lane & 1; only lanes 4g and 4g + 1 are read)
+            const int hw = 8 * u + g + (t & 1);
+            const uint32_t win = __funnelshift_r(mstream[hw >> 1], mstream[(hw >> 1) + 1], 16 * (hw & 1));
+            const uint32_t eX = (win & 0xFFFFu) | ((win << 12) & 0xFFFF0000u);
+            const uint32_t eY = ((win >> 8) & 0xFFFFu) | ((win << 4) & 0xFFFF0000u);
+#pragma unroll
+            for (int j = 0; j < kNT; ++j) {
+                float X[4], Y[4];
+                mma_sp_bf16_16832(X, V[0], V[1], V[4], V[5], bw[j][0][0], bw[j][0][1], bw[j][1][0], bw[j][1][1], eX);
+                mma_sp_bf16_16832(Y, V[2], V[3], V[6], V[7], bw[j][0][0], bw[j][0][1], bw[j][1][0], bw[j][1][1], eY);
+                finish(j, X, Y);
             }
         }
         // pooled row 8u + g, channels cg*80 + 20t ... + 19
@@ -268,12 +304,19 @@ int sb_conv1_mma_launch(const uint8_t* codes, const int32_t* src, const int32_t*
     p.units_per_seq = (t_pool + kUnitPooled - 1) / kUnitPooled;
     p.rows_async = (L % 8 == 0) && ((reinterpret_cast<uintptr_t>(codes) & 7) == 0);      // 8-byte cp.async per row chunk
     p.row_bytes = ((kUnitPos * p.units_per_seq + 16 > L ? kUnitPos * p.units_per_seq + 16 : L) + 15) & ~15;
+    // Alone on the GPU (two CTAs per SM) the kernel is latency-bound and the dense MMAs' shorter setup wins (3.0 vs 3.5 ms
+    // per 32 768 sequences); next to a tc_layer_kernel CTA what counts is the tensor-pipe time it takes from the tcgen05
+    // MMAs, which the sparse MMAs halve (r02: step 31.35 vs 31.5 ms).  SB_CONV1_SPARSE=0 / 1 forces one or the other.
+    {
+        const char* e = getenv("SB_CONV1_SPARSE");
+        p.dense_only = e ? (e[0] == '0') : (ctas_per_sm != 1);
+    }
     p.bfrag = reinterpret_cast<const uint32_t*>(bfrag);
     p.bias = bias_padded;
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
     const int streams_per_cta = kWarps / p.n_cg;
     long long ctas = (n_rows + streams_per_cta - 1) / streams_per_cta;      // a position stream owns whole sequences
-    const size_t smem = (size_t)2 * kWarps * p.row_bytes;
+    const size_t smem = (size_t)2 * kWarps * p.row_bytes + (size_t)kWarps * (p.row_bytes / 8 + 2) * 4;
     SB_REQUIRE(smem <= 100 * 1024, "sb_conv1_mma_launch: sequences of %d bases need %zu bytes of shared memory", L, smem);
     static size_t attr = 0;
     if (smem > attr) {
