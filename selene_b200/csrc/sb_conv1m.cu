@@ -13,9 +13,11 @@
 //   rows      tile X row g / g+8 = positions 4g / 4g+1, tile Y row g / g+8 = positions 4g+2 / 4g+3 (relative to the
 //               unit), so the four members of pool window g are the four accumulator registers a thread holds for a
 //               column: pooling needs no shuffle.
-//   A         never touches memory: K index = tap*4 + base, a thread's A registers are the one-hot patterns of the
-//               TEN codes at positions 4g + t/2 ... + 9 (each register a bf16 pair: 1.0 in the slot of the base, or
-//               0.25 / 0.25 for an unknown base), fetched as three word shuffles from the 40 code bytes of the unit.
+//   A         never touches memory: K index = tap*4 + base.  Dense path: a thread's A registers are the one-hot patterns of
+//               the TEN codes at positions 4g + t/2 ... + 9 (each register a bf16 pair: 1.0 in the slot of the base, or
+//               0.25 / 0.25 for an unknown base), read from the code row staged in shared memory.  Sparse path (no unknown
+//               base in the unit, kernel co-resident with the tcgen05 layers): the one-hot operand is 2:4 sparse, one
+//               mma.sp.m16n8k32 covers all 8 taps (see mma_sp_bf16_16832).
 //   B         in registers for the whole kernel (a warp keeps its 80 channels): 40 registers; the bias (the initial
 //             accumulator value) is read from shared memory.
 //   columns   column c of n-tile j is channel 10 c + j of the warp's 80, so a thread ends up with 20 CONSECUTIVE
@@ -68,13 +70,6 @@ __device__ __forceinline__ void mma_sp_bf16_16832(float (&d)[4], const uint32_t 
 __device__ __forceinline__ uint32_t pair_pattern(uint32_t code, uint32_t h) {
     const uint32_t hot = (code & 1u) ? 0x3F800000u : 0x00003F80u;
     return code >= 4u ? 0x3E803E80u : ((code >> 1) == h ? hot : 0u);
-}
-
-// bytes of 0x3F800000 permuted by the low 16 bits of `sel` (prmt reads four 4-bit selectors; the rest is ignored)
-__device__ __forceinline__ uint32_t prmt_sel(uint32_t sel) {
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(0x3F800000u), "r"(0u), "r"(sel));
-    return r;
 }
 
 __device__ __forceinline__ float max3f(float a, float b, float c) {

@@ -375,8 +375,7 @@ int sb_lstm_persistent_launch(const void* whh0, const void* whh1, int h_ld, cons
     if (cl && cl[0] == '0') cluster = false;
     if (cl && cl[0] == '1') cluster = p.n_tiles % 2 == 0;
     p.csize = cluster ? 2 : 1;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(unit_tiles * p.csize), 2);
     cfg.blockDim = dim3(kLThreads);
     cfg.dynamicSmemBytes = smem;
