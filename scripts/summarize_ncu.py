@@ -21,7 +21,7 @@ for r in rows[hi + 2:]:
     a[1] += float(r[vi].replace(',', ''))
 tot = sum(a[1] for a in agg.values())
 out.write("# ncu launch list (%s)\n\n`ncu --metrics gpu__time_duration.sum --clock-control none` over "
-          "`python bench.py --steps 2 --warmup 1 --no-cpu --variants-per-step 4096 --genome-mbp 24` "
+          "`python bench.py --steps 2 --warmup 1 --no-cpu --no-hbm --no-train --strong-variants 0` (the bench step at its real size: 16 384 variants, 240 Mbp genome) "
           "(cold-cache, serialised: compare shares)\n\n| kernel | launches | total us | share |\n|---|---|---|---|\n" % tag)
 for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
     out.write("| `%s` | %d | %.1f | %.1f%% |\n" % (k, a[0], a[1] / 1e3, 100 * a[1] / tot))
