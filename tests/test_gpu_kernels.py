@@ -51,6 +51,27 @@ def test_tc_gemm_selftest(torch, M, N, K):
     assert err <= 2e-3 * max(1.0, ref.abs().max().item()), "max abs err %g" % err
 
 
+@pytest.mark.parametrize("pair", ["0", "2"])
+@pytest.mark.parametrize("M,N,K", [(129, 240, 192), (256, 480, 640), (385, 256, 64), (1000, 920, 928), (2049, 144, 320)])
+def test_tc_gemm_single_cta_and_cta_pairs(torch, monkeypatch, pair, M, N, K):
+    """The same GEMMs through 128-row tiles (SB_TC_PAIR=0) and through CTA pairs with cta_group::2 MMAs (SB_TC_PAIR=2
+    forces 256-row tiles whatever the wave count): ragged last tiles, a second half that lies wholly past the rows,
+    N tiles whose halves are 72 / 120 / 128 rows of B."""
+    from selene_b200 import _lib
+    monkeypatch.setenv("SB_TC_PAIR", pair)
+    lib = _lib.load()
+    gen = torch.Generator(device="cuda").manual_seed(M * 5 + N * 11 + K)
+    a = (torch.randn((M, K), device="cuda", generator=gen) * 0.5).to(torch.bfloat16)
+    b = (torch.randn((N, K), device="cuda", generator=gen) * 0.5).to(torch.bfloat16)
+    c = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32)
+    _lib.check(lib.sb_tc_gemm_selftest(_lib.ptr(a), _lib.ptr(b), M, N, K, _lib.ptr(c), _lib.stream_ptr()),
+               "sb_tc_gemm_selftest")
+    torch.cuda.synchronize()
+    ref = a.float() @ b.float().t()
+    err = (c - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), "max abs err %g" % err
+
+
 # ------------------------------------------------------------------------------------------------
 # kernel (a): encode / codes / flags
 # ------------------------------------------------------------------------------------------------
