@@ -445,7 +445,7 @@ def train_leg(model_cls, rank, world, batch=64, steps=20, warmup=5, genome=None,
     e0.record()
     for _ in range(steps):
         tr.forward_backward(xs, ys)
-        tr.allreduce_grads(overlap=True)
+        tr.allreduce_grads(overlap=True, sgd_tail=True)
         tr.sgd_step()
     e1.record()
     torch.cuda.synchronize()

@@ -278,6 +278,12 @@ int sb_net_forward_backward(sb_net* net, const float* x, const float* targets, i
                             void* workspace, size_t workspace_bytes, float* grads, float* loss, void* stream);
 /* torch.optim.SGD(lr, momentum, weight_decay) update of the handle's fp32 weights (models/deepsea.py:66-74) */
 int sb_net_sgd_step(sb_net* net, const float* grads, float lr, float momentum, float weight_decay, void* stream);
+/* the same update for layers [layer_begin, layer_end) only; `finish` != 0 on the call that completes a step.  Lets a
+ * data-parallel trainer update the classifier on its communication stream as soon as that part of the gradient is
+ * reduced (after the event of sb_net_set_grad_event, which is recorded once the backward pass no longer reads those
+ * layers' weights) while the convolution gradients are still being computed. */
+int sb_net_sgd_step_layers(sb_net* net, const float* grads, float lr, float momentum, float weight_decay,
+                           int layer_begin, int layer_end, int finish, void* stream);
 /* fp32 parameters (from_grads NULL) or gradients (from_grads = the flat vector) of one layer, to host,
  * in torch layout: conv (cout, cin, k), fc (cout, cin); bias (cout).  Synchronises the device. */
 int sb_net_get_layer_params(const sb_net* net, int layer, const float* from_grads, float* w_host, float* b_host);

@@ -452,8 +452,10 @@ extern "C" int sb_net_forward_backward(sb_net* net, const float* x, const float*
             dy, rows, N.cout, N.cout, gb);
         SB_COUNT_LAUNCH();
         SB_CHECK_LAUNCH();
-        if (T->grad_event[li]) SB_CHECK_CUDA(cudaEventRecord(T->grad_event[li], s));
-        if (li == 0) break;
+        if (li == 0) {
+            if (T->grad_event[li]) SB_CHECK_CUDA(cudaEventRecord(T->grad_event[li], s));
+            break;
+        }
         if (conv) {
             // dgrad as a forward-style GEMM over the shifted view of dfull with the taps-flipped W^T; the
             // result (gradient w.r.t. the previous layer's output) overwrites g_cur, which is consumed
@@ -472,6 +474,9 @@ extern "C" int sb_net_forward_backward(sb_net* net, const float* x, const float*
             if (rc) return rc;
             float* t = g_cur; g_cur = g_oth; g_oth = t;
         }
+        // recorded after the layer's dgrad: from here on neither the gradients NOR the weights of layers >= li are touched
+        // by this pass, so an optimiser step of those layers may run concurrently (sb_net_sgd_step_layers)
+        if (T->grad_event[li]) SB_CHECK_CUDA(cudaEventRecord(T->grad_event[li], s));
     }
     return SB_OK;
 }
@@ -482,14 +487,16 @@ static bool sgd_pack_layer_tc(sb_net* net, size_t li, const float* g, float lr, 
                               int first, cudaStream_t s);
 static void sgd_pack_done_tc(sb_net* net);
 
-extern "C" int sb_net_sgd_step(sb_net* net, const float* grads, float lr, float momentum, float weight_decay,
-                               void* stream) {
-    SB_REQUIRE(net && net->train && grads, "sb_net_sgd_step: call sb_net_train_init first");
+extern "C" int sb_net_sgd_step_layers(sb_net* net, const float* grads, float lr, float momentum, float weight_decay,
+                                      int layer_begin, int layer_end, int finish, void* stream) {
+    SB_REQUIRE(net && net->train && grads, "sb_net_sgd_step_layers: call sb_net_train_init first");
+    SB_REQUIRE(layer_begin >= 0 && layer_begin <= layer_end && layer_end <= (int)net->layers.size(),
+               "sb_net_sgd_step_layers: bad layer range [%d, %d)", layer_begin, layer_end);
     SB_CHECK_CUDA(cudaSetDevice(net->device));
     cudaStream_t s = (cudaStream_t)stream;
     sb_train_state* T = net->train;
     const int first = T->steps == 0;
-    for (size_t li = 0; li < net->layers.size(); ++li) {
+    for (size_t li = (size_t)layer_begin; li < (size_t)layer_end; ++li) {
         NetLayer& N = net->layers[li];
         const long long nw = (long long)N.k_f32 * N.ldw_f32, nb = N.ldw_f32;
         if (!(li > 0 && sgd_pack_layer_tc(net, li, grads + T->goff_w[li], lr, momentum, weight_decay, first, s)))
@@ -501,10 +508,18 @@ extern "C" int sb_net_sgd_step(sb_net* net, const float* grads, float lr, float 
         SB_COUNT_LAUNCH();
     }
     SB_CHECK_LAUNCH();
-    sgd_pack_done_tc(net);
-    T->steps += 1;
-    net->inference_weights_stale = true;
+    if (finish) {
+        sgd_pack_done_tc(net);
+        T->steps += 1;
+        net->inference_weights_stale = true;
+    }
     return SB_OK;
+}
+
+extern "C" int sb_net_sgd_step(sb_net* net, const float* grads, float lr, float momentum, float weight_decay,
+                               void* stream) {
+    SB_REQUIRE(net && net->train && grads, "sb_net_sgd_step: call sb_net_train_init first");
+    return sb_net_sgd_step_layers(net, grads, lr, momentum, weight_decay, 0, (int)net->layers.size(), 1, stream);
 }
 
 // device (k_f32 x ldw_f32, K index = tap*cin + channel; FC after a conv stack position-major) <-> torch layout

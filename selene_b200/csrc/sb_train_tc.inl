@@ -726,7 +726,6 @@ extern "C" int sb_net_forward_backward_tc(sb_net* net, const float* x, const flo
             dy, rows, ldo, N.cout, gb);
         SB_COUNT_LAUNCH();
         SB_CHECK_LAUNCH();
-        if (T->grad_event[li]) SB_CHECK_CUDA(cudaEventRecord(T->grad_event[li], s));
         // dgrad on tcgen05 -> gradient w.r.t. this layer's input (previous layer's final output)
         if (conv) {
             rc = launch_tc_plain(g_oth, rows + (N.k - 1), ldo, N.k * ldo, S->L[li].wt, N.cin, S->L[li].wt_ld, net->zero_bias_tc,
@@ -738,6 +737,9 @@ extern "C" int sb_net_forward_backward_tc(sb_net* net, const float* x, const flo
             if (rc) return rc;
             bf16* t = g_cur; g_cur = g_oth; g_oth = t;
         }
+        // recorded after the layer's dgrad (which reads its weights): gradients and weights of layers >= li are final /
+        // unread from here on, so their all-reduce AND optimiser step may overlap the rest of the backward pass
+        if (T->grad_event[li]) SB_CHECK_CUDA(cudaEventRecord(T->grad_event[li], s));
         if (li == 1) break;
     }
 

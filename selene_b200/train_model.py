@@ -30,6 +30,7 @@ class B200Trainer(object):
         if self.grad_comm_dtype not in ("fp32", "bf16"):
             raise ValueError("grad_comm_dtype must be 'fp32' or 'bf16', got %r" % (grad_comm_dtype,))
         self._grads16 = None
+        self._tail_sgd_done = False
         layers = model_or_layers if isinstance(model_or_layers, list) else layers_from_module(model_or_layers)
         self.net = B200Net(layers, sequence_length, perm=perm, device=device)
         self._lib = self.net._lib
@@ -110,10 +111,12 @@ class B200Trainer(object):
             _lib.ptr(ws), ws.numel(), _lib.ptr(self.grads), _lib.ptr(self.loss), _lib.stream_ptr()),
             "sb_net_forward_backward")
 
-    def allreduce_grads(self, overlap=True):
+    def allreduce_grads(self, overlap=True, sgd_tail=False):
         """Mean of the flat gradient vector over the ranks (NCCL).  With ``overlap`` the classifier tail is reduced
         on a side stream as soon as ``sb_net_forward_backward`` has produced it (the event of sb_net_set_grad_event),
-        i.e. while the convolution gradients are still being computed; the head follows on the current stream."""
+        i.e. while the convolution gradients are still being computed; the head follows on the current stream.
+        ``sgd_tail`` (what ``step`` / ``step_async`` pass): the classifier's optimiser step is enqueued right behind its
+        all-reduce on the side stream too, and the following ``sgd_step()`` only updates the remaining layers."""
         import torch
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
@@ -146,6 +149,13 @@ class B200Trainer(object):
                 tail = reduce(self._tail_off, n, async_op=True)
                 tail.wait()
                 widen(self._tail_off, n)
+                if sgd_tail:
+                    # the classifier's optimiser step (89 % of the parameters) right behind its all-reduce, still on
+                    # the side stream: it overlaps the convolution backward and the head's all-reduce
+                    _lib.check(self._lib.sb_net_sgd_step_layers(self._h, _lib.ptr(self.grads), self.lr, self.momentum,
+                                                                self.weight_decay, self._tail_layer, self.n_layers, 0,
+                                                                _lib.stream_ptr()), "sb_net_sgd_step_layers")
+                    self._tail_sgd_done = True
             reduce(0, self._tail_off)
             widen(0, self._tail_off)
             cur.wait_stream(self._comm_stream)            # the current stream waits for the side-stream reduction
@@ -156,8 +166,14 @@ class B200Trainer(object):
             self.grads.div_(div)
 
     def sgd_step(self):
-        _lib.check(self._lib.sb_net_sgd_step(self._h, _lib.ptr(self.grads), self.lr, self.momentum, self.weight_decay,
-                                             _lib.stream_ptr()), "sb_net_sgd_step")
+        if self._tail_sgd_done:      # allreduce_grads already updated the classifier on the communication stream
+            _lib.check(self._lib.sb_net_sgd_step_layers(self._h, _lib.ptr(self.grads), self.lr, self.momentum,
+                                                        self.weight_decay, 0, self._tail_layer, 1, _lib.stream_ptr()),
+                       "sb_net_sgd_step_layers")
+            self._tail_sgd_done = False
+        else:
+            _lib.check(self._lib.sb_net_sgd_step(self._h, _lib.ptr(self.grads), self.lr, self.momentum, self.weight_decay,
+                                                 _lib.stream_ptr()), "sb_net_sgd_step")
         self.step_count += 1
 
     def step_async(self, inputs, targets, masks=None):
@@ -167,7 +183,7 @@ class B200Trainer(object):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             self._enable_overlap()
         self.forward_backward(inputs, targets, masks)
-        self.allreduce_grads()
+        self.allreduce_grads(sgd_tail=True)
         self.sgd_step()
 
     def loss_value(self):
@@ -179,7 +195,7 @@ class B200Trainer(object):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             self._enable_overlap()
         self.forward_backward(inputs, targets, masks)
-        self.allreduce_grads()
+        self.allreduce_grads(sgd_tail=True)
         self.sgd_step()
         return float(self.loss.item())
 
