@@ -281,8 +281,9 @@ int sb_net_sgd_step(sb_net* net, const float* grads, float lr, float momentum, f
 /* the same update for layers [layer_begin, layer_end) only; `finish` != 0 on the call that completes a step.  Lets a
  * data-parallel trainer update the classifier on its communication stream as soon as that part of the gradient is
  * reduced (after the event of sb_net_set_grad_event, which is recorded once the backward pass no longer reads those
- * layers' weights) while the convolution gradients are still being computed. */
-int sb_net_sgd_step_layers(sb_net* net, const float* grads, float lr, float momentum, float weight_decay,
+ * layers' weights) while the convolution gradients are still being computed.  grads_bf16 != 0: `grads` is the flat
+ * vector as bf16 (same element offsets), i.e. the buffer a bf16 all-reduce just filled, read without widening it. */
+int sb_net_sgd_step_layers(sb_net* net, const void* grads, int grads_bf16, float lr, float momentum, float weight_decay,
                            int layer_begin, int layer_end, int finish, void* stream);
 /* fp32 parameters (from_grads NULL) or gradients (from_grads = the flat vector) of one layer, to host,
  * in torch layout: conv (cout, cin, k), fc (cout, cin); bias (cout).  Synchronises the device. */

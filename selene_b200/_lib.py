@@ -76,7 +76,7 @@ SIGNATURES = {
     "sb_net_train_workspace_bytes_tc": (C.c_size_t, [_P, _L]),
     "sb_net_forward_backward_tc": (_I, [_P, _P, _P, _L, _P, C.c_ulonglong, _P, C.c_size_t, _P, _P, _P]),
     "sb_net_sgd_step": (_I, [_P, _P, C.c_float, C.c_float, C.c_float, _P]),
-    "sb_net_sgd_step_layers": (_I, [_P, _P, C.c_float, C.c_float, C.c_float, _I, _I, _I, _P]),
+    "sb_net_sgd_step_layers": (_I, [_P, _P, _I, C.c_float, C.c_float, C.c_float, _I, _I, _I, _P]),
     "sb_net_get_layer_params": (_I, [_P, _I, _P, _P, _P]),
     "sb_net_get_layer_momentum": (_I, [_P, _I, _P, _P]),
     "sb_net_set_layer_momentum": (_I, [_P, _I, _P, _P]),

@@ -225,11 +225,16 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
 }
 
 // torch.optim.SGD: g += wd*w; v = mom*v + g (v = g on the first step); w -= lr*v
-__global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ w, float* __restrict__ v, const float* __restrict__ g,
+// gradient element as fp32: the flat gradient vector is fp32, or bf16 when it comes straight out of a bf16 all-reduce
+__device__ __forceinline__ float grad_at(const float* g, long long i) { return g[i]; }
+__device__ __forceinline__ float grad_at(const __nv_bfloat16* g, long long i) { return __bfloat162float(g[i]); }
+
+template <typename GT>
+__global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ w, float* __restrict__ v, const GT* __restrict__ g,
                                                   long long n, float lr, float mom, float wd, int first) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float gi = g[i] + wd * w[i];
+        const float gi = grad_at(g, i) + wd * w[i];
         const float vi = first ? gi : mom * v[i] + gi;
         v[i] = vi;
         w[i] -= lr * vi;
@@ -483,12 +488,13 @@ extern "C" int sb_net_forward_backward(sb_net* net, const float* x, const float*
 
 // sb_train_tc.inl: SGD update of layer li's weights fused with the bf16 repacking the tcgen05 training step needs
 // (returns false when the tensor-core training state does not exist)
-static bool sgd_pack_layer_tc(sb_net* net, size_t li, const float* g, float lr, float momentum, float weight_decay,
+template <typename GT>
+static bool sgd_pack_layer_tc(sb_net* net, size_t li, const GT* g, float lr, float momentum, float weight_decay,
                               int first, cudaStream_t s);
 static void sgd_pack_done_tc(sb_net* net);
 
-extern "C" int sb_net_sgd_step_layers(sb_net* net, const float* grads, float lr, float momentum, float weight_decay,
-                                      int layer_begin, int layer_end, int finish, void* stream) {
+extern "C" int sb_net_sgd_step_layers(sb_net* net, const void* grads, int grads_bf16, float lr, float momentum,
+                                      float weight_decay, int layer_begin, int layer_end, int finish, void* stream) {
     SB_REQUIRE(net && net->train && grads, "sb_net_sgd_step_layers: call sb_net_train_init first");
     SB_REQUIRE(layer_begin >= 0 && layer_begin <= layer_end && layer_end <= (int)net->layers.size(),
                "sb_net_sgd_step_layers: bad layer range [%d, %d)", layer_begin, layer_end);
@@ -496,14 +502,27 @@ extern "C" int sb_net_sgd_step_layers(sb_net* net, const float* grads, float lr,
     cudaStream_t s = (cudaStream_t)stream;
     sb_train_state* T = net->train;
     const int first = T->steps == 0;
+    const float* g32 = reinterpret_cast<const float*>(grads);
+    const __nv_bfloat16* g16 = reinterpret_cast<const __nv_bfloat16*>(grads);
     for (size_t li = (size_t)layer_begin; li < (size_t)layer_end; ++li) {
         NetLayer& N = net->layers[li];
         const long long nw = (long long)N.k_f32 * N.ldw_f32, nb = N.ldw_f32;
-        if (!(li > 0 && sgd_pack_layer_tc(net, li, grads + T->goff_w[li], lr, momentum, weight_decay, first, s)))
-            sgd_kernel<<<grid_for(nw, net->device), 256, 0, s>>>(N.wf, T->mom_w[li], grads + T->goff_w[li], nw, lr, momentum,
+        const bool packed = li > 0 && (grads_bf16 ? sgd_pack_layer_tc(net, li, g16 + T->goff_w[li], lr, momentum, weight_decay, first, s)
+                                                  : sgd_pack_layer_tc(net, li, g32 + T->goff_w[li], lr, momentum, weight_decay, first, s));
+        if (!packed) {
+            if (grads_bf16)
+                sgd_kernel<<<grid_for(nw, net->device), 256, 0, s>>>(N.wf, T->mom_w[li], g16 + T->goff_w[li], nw, lr, momentum,
+                                                                     weight_decay, first);
+            else
+                sgd_kernel<<<grid_for(nw, net->device), 256, 0, s>>>(N.wf, T->mom_w[li], g32 + T->goff_w[li], nw, lr, momentum,
+                                                                     weight_decay, first);
+        }
+        if (grads_bf16)
+            sgd_kernel<<<grid_for(nb, net->device), 256, 0, s>>>(N.biasf, T->mom_b[li], g16 + T->goff_b[li], nb, lr, momentum,
                                                                  weight_decay, first);
-        sgd_kernel<<<grid_for(nb, net->device), 256, 0, s>>>(N.biasf, T->mom_b[li], grads + T->goff_b[li], nb, lr, momentum,
-                                                             weight_decay, first);
+        else
+            sgd_kernel<<<grid_for(nb, net->device), 256, 0, s>>>(N.biasf, T->mom_b[li], g32 + T->goff_b[li], nb, lr, momentum,
+                                                                 weight_decay, first);
         SB_COUNT_LAUNCH();
         SB_COUNT_LAUNCH();
     }
@@ -519,7 +538,7 @@ extern "C" int sb_net_sgd_step_layers(sb_net* net, const float* grads, float lr,
 extern "C" int sb_net_sgd_step(sb_net* net, const float* grads, float lr, float momentum, float weight_decay,
                                void* stream) {
     SB_REQUIRE(net && net->train && grads, "sb_net_sgd_step: call sb_net_train_init first");
-    return sb_net_sgd_step_layers(net, grads, lr, momentum, weight_decay, 0, (int)net->layers.size(), 1, stream);
+    return sb_net_sgd_step_layers(net, grads, 0, lr, momentum, weight_decay, 0, (int)net->layers.size(), 1, stream);
 }
 
 // device (k_f32 x ldw_f32, K index = tap*cin + channel; FC after a conv stack position-major) <-> torch layout

@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(256) pack_fwd_kernel(const float* __restrict__
 
 // SGD update (torch.optim.SGD with momentum and weight decay, as sgd_kernel) of one layer's fp32 master weights fused
 // with both repackings above: one pass over w / momentum / gradient instead of three passes over w.
-__global__ void __launch_bounds__(256) sgd_pack_kernel(float* __restrict__ wf, float* __restrict__ v, const float* __restrict__ g,
+template <typename GT>
+__global__ void __launch_bounds__(256) sgd_pack_kernel(float* __restrict__ wf, float* __restrict__ v, const GT* __restrict__ g,
                                                        int ldw, long long K, int cout, float lr, float mom, float wd, int first,
                                                        int ch, int ch_ld, bf16* __restrict__ wb, int w_ld, int taps, int C,
                                                        int cout_ld, bf16* __restrict__ wt, int wt_ld) {
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(256) sgd_pack_kernel(float* __restrict__ wf, f
         float wn = 0.f;
         if (kk < K && o < ldw) {
             const long long i = kk * ldw + o;
-            const float gi = g[i] + wd * wf[i];
+            const float gi = grad_at(g, i) + wd * wf[i];
             const float vi = first ? gi : mom * v[i] + gi;
             v[i] = vi;
             wn = wf[i] - lr * vi;
@@ -791,7 +792,8 @@ extern "C" int sb_net_forward_backward_tc(sb_net* net, const float* x, const flo
 }
 
 
-static bool sgd_pack_layer_tc(sb_net* net, size_t li, const float* g, float lr, float momentum, float weight_decay,
+template <typename GT>
+static bool sgd_pack_layer_tc(sb_net* net, size_t li, const GT* g, float lr, float momentum, float weight_decay,
                               int first, cudaStream_t s) {
     if (!net->train_tc || li == 0 || li >= net->train_tc->L.size()) return false;
     const char* off = getenv("SB_SGD_FUSED_PACK");   // "0": plain SGD kernel, repack at the start of the next step

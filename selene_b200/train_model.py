@@ -148,14 +148,17 @@ class B200Trainer(object):
             with torch.cuda.stream(self._comm_stream):
                 tail = reduce(self._tail_off, n, async_op=True)
                 tail.wait()
-                widen(self._tail_off, n)
                 if sgd_tail:
                     # the classifier's optimiser step (89 % of the parameters) right behind its all-reduce, still on
-                    # the side stream: it overlaps the convolution backward and the head's all-reduce
-                    _lib.check(self._lib.sb_net_sgd_step_layers(self._h, _lib.ptr(self.grads), self.lr, self.momentum,
-                                                                self.weight_decay, self._tail_layer, self.n_layers, 0,
-                                                                _lib.stream_ptr()), "sb_net_sgd_step_layers")
+                    # the side stream: it overlaps the convolution backward and the head's all-reduce.  With bf16
+                    # communication it reads the reduced bf16 vector directly (self.grads keeps this rank's own tail).
+                    _lib.check(self._lib.sb_net_sgd_step_layers(self._h, _lib.ptr(self._grads16 if half else self.grads),
+                                                                1 if half else 0, self.lr, self.momentum, self.weight_decay,
+                                                                self._tail_layer, self.n_layers, 0, _lib.stream_ptr()),
+                               "sb_net_sgd_step_layers")
                     self._tail_sgd_done = True
+                else:
+                    widen(self._tail_off, n)
             reduce(0, self._tail_off)
             widen(0, self._tail_off)
             cur.wait_stream(self._comm_stream)            # the current stream waits for the side-stream reduction
@@ -167,7 +170,7 @@ class B200Trainer(object):
 
     def sgd_step(self):
         if self._tail_sgd_done:      # allreduce_grads already updated the classifier on the communication stream
-            _lib.check(self._lib.sb_net_sgd_step_layers(self._h, _lib.ptr(self.grads), self.lr, self.momentum,
+            _lib.check(self._lib.sb_net_sgd_step_layers(self._h, _lib.ptr(self.grads), 0, self.lr, self.momentum,
                                                         self.weight_decay, 0, self._tail_layer, 1, _lib.stream_ptr()),
                        "sb_net_sgd_step_layers")
             self._tail_sgd_done = False
