@@ -182,6 +182,53 @@ def test_fused_sgd_repack_equals_separate_passes(monkeypatch):
     assert runs[0][0][-1] < runs[0][0][0]
 
 
+def test_sgd_step_by_layer_ranges_and_bf16_gradients():
+    """sb_net_sgd_step_layers (what a data-parallel trainer calls: classifier on the communication stream behind its
+    all-reduce, the rest afterwards) must equal sb_net_sgd_step; with grads_bf16 the classifier's update must equal
+    the fp32 update fed with the same gradients rounded to bf16."""
+    import torch
+    import sb_models as M
+    from selene_b200 import _lib
+    from selene_b200.train_model import B200Trainer
+    rng = np.random.default_rng(5)
+    n = 4
+    x = np.eye(4, dtype=np.float32)[rng.integers(0, 4, (n, 1000))]
+    y = (rng.random((n, 919)) < 0.1).astype(np.float32)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+
+    def trainer():
+        torch.manual_seed(9)
+        return B200Trainer(M.DeepSEA(1000, 919), 1000, lr=0.1, momentum=0.9, weight_decay=1e-4, precision="bf16", seed=1)
+    lib = _lib.load()
+    results = {}
+    for mode in ("whole", "ranges", "ranges_bf16", "whole_rounded"):
+        tr = trainer()
+        tail = tr._tail_layer
+        for _ in range(3):
+            tr.forward_backward(xd, yd)
+            if mode == "whole":
+                tr.sgd_step()
+                continue
+            g16 = tr.grads.to(torch.bfloat16)
+            if mode == "whole_rounded":          # the classifier's gradients rounded to bf16, update in fp32
+                off = int(lib.sb_net_param_offset(tr._h, tail))
+                tr.grads[off:] = g16[off:].float()
+                tr.sgd_step()
+                continue
+            half = mode == "ranges_bf16"
+            _lib.check(lib.sb_net_sgd_step_layers(tr._h, _lib.ptr(g16 if half else tr.grads), 1 if half else 0, tr.lr,
+                                                  tr.momentum, tr.weight_decay, tail, tr.n_layers, 0, _lib.stream_ptr()),
+                       "sb_net_sgd_step_layers")
+            _lib.check(lib.sb_net_sgd_step_layers(tr._h, _lib.ptr(tr.grads), 0, tr.lr, tr.momentum, tr.weight_decay,
+                                                  0, tail, 1, _lib.stream_ptr()), "sb_net_sgd_step_layers")
+        results[mode] = [tr.layer_params(li) for li in range(tr.n_layers)]
+    for li in range(len(results["whole"])):
+        for a, b in zip(results["whole"][li], results["ranges"][li]):
+            assert np.abs(a - b).max() <= 2e-6, li            # run-to-run noise of the atomically accumulated gradients
+        for a, b in zip(results["whole_rounded"][li], results["ranges_bf16"][li]):
+            assert np.abs(a - b).max() <= 2e-6, li
+
+
 class _FixedSampler(object):
     """A sampler with the reference's interface that cycles through fixed batches (so two runs see the same data)."""
     modes = ["train", "validate"]
