@@ -649,6 +649,8 @@ struct WgParams {
     int m_tiles, n_tiles, splits, kb_total;
     float* g;       // (N x ldg) fp32
     int ldg;
+    int overwrite;  // one K pass per tile: plain stores over all ldg columns instead of adds into a zeroed buffer
+    int m_fastest;  // tile order (overwrite mode only)
 };
 
 constexpr int kWgBlockN = 256;
@@ -691,8 +693,16 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     sb_tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // item -> (m tile, n tile, split); n fastest so neighbouring CTAs share the dY tile
+    // item -> (m tile, n tile, split); n fastest so neighbouring CTAs share the dY tile.  In overwrite mode (a long,
+    // single-pass G) m is fastest: the CTAs in flight then store whole rows of G and share the X tile.
     auto decode = [&](int item, int& mt, int& nt, int& kb0, int& kb1) {
+        if (p.m_fastest) {
+            mt = item % p.m_tiles;
+            nt = item / p.m_tiles;
+            kb0 = 0;
+            kb1 = p.kb_total;
+            return;
+        }
         nt = item % p.n_tiles;
         const int rest = item / p.n_tiles;
         mt = rest % p.m_tiles;
@@ -772,7 +782,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                     uint32_t rr[16];
                     sb_tmem_ld16(taddr + c * 16, rr);
                     sb_tmem_wait_ld();
-                    if (m < p.M) {
+                    if (p.overwrite) {   // rows of dY^T past M are TMA zero fill: the padded columns get their zeros here
+                        if (m < p.ldg) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (nb + j < p.N) p.g[(long long)(nb + j) * p.ldg + m] = __uint_as_float(rr[j]);
+                        }
+                    } else if (m < p.M) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
                             if (nb + j < p.N) atomicAdd(p.g + (long long)(nb + j) * p.ldg + m, __uint_as_float(rr[j]));
@@ -792,8 +808,24 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
 // G (N x ldg, fp32) += dY^T . Xview ; dy: rows x M bf16 (row stride dy_ld), x: bf16 buffer whose row r is the
 // run of N elements starting at r*x_ld (overlapping when N > x_ld: taps > 1).
+static int wgrad_splits(long long rows, int M, int N, int device) {
+    const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + kWgBlockN - 1) / kWgBlockN);
+    const int kb_total = (int)((rows + kBlockK - 1) / kBlockK);
+    int splits = (2 * sb_sm_count(device)) / tiles;
+    if (splits < 1) splits = 1;
+    return splits > kb_total ? kb_total : splits;
+}
+
+// true when sb_tc_wgrad_launch(..., overwrite = 1) stores G (all ldg columns of its N rows) instead of adding to it,
+// i.e. the caller need not zero G first: every tile is reduced in one K pass and the M tiles cover the padded columns
+bool sb_tc_wgrad_overwrites(long long rows, int M, int N, int ldg, int device) {
+    const char* e = getenv("SB_WGRAD_OVERWRITE");
+    if (e && e[0] == '0') return false;
+    return rows > 0 && wgrad_splits(rows, M, N, device) == 1 && ldg <= ((M + kBlockM - 1) / kBlockM) * kBlockM;
+}
+
 int sb_tc_wgrad_launch(const void* dy, int dy_ld, const void* x, int x_ld, long long x_rows_alloc, long long rows,
-                       int M, int N, float* g, int ldg, int device, cudaStream_t stream) {
+                       int M, int N, float* g, int ldg, int device, cudaStream_t stream, int overwrite) {
     SB_REQUIRE(dy_ld % 8 == 0 && x_ld % 8 == 0, "sb_tc_wgrad_launch: leading dimensions must be multiples of 8");
     if (rows <= 0) return SB_OK;
     const int span = (N + x_ld - 1) / x_ld;                        // rows touched by one X row view
@@ -829,11 +861,11 @@ int sb_tc_wgrad_launch(const void* dy, int dy_ld, const void* x, int x_ld, long 
     p.n_tiles = (N + kWgBlockN - 1) / kWgBlockN;
     p.kb_total = (int)((rows + kBlockK - 1) / kBlockK);
     const int sms = sb_sm_count(device);
-    int splits = (2 * sms) / (p.m_tiles * p.n_tiles);
-    if (splits < 1) splits = 1;
-    if (splits > p.kb_total) splits = p.kb_total;
-    p.splits = splits;
+    p.splits = wgrad_splits(rows, M, N, device);
     p.g = g; p.ldg = ldg;
+    p.overwrite = (overwrite && sb_tc_wgrad_overwrites(rows, M, N, ldg, device)) ? 1 : 0;
+    const char* ord = getenv("SB_WGRAD_ORDER");
+    p.m_fastest = (p.overwrite && !(ord && ord[0] == '0')) ? 1 : 0;
     static bool attr_set = false;
     if (!attr_set) {
         SB_CHECK_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -852,7 +884,7 @@ extern "C" int sb_tc_wgrad_selftest(const void* dy_bf16, const void* x_bf16, lon
     SB_REQUIRE(dy_bf16 && x_bf16 && g, "sb_tc_wgrad_selftest: null argument");
     int dev = 0;
     SB_CHECK_CUDA(cudaGetDevice(&dev));
-    return sb_tc_wgrad_launch(dy_bf16, M, x_bf16, x_ld, rows, rows, M, N, g, M, dev, (cudaStream_t)stream);
+    return sb_tc_wgrad_launch(dy_bf16, M, x_bf16, x_ld, rows, rows, M, N, g, M, dev, (cudaStream_t)stream, 0);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -64,4 +64,5 @@ int sb_tc_launch(const SbTcLayer& L, int device, cudaStream_t stream, const SbSc
 
 // wgrad: G (N x ldg fp32) += dY^T . Xview (see sb_tc.cu); G must be zeroed by the caller.
 int sb_tc_wgrad_launch(const void* dy, int dy_ld, const void* x, int x_ld, long long x_rows_alloc, long long rows,
-                       int M, int N, float* g, int ldg, int device, cudaStream_t stream);
+                       int M, int N, float* g, int ldg, int device, cudaStream_t stream, int overwrite = 0);
+bool sb_tc_wgrad_overwrites(long long rows, int M, int N, int ldg, int device);

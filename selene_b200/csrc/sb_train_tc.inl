@@ -64,42 +64,55 @@ __global__ void __launch_bounds__(256) pack_fwd_kernel(const float* __restrict__
 // SGD update (torch.optim.SGD with momentum and weight decay, as sgd_kernel) of one layer's fp32 master weights fused
 // with both repackings above: one pass over w / momentum / gradient instead of three passes over w.
 template <typename GT>
-__global__ void __launch_bounds__(256) sgd_pack_kernel(float* __restrict__ wf, float* __restrict__ v, const GT* __restrict__ g,
-                                                       int ldw, long long K, int cout, float lr, float mom, float wd, int first,
-                                                       int ch, int ch_ld, bf16* __restrict__ wb, int w_ld, int taps, int C,
-                                                       int cout_ld, bf16* __restrict__ wt, int wt_ld) {
+__global__ void __launch_bounds__(256, 8) sgd_pack_kernel(float* __restrict__ wf, float* __restrict__ v, const GT* __restrict__ g,
+                                                          int ldw, int K, int cout, float lr, float mom, float wd, int first,
+                                                          int ch, int ch_ld, bf16* __restrict__ wb, int w_ld, int taps, int C,
+                                                          int cout_ld, bf16* __restrict__ wt, int wt_ld, int o_blocks) {
     __shared__ float tile[32][33];
-    const long long k0 = (long long)blockIdx.x * 32;
-    const int o0 = blockIdx.y * 32;
+    // o_blocks > 0: 1-D grid with the channel blocks fastest, so the CTAs in flight sweep whole rows of w / momentum /
+    // gradient (contiguous megabytes) instead of a 128-byte column strip with a row-pitch stride.  All index arithmetic
+    // is 32-bit and the tap / channel split of a row is skipped for FC layers (ncu, r02k: the 64-bit divisions of the
+    // first version kept the issue slots 64 % busy on a kernel that should only wait for HBM).
+    const int k0 = (o_blocks > 0 ? (int)(blockIdx.x / o_blocks) : (int)blockIdx.x) * 32;
+    const int o0 = (o_blocks > 0 ? (int)(blockIdx.x % o_blocks) : (int)blockIdx.y) * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const int o = o0 + tx;
 #pragma unroll
     for (int r = ty; r < 32; r += 8) {
-        const long long kk = k0 + r;
-        const int o = o0 + tx;
+        const int kk = k0 + r;
         float wn = 0.f;
         if (kk < K && o < ldw) {
-            const long long i = kk * ldw + o;
-            const float gi = grad_at(g, i) + wd * wf[i];
+            const long long i = (long long)kk * ldw + o;
+            const float w0 = wf[i];
+            const float gi = grad_at(g, i) + wd * w0;
             const float vi = first ? gi : mom * v[i] + gi;
             v[i] = vi;
-            wn = wf[i] - lr * vi;
+            wn = w0 - lr * vi;
             wf[i] = wn;
             if (o < cout) {   // dgrad operand, same orientation: wt[c][tap' * cout_ld + o], taps flipped
-                const int c = (int)(kk % C);
-                const int tp = taps - 1 - (int)(kk / C);
-                wt[(long long)c * wt_ld + (long long)tp * cout_ld + o] = __float2bfloat16_rn(wn);
+                int c = kk, tp = 0;
+                if (taps > 1) {
+                    const int t = (int)((unsigned)kk / (unsigned)C);
+                    c = kk - t * C;
+                    tp = taps - 1 - t;
+                }
+                wt[(long long)c * wt_ld + tp * cout_ld + o] = __float2bfloat16_rn(wn);
             }
         }
         tile[r][tx] = wn;
     }
     __syncthreads();
+    const int kk = k0 + tx;
+    int col = kk;                                              // forward operand, transposed: wb[o][col(kk)]
+    if (ch != ch_ld) {
+        const int q = (int)((unsigned)kk / (unsigned)ch);
+        col = q * ch_ld + (kk - q * ch);
+    }
+    if (kk < K) {
 #pragma unroll
-    for (int r = ty; r < 32; r += 8) {   // forward operand, transposed: wb[o][col(kk)]
-        const int o = o0 + r;
-        const long long kk = k0 + tx;
-        if (o < cout && kk < K) {
-            const long long col = (kk / ch) * ch_ld + kk % ch;
-            wb[(long long)o * w_ld + col] = __float2bfloat16_rn(tile[tx][r]);
+        for (int r = ty; r < 32; r += 8) {
+            const int oo = o0 + r;
+            if (oo < cout) wb[(long long)oo * w_ld + col] = __float2bfloat16_rn(tile[tx][r]);
         }
     }
 }
@@ -299,24 +312,74 @@ __global__ void __launch_bounds__(256) bce_bf16_kernel(const float* __restrict__
     if ((threadIdx.x & 31) == 0) atomicAdd(loss, local);
 }
 
+// db[o] += sum_r dy[r][o] (bias gradient).  A CTA owns a strip of 64 channels (one 128-byte line per row) and a slab of
+// rows: 8 lanes x 16-byte loads cover the strip, the other 32 threads-per-strip interleave the rows, 8 loads are in
+// flight per thread; one atomic per (CTA, channel) at the end, so a channel sees as many adds as there are slabs.
+constexpr int kColsumStrip = 64;
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ dy, long long rows, int ld, int n_cols,
-                                                          float* __restrict__ db) {
-    const int o = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int part = threadIdx.x >> 5;
-    __shared__ float red[8][33];
-    const long long r0 = (long long)blockIdx.y * kColsumRows;
-    const long long r1 = r0 + kColsumRows < rows ? r0 + kColsumRows : rows;
-    float s = 0.f;
-    if (o < n_cols)
-        for (long long r = r0 + part; r < r1; r += 8) s += __bfloat162float(dy[r * ld + o]);
-    red[part][threadIdx.x & 31] = s;
+                                                          long long rows_per_slab, float* __restrict__ db) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cq = threadIdx.x & 7;                                // 8 channels = one uint4
+    const int rl = threadIdx.x >> 3;                               // 0..31: row lane
+    const int c0 = blockIdx.x * kColsumStrip + cq * 8;
+    const long long r0 = (long long)blockIdx.y * rows_per_slab;
+    const long long r1 = r0 + rows_per_slab < rows ? r0 + rows_per_slab : rows;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    if (c0 < ld) {                                                 // ld % 8 == 0: a uint4 is inside the row or not at all
+        const uint4* src = reinterpret_cast<const uint4*>(dy + c0);
+        const long long ld8 = ld / 8;
+        long long r = r0 + rl;
+        for (; r + 7 * 32 < r1; r += 8 * 32) {
+            uint4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (r + 32 * u) * ld8);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                float f[8];
+                bf16x8_to_f32(v[u], f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] += f[k];
+            }
+        }
+        for (; r < r1; r += 32) {
+            float f[8];
+            bf16x8_to_f32(__ldg(src + r * ld8), f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += f[k];
+        }
+    }
+    // the 4 row lanes of a warp, then the 8 warps
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 8);
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
+    }
+    __shared__ float red[8][kColsumStrip];
+    if (lane < 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) red[warp][lane * 8 + k] = acc[k];
+    }
     __syncthreads();
-    if (part == 0 && o < n_cols) {
+    if (threadIdx.x < kColsumStrip) {
         float t = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x & 31];
-        if (t != 0.f) atomicAdd(db + o, t);
+        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        const int o = blockIdx.x * kColsumStrip + threadIdx.x;
+        if (o < n_cols && t != 0.f) atomicAdd(db + o, t);
     }
+}
+
+static void launch_colsum_bf16(const bf16* dy, long long rows, int ld, int n_cols, float* db, int dev, cudaStream_t s) {
+    const int strips = (n_cols + kColsumStrip - 1) / kColsumStrip;
+    long long slabs = (2 * sb_sm_count(dev) + strips - 1) / strips;
+    const long long max_slabs = (rows + 255) / 256;                 // at least 8 rows per row lane
+    if (slabs > max_slabs) slabs = max_slabs;
+    if (slabs < 1) slabs = 1;
+    const long long rows_per_slab = (rows + slabs - 1) / slabs;
+    colsum_bf16_kernel<<<dim3((unsigned)strips, (unsigned)((rows + rows_per_slab - 1) / rows_per_slab)), 256, 0, s>>>(
+        dy, rows, ld, n_cols, rows_per_slab, db);
 }
 
 // First-conv weight gradient: dW[(j*4 + c)][o] = sum_r x[r + j][c] * dY[r][o] with the 4*taps (<= 32)
@@ -681,7 +744,20 @@ extern "C" int sb_net_forward_backward_tc(sb_net* net, const float* x, const flo
     bf16* g_cur = reinterpret_cast<bf16*>(base + P.g_a);
     bf16* g_oth = reinterpret_cast<bf16*>(base + P.g_b);
     SB_CHECK_CUDA(cudaMemsetAsync(loss, 0, 4, s));
-    SB_CHECK_CUDA(cudaMemsetAsync(grads, 0, T->n_params * 4, s));
+    // weight-gradient blocks whose wgrad reduces every tile in ONE K pass (FC layers: rows = batch <= one k-block) are
+    // stored, not accumulated: everything else (split-K accumulators, bias sums, padded columns) starts from zero
+    std::vector<char> wg_stores(L, 0);
+    {
+        size_t z0 = 0;
+        for (size_t li = 1; li < L; ++li) {
+            const NetLayer& N = net->layers[li];
+            wg_stores[li] = sb_tc_wgrad_overwrites((long long)n * N.t_in, N.cout, N.k_f32, N.ldw_f32, dev) ? 1 : 0;
+            if (!wg_stores[li]) continue;
+            if (T->goff_w[li] > z0) SB_CHECK_CUDA(cudaMemsetAsync(grads + z0, 0, (T->goff_w[li] - z0) * 4, s));
+            z0 = T->goff_b[li];
+        }
+        if (T->n_params > z0) SB_CHECK_CUDA(cudaMemsetAsync(grads + z0, 0, (T->n_params - z0) * 4, s));
+    }
     {
         const int ldz = S->L[L - 1].cout_ld;
         bce_bf16_kernel<<<grid_for((long long)n * ldz, dev), 256, 0, s>>>(logits, ldl, targets, n, F, g_cur, ldz, loss);
@@ -721,10 +797,10 @@ extern "C" int sb_net_forward_backward_tc(sb_net* net, const float* x, const flo
             dy = g_cur;
         }
         // wgrad on tcgen05: G[kk][o] += sum_r Xin[r*ld_in + kk] dY[r][o]
-        rc = sb_tc_wgrad_launch(dy, ldo, xin[li], conv ? ld_in : N.a_ld, rows, rows, N.cout, N.k_f32, gw, N.ldw_f32, dev, s);
+        rc = sb_tc_wgrad_launch(dy, ldo, xin[li], conv ? ld_in : N.a_ld, rows, rows, N.cout, N.k_f32, gw, N.ldw_f32, dev, s,
+                                wg_stores[li]);
         if (rc) return rc;
-        colsum_bf16_kernel<<<dim3((N.cout + 31) / 32, (unsigned)((rows + kColsumRows - 1) / kColsumRows)), 256, 0, s>>>(
-            dy, rows, ldo, N.cout, gb);
+        launch_colsum_bf16(dy, rows, ldo, N.cout, gb, dev, s);
         SB_COUNT_LAUNCH();
         SB_CHECK_LAUNCH();
         // dgrad on tcgen05 -> gradient w.r.t. this layer's input (previous layer's final output)
@@ -762,8 +838,7 @@ extern "C" int sb_net_forward_backward_tc(sb_net* net, const float* x, const flo
         w0_grad_unpad_kernel<<<grid_for((long long)N0.k * 4 * N0.cout, dev), 256, 0, s>>>(g8, N0.ldw_f32, N0.k, N0.cout,
                                                                                          grads + T->goff_w[0], N0.ldw_f32);
         SB_COUNT_LAUNCH();
-        colsum_bf16_kernel<<<dim3((N0.cout + 31) / 32, (unsigned)((rows + kColsumRows - 1) / kColsumRows)), 256, 0, s>>>(
-            dfull0, rows, ld0b, N0.cout, grads + T->goff_b[0]);
+        launch_colsum_bf16(dfull0, rows, ld0b, N0.cout, grads + T->goff_b[0], dev, s);
         SB_COUNT_LAUNCH();
         SB_CHECK_LAUNCH();
     } else {
@@ -802,9 +877,12 @@ static bool sgd_pack_layer_tc(sb_net* net, size_t li, const GT* g, float lr, flo
     const TcTrainLayer& T = net->train_tc->L[li];
     const bool conv = N.type == SB_LAYER_CONV;
     const int ch = conv ? N.cin : (N.fc_prev_c > 0 ? N.fc_prev_c : N.cin);
-    sgd_pack_kernel<<<dim3((unsigned)((N.k_f32 + 31) / 32), (unsigned)((N.ldw_f32 + 31) / 32)), 256, 0, s>>>(
-        N.wf, net->train->mom_w[li], g, N.ldw_f32, N.k_f32, N.cout, lr, momentum, weight_decay, first, ch, round_up(ch, 8),
-        N.wb, N.w_ld, conv ? N.k : 1, N.cin, T.cout_ld, T.wt, T.wt_ld);
+    const unsigned kbs = (unsigned)((N.k_f32 + 31) / 32), obs = (unsigned)((N.ldw_f32 + 31) / 32);
+    const char* ord = getenv("SB_SGD_ORDER");                  // "0": 2-D grid, row blocks fastest (r02 first half)
+    const bool rows_first = ord && ord[0] == '0';
+    sgd_pack_kernel<<<rows_first ? dim3(kbs, obs) : dim3(kbs * obs), 256, 0, s>>>(
+        N.wf, net->train->mom_w[li], g, N.ldw_f32, (int)N.k_f32, N.cout, lr, momentum, weight_decay, first, ch, round_up(ch, 8),
+        N.wb, N.w_ld, conv ? N.k : 1, N.cin, T.cout_ld, T.wt, T.wt_ld, rows_first ? 0 : (int)obs);
     return true;
 }
 
