@@ -11,6 +11,7 @@ Because every chunk's offset is known up front, chunks of one file are written c
 integer per file (no score tile crosses NVLink or funnels through rank 0's PCIe link).  The files are
 byte-identical to a single-process run.
 """
+import mmap
 import os
 import threading
 from concurrent.futures import ThreadPoolExecutor
@@ -23,6 +24,7 @@ _CHUNK_BYTES = 32 << 20
 _POOL = None
 _POOL_SIZE = int(os.environ.get("SB_WRITER_THREADS", "0")) or max(2, min(12, (os.cpu_count() or 4) - 2))
 _TLS = threading.local()
+_USE_MMAP = os.environ.get("SB_WRITER_MMAP", "0") == "1"     # chunk text copied through a shared mapping instead of pwrite
 
 
 def writer_pool():
@@ -71,6 +73,15 @@ def _chunk_job(fd, file_off, data, r0, r1, row_off_dev, off0, nbytes, pre_dev, p
             pre_off_dev.data_ptr() + r0 * 8, out_ptr, st["stream"].cuda_stream), "sb_format_e2_rows_prefixed")
         st["host"][:nbytes].copy_(st["dev"][:nbytes], non_blocking=True)
     st["stream"].synchronize()
+    if _USE_MMAP and nbytes:
+        # the file already has its size (ftruncate): copy into a shared mapping of the chunk's pages.  Unlike pwrite,
+        # page-cache copies through a mapping do not take the inode's write lock, so chunks of ONE file land in parallel.
+        lo = file_off - file_off % mmap.ALLOCATIONGRANULARITY
+        with mmap.mmap(fd, file_off + nbytes - lo, offset=lo) as m:
+            dst = np.frombuffer(m, dtype=np.uint8, count=nbytes, offset=file_off - lo)
+            np.copyto(dst, st["host"].numpy()[:nbytes])
+            del dst
+        return nbytes
     view = memoryview(st["host"].numpy())[:nbytes]
     done = 0
     while done < nbytes:
@@ -198,6 +209,8 @@ class TsvFile(object):
             r1 = int(np.searchsorted(off_host, off_host[r0] + _CHUNK_BYTES, side="right")) - 1
             r1 = min(n, max(r1, r0 + 1))
             nbytes = int(off_host[r1] - off_host[r0])
+            if _USE_MMAP and r0 == 0:
+                os.ftruncate(self._fd, self._pos + int(off_host[-1]))
             self._futures.append(pool.submit(_chunk_job, self._fd, self._pos + int(off_host[r0]), t, r0, r1, row_off,
                                              int(off_host[r0]), nbytes, pre_dev, pre_off_dev, ready))
             r0 = r1

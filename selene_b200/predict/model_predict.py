@@ -203,7 +203,11 @@ class AnalyzeSequences(object):
             Genome.update_bases_order(['A', 'C', 'G', 'T'])     # :182-183
         self._write_mem_limit = write_mem_limit
         self.multi_gpu_output = "shards"     # or "gather": see variant_effect_prediction
-        self.vep_block_variants = 32768      # single-process VEP: variants scored per block while the previous is written
+        # single-process VEP: variants scored per block while the previous block's rows are written.  64 x 148 variants =
+        # 18 944 rows = four wave-exact chunks of the DeepSEA-family nets on 148 SMs; measured file to file on one B200
+        # (profiles/r02k_vep_file.md): 32 768 -> 247 k variants/s, 18 944 -> 289 k, 9 472 -> 306 k (the last block's
+        # write is the part nothing overlaps)
+        self.vep_block_variants = 9472
         # the weights are re-normalised for models that do it on every forward (heartenn.py:73-78)
         from ..nets import unwrap_non_strand_specific
         inner = unwrap_non_strand_specific(model)[0]
@@ -737,23 +741,36 @@ class AnalyzeSequences(object):
             files = [(name, TsvFile(path + ".tsv", VARIANTEFFECT_COLS, self.features)) for name, path, _p in output_files()]
             block = max(self.batch_size, (self.vep_block_variants // self.batch_size) * self.batch_size)
 
+            def host_lap(name, t0):
+                now = time.perf_counter()
+                timing[name] = timing.get(name, 0.0) + now - t0
+                return now
+
             def finalize(tbl, arrays, resolve):
+                t0 = time.perf_counter()
                 match, unk = resolve()
+                t0 = host_lap("host_wait_scores_s", t0)
                 warn(tbl, match, unk)
                 pre = tbl.id_prefix(match, unk)
+                t0 = host_lap("host_id_columns_s", t0)
                 for name, fh in files:
                     fh.append(arrays[name], pre[0], pre[1])
+                host_lap("host_append_s", t0)
             pending = None
             for b0 in range(0, n, block):
+                t0 = time.perf_counter()
                 tbl = local.rows(b0, min(n, b0 + block))
                 cur = (tbl,) + enqueue(tbl)
+                host_lap("host_enqueue_s", t0)
                 if pending is not None:
                     finalize(*pending)
                 pending = cur
             if pending is not None:
                 finalize(*pending)
+            t0 = time.perf_counter()
             for _name, fh in files:
                 fh.finish()
+            host_lap("host_wait_writers_s", t0)
             lap("score_and_write_s")
             return None
 
