@@ -103,6 +103,54 @@ def test_device_dropout_statistics():
     assert np.isfinite(l1) and np.isfinite(l2) and l2 < l1 + 1e-3
 
 
+def test_fc_weight_gradients_stored_in_one_pass_equal_accumulated(monkeypatch):
+    """An FC layer's wgrad over a batch of <= 64 rows is one K pass per tile: tc_wgrad_kernel stores it (and the zeros of
+    the padded columns) instead of adding into a block the step zeroed first.  Both modes must give the same values for
+    those blocks up to run-to-run noise, must not depend on what the caller left in the gradient vector (NaN here) and
+    must leave exact zeros in the padded columns."""
+    import torch
+    import sb_models as M
+    from selene_b200 import _lib
+    from selene_b200.train_model import B200Trainer
+    rng = np.random.default_rng(21)
+    n = 6
+    x = np.eye(4, dtype=np.float32)[rng.integers(0, 4, (n, 1000))]
+    y = (rng.random((n, 919)) < 0.1).astype(np.float32)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    lib = _lib.load()
+    got = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SB_WGRAD_OVERWRITE", mode)
+        torch.manual_seed(4)
+        tr = B200Trainer(M.DeepSEA(1000, 919), 1000, lr=0.1, momentum=0.9, weight_decay=1e-4, precision="bf16", seed=2)
+        tr.grads.fill_(float("nan"))
+        tr.forward_backward(xd, yd)
+        g = tr.grads.cpu().numpy().copy()
+        assert np.isfinite(g).all()
+        offs = [int(lib.sb_net_param_offset(tr._h, li)) for li in range(tr.n_layers)] + [g.size]
+        got[mode] = (g, offs, float(tr.loss.cpu()))
+        # two more steps so that the stored gradients also went through the optimiser and the repacked operands
+        tr.sgd_step()
+        tr.forward_backward(xd, yd)
+        got[mode] += (tr.grads.cpu().numpy().copy(),)
+    (g1, offs, l1, h1), (g0, _o, l0, h0) = got["1"], got["0"]
+    assert abs(l1 - l0) <= 2e-6
+    # run-to-run noise: fc1's forward is split-K (fp32 atomics), so logits differ in the last bit between two runs and a
+    # few bf16 roundings of dL/dz flip; gradients agree to a fraction of a percent of the block's largest entry
+    for li in range(len(offs) - 1):
+        a, b = g1[offs[li]:offs[li + 1]], g0[offs[li]:offs[li + 1]]
+        scale = np.abs(b).max() + 1e-30
+        assert np.abs(a - b).max() <= 1e-2 * scale, (li, np.abs(a - b).max() / scale)
+    # padded columns (cout rounded up to 4) of the stored blocks are exact zeros in both modes
+    for li, cout in ((len(offs) - 3, 919), (len(offs) - 2, 919)):     # Linear(50880, 919), Linear(919, 919)
+        ld = (cout + 3) // 4 * 4
+        for g in (g1, g0, h1, h0):
+            blk = g[offs[li]:offs[li + 1]].reshape(-1, ld)
+            assert np.all(blk[:, cout:] == 0), li
+            assert np.abs(blk[:-1, :cout]).max() > 0
+    assert np.abs(h1 - h0).max() <= 2e-2 * np.abs(h0).max()
+
+
 @pytest.mark.parametrize("with_masks", [False, True])
 def test_train_step_tcgen05_close_to_torch(with_masks):
     """bf16 tensor-core training step (fp32 master weights / gradients): gradients within bf16 rounding of
